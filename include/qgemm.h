@@ -1,0 +1,171 @@
+/*
+ * qgemm.h -- C ABI of libqgemm_sm100.so: the B200 (sm_100a) implementation of
+ * the llama.cpp-layout block-quantized GEMM
+ *
+ *     C[T,F] = A[T,K] . B[F,K]^T      A = block_q8_1 activations (T tokens)
+ *                                     B = block_q4_0/q4_1/q5_0/q5_1/q8_0 weights (F rows)
+ *
+ * plus the quantize_q8_1 activation kernel that feeds it.  Plain pointers and
+ * sizes only; every pointer is a DEVICE pointer unless a parameter says "host".
+ * The caller owns every buffer, nothing is allocated behind its back, all work
+ * is enqueued asynchronously on `stream` (a cudaStream_t passed as void*).
+ * Functions return 0 or a negative QGEMM_E_* code; they never exit().
+ * There is no CPU fallback: without an sm_100 device every compute entry
+ * returns QGEMM_E_ARCH / QGEMM_E_CUDA.
+ *
+ * Each entry names the reference interface it replaces (paths relative to the
+ * root of qhy991/llama.cpp-quant-gemm).  The C++ drop-in headers in this
+ * directory (gemm_cuda_naive.cuh, ... , quantize.h, llama_adapter.h) and
+ * kernels/gemm/ (gemm_quant_formats.cuh, ...) keep the reference's function
+ * names and signatures and forward to these symbols; the python package
+ * quant_gemm binds them with ctypes.
+ */
+#ifndef QGEMM_H
+#define QGEMM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QGEMM_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define QGEMM_API __attribute__((visibility("default")))
+#else
+#define QGEMM_API
+#endif
+
+/* ---- error codes ---------------------------------------------------------- */
+#define QGEMM_OK 0
+#define QGEMM_E_BADARG (-1)    /* null pointer, K % 32 != 0, unknown type, negative size   */
+#define QGEMM_E_ALIGN (-2)     /* a pointer breaks the format's minimum alignment           */
+#define QGEMM_E_ARCH (-3)      /* current device is not sm_100                              */
+#define QGEMM_E_CUDA (-4)      /* a CUDA call failed; the CUDA error is left sticky          */
+#define QGEMM_E_WORKSPACE (-5) /* workspace missing or smaller than qgemm_workspace_bytes() */
+
+/* ---- tensor types: numerically equal to ggml_type / the reference's
+ *      enum QuantType (compat/ggml_types.h:199-215) -------------------------- */
+#define QGEMM_TYPE_Q4_0 2
+#define QGEMM_TYPE_Q4_1 3
+#define QGEMM_TYPE_Q5_0 6
+#define QGEMM_TYPE_Q5_1 7
+#define QGEMM_TYPE_Q8_0 8
+#define QGEMM_TYPE_Q8_1 9
+
+/* ---- quantizer flags ---------------------------- */
+#define QGEMM_Q81_ROUND_AWAY 0u  /* roundf(): include/quantize.h:165-193 CPU ref (default)   */
+#define QGEMM_Q81_ROUND_EVEN 1u  /* __float2int_rn(): include/quantize.h:302-337 GPU kernel   */
+#define QGEMM_Q81_S_FROM_QSUM 2u /* s = half(sum(q) * d): tests/framework/test_framework.cuh:195-225 */
+#define QGEMM_Q81_CLAMP127 4u    /* clamp q to [-127,127]: python ext gemm_ops.cu:75-110, framework */
+
+/* ---- GEMM flags ----------------------------------------------------------- */
+#define QGEMM_MS_EXACT 0x1u     /* q4_1/q5_1: + m*s (llama.cpp-true) instead of the
+                                   reference's + m*s/4 (gemm_quant_formats.cuh:148,266)     */
+#define QGEMM_SEQUENTIAL 0x8u   /* one thread per output, blocks accumulated in order
+                                   b = 0..K/32-1 with the reference GPU kernel's exact FMA
+                                   sequence: bit-identical to kernels/gemm/
+                                   gemm_quant_formats.cuh:312-334 built by nvcc.  Slow.      */
+#define QGEMM_PATH_MASK 0xF00u
+#define QGEMM_PATH_AUTO 0x000u
+#define QGEMM_PATH_GENERIC 0x100u /* same kernel as QGEMM_SEQUENTIAL                         */
+#define QGEMM_PATH_GEMV 0x200u    /* decode: bulk-copy-staged weight stream + dp4a            */
+#define QGEMM_PATH_MMA 0x300u     /* skinny: mma.sync m16n8k32 u8/s8, tokens on N             */
+#define QGEMM_PATH_TCGEN05 0x400u /* prefill: tcgen05.mma kind::i8, TMEM accumulators         */
+
+/* ---- housekeeping ----------------------------------------------------------- */
+QGEMM_API int qgemm_version(void);
+QGEMM_API const char *qgemm_strerror(int code);
+QGEMM_API size_t qgemm_block_bytes(int type);     /* get_block_bytes(), compat/ggml_types.h:248-258 */
+/* Kernels launched by this library since load / since the last reset (all threads). */
+QGEMM_API int64_t qgemm_launch_count(void);
+QGEMM_API void qgemm_reset_launch_count(void);
+/* QGEMM_PATH_* actually taken by the calling thread's most recent qgemm_gemm*(). */
+QGEMM_API uint32_t qgemm_last_path(void);
+
+/* ---- quantize / dequantize -------------------------------------------------- */
+/*
+ * x[rows][K] fp32 -> y[rows][K/32] block_q8_1.
+ * Replaces quantize_q8_1_cuda() (include/quantize.h:361-368), the python
+ * extension's quantize_q8_1_cuda() (python/quant_gemm/csrc/gemm_ops.cu:175-202)
+ * and, on the host side of tests, quantize_row_q8_1_ref() (quantize.h:165-193).
+ * Default flags reproduce quantize_row_q8_1_ref() byte for byte.
+ */
+QGEMM_API int qgemm_quantize_q8_1(const float *x, void *y, int64_t rows, int64_t K, uint32_t flags, void *stream);
+
+/*
+ * Weight quantizers (test-data producers): x[rows][K] fp32 -> y[rows][K/32] blocks.
+ * q4_0/q8_0 replace quantize_q4_0_cuda()/quantize_q8_0_cuda()
+ * (include/quantize.h:343-359) and python quantize_q4_0 (gemm_ops.cu:146-173);
+ * q4_1/q5_0/q5_1 follow testing::quantize::to_q4_1/q5_0/q5_1
+ * (tests/framework/test_framework.cuh:256-367).  flags: QGEMM_Q81_ROUND_EVEN
+ * selects __float2int_rn rounding (the include/ GPU kernels); default roundf.
+ */
+QGEMM_API int qgemm_quantize_weight(int wtype, const float *x, void *y, int64_t rows, int64_t K, uint32_t flags,
+                          void *stream);
+
+/*
+ * blocks -> fp32.  Replaces dequantize_row_q4_0/q8_0/q8_1 (include/quantize.h:84-211)
+ * and python dequantize_q4_0 (gemm_ops.cu:204-229).
+ */
+QGEMM_API int qgemm_dequantize(int type, const void *x, float *y, int64_t rows, int64_t K, void *stream);
+
+/* ---- GEMM ------------------------------------------------------------------- */
+/*
+ * C[t*ldc_t + f*ldc_f] = sum_{b<K/32} dot(weight[f][b], act_q8_1[t][b])
+ *
+ *   q4_0: d_w*(d_a*sumi -  8*s_a)      q4_1: d_w*d_a*sumi + m_w*s_a/4   (QGEMM_MS_EXACT: m_w*s_a)
+ *   q5_0: d_w*(d_a*sumi - 16*s_a)      q5_1: d_w*d_a*sumi + m_w*s_a/4
+ *   q8_0: d_w*d_a*sumi
+ *
+ * One entry for both of the reference's conventions:
+ *   include/ style  gemm_w4a8_*(A_q8_1[M], B_w[N], C[M,N], M,N,K)  (include/gemm_cuda_naive.cuh:285-301,
+ *                   gemm_cuda_tiled.cuh:293-301, gemm_cuda_dp4a.cuh:409-444)
+ *                   -> T=M, F=N, ldc_t=N, ldc_f=1
+ *   ggml style      gemm_q*_q8_1(weight[M], act[N], out[M,N], M,N,K) (kernels/gemm/gemm_quant_formats.cuh:343-428,
+ *                   gemm_warp_optimized.cuh:377-1210, gemm_async_copy.cuh:237, gemm_vectorized.cuh:239-280,
+ *                   python gemm_q4_0_q8_1 gemm_ops.cu:231-259)
+ *                   -> F=M, T=N, ldc_t=1, ldc_f=N
+ *
+ * workspace: qgemm_workspace_bytes() bytes of device memory, 256-byte aligned
+ * (may be NULL when that returns 0).  Alignment: act 4 bytes, weight 2 bytes, C 4 bytes
+ * (the reference's requirement); rows that are 16-byte aligned take the fast paths.
+ */
+QGEMM_API size_t qgemm_workspace_bytes(int wtype, int T, int F, int K, uint32_t flags);
+
+QGEMM_API int qgemm_gemm(int wtype, const void *act_q8_1, const void *weight, float *C, int T, int F, int K,
+               int64_t ldc_t, int64_t ldc_f, uint32_t flags, void *workspace, size_t workspace_bytes,
+               void *stream);
+
+/*
+ * Same, with fp32 activations act_f32[T][K]: quantize_q8_1 (flags' QGEMM_Q81_*
+ * bits, shifted left by 16) runs first into the workspace, then the GEMM.
+ * Successor of gemm_q4_0_fp16_fused() (kernels/gemm/gemm_fused.cuh:311-338) and of
+ * the designed-but-unwritten gemm_w4a8() of docs/analysis/W4A8_DATAFLOW_ANALYSIS.md:93-160.
+ */
+QGEMM_API int qgemm_gemm_f32act(int wtype, const float *act_f32, const void *weight, float *C, int T, int F, int K,
+                      int64_t ldc_t, int64_t ldc_f, uint32_t flags, void *workspace,
+                      size_t workspace_bytes, void *stream);
+
+/*
+ * Test hook for the bit-exactness contract: sumi[(t*F + f)*(K/32) + b] =
+ * the int32 block dot product exactly as the selected path computes it
+ * (QGEMM_PATH_* in flags picks whose integers are dumped).
+ */
+QGEMM_API int qgemm_sumi(int wtype, const void *act_q8_1, const void *weight, int32_t *sumi, int T, int F, int K,
+               uint32_t flags, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- multi-GPU sharding helper (host arithmetic only) ------------------------ */
+/*
+ * Weight rows [0,F) split into `world` contiguous ranges whose sizes are
+ * multiples of `align` (except the last): rank's range is [*f0, *f1).
+ * New functionality; the reference has no multi-GPU code.
+ */
+QGEMM_API int qgemm_shard_range(int F, int world, int rank, int align, int *f0, int *f1);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QGEMM_H */

@@ -1,0 +1,253 @@
+// qgemm_abi.cu -- the extern "C" surface of libqgemm_sm100.so (include/qgemm.h):
+// argument validation, device check, path selection, launch bookkeeping.
+#include <atomic>
+#include <mutex>
+
+#include "qgemm_common.cuh"
+
+namespace qgemm {
+
+// kernels (defined in the other translation units)
+cudaError_t launch_quantize_q8_1(const float*, void*, int64_t nblocks, uint32_t flags, cudaStream_t);
+cudaError_t launch_quantize_weight(int wtype, const float*, void*, int64_t nblocks, uint32_t flags, cudaStream_t);
+cudaError_t launch_dequantize(int type, const void*, float*, int64_t nblocks, cudaStream_t);
+cudaError_t launch_gemm_sequential(int wtype, const void* act, const void* wgt, float* C, int T, int F, int K,
+                                   int64_t ldc_t, int64_t ldc_f, uint32_t flags, cudaStream_t);
+cudaError_t launch_sumi_generic(int wtype, const void* act, const void* wgt, int32_t* out, int T, int F, int K,
+                                cudaStream_t);
+bool gemv_supported(int wtype, const void* act, const void* wgt, int F, int K);
+cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
+                        int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t);
+bool mmq_supported(int wtype, const void* act, const void* wgt, int T, int F, int K);
+size_t mmq_workspace_bytes(int wtype, int T, int F, int K);
+cudaError_t launch_mmq(int wtype, const void* act, const void* wgt, float* C, int32_t* sumi_out, int T, int F, int K,
+                       int64_t ldc_t, int64_t ldc_f, uint32_t flags, void* ws, size_t ws_bytes, int num_sms,
+                       cudaStream_t);
+
+static std::atomic<int64_t> g_launches{0};
+void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static thread_local uint32_t t_last_path = 0;
+
+struct DeviceInfo {
+    int cc_major = -1, cc_minor = -1, sms = 0;
+    bool ok = false;
+};
+static DeviceInfo g_dev[64];
+static std::mutex g_dev_mu;
+
+// 0 on success; fills *info for the current device.
+static int device_check(DeviceInfo* info) {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return QGEMM_E_CUDA;
+    {
+        std::lock_guard<std::mutex> lk(g_dev_mu);
+        DeviceInfo& d = g_dev[dev];
+        if (d.cc_major < 0) {
+            if (cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+                cudaDeviceGetAttribute(&d.cc_minor, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess ||
+                cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+                d.cc_major = -1;
+                return QGEMM_E_CUDA;
+            }
+            d.ok = (d.cc_major == 10);  // built for sm_100a only: no PTX fallback, no other arch
+        }
+        *info = d;
+    }
+    return info->ok ? QGEMM_OK : QGEMM_E_ARCH;
+}
+
+static bool is_weight_type(int t) {
+    return t == QGEMM_TYPE_Q4_0 || t == QGEMM_TYPE_Q4_1 || t == QGEMM_TYPE_Q5_0 || t == QGEMM_TYPE_Q5_1 ||
+           t == QGEMM_TYPE_Q8_0;
+}
+static bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int check_gemm_args(int wtype, const void* act, const void* wgt, const void* out, int T, int F, int K) {
+    if (!is_weight_type(wtype) || T < 0 || F < 0 || K < 0 || (K % kQK) != 0) return QGEMM_E_BADARG;
+    if (T == 0 || F == 0) return QGEMM_OK;
+    if (!act || !wgt || !out) return QGEMM_E_BADARG;
+    if (!aligned(act, 4) || !aligned(wgt, 2) || !aligned(out, 4)) return QGEMM_E_ALIGN;
+    return QGEMM_OK;
+}
+
+__global__ void fill_zero_strided(float* C, int T, int F, int64_t ldc_t, int64_t ldc_f) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)T * F) return;
+    C[(i / F) * ldc_t + (i % F) * ldc_f] = 0.0f;
+}
+
+static int run_gemm(int wtype, const void* act, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
+                    int64_t ldc_f, uint32_t flags, void* ws, size_t ws_bytes, cudaStream_t st,
+                    const DeviceInfo& dev) {
+    if (K == 0) {  // empty contraction: the reference's loop leaves sum = 0.0f
+        const int64_t n = (int64_t)T * F;
+        fill_zero_strided<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(C, T, F, ldc_t, ldc_f);
+        note_launch();
+        t_last_path = QGEMM_PATH_GENERIC;
+        return cudaGetLastError() == cudaSuccess ? QGEMM_OK : QGEMM_E_CUDA;
+    }
+    uint32_t path = flags & QGEMM_PATH_MASK;
+    if (flags & QGEMM_SEQUENTIAL) path = QGEMM_PATH_GENERIC;
+    if (path == QGEMM_PATH_AUTO) {
+        if (T >= 64 && mmq_supported(wtype, act, wgt, T, F, K) && ws && ws_bytes >= mmq_workspace_bytes(wtype, T, F, K))
+            path = QGEMM_PATH_TCGEN05;
+        else if (gemv_supported(wtype, act, wgt, F, K))
+            path = QGEMM_PATH_GEMV;
+        else
+            path = QGEMM_PATH_GENERIC;
+    }
+    cudaError_t e;
+    switch (path) {
+    case QGEMM_PATH_GEMV:
+        if (!gemv_supported(wtype, act, wgt, F, K)) return QGEMM_E_ALIGN;
+        e = launch_gemv(wtype, act, wgt, C, T, F, K, ldc_t, ldc_f, flags, dev.sms, st);
+        break;
+    case QGEMM_PATH_TCGEN05:
+    case QGEMM_PATH_MMA:
+        if (!mmq_supported(wtype, act, wgt, T, F, K)) return QGEMM_E_ALIGN;
+        if (!ws || ws_bytes < mmq_workspace_bytes(wtype, T, F, K)) return QGEMM_E_WORKSPACE;
+        e = launch_mmq(wtype, act, wgt, C, nullptr, T, F, K, ldc_t, ldc_f, flags, ws, ws_bytes, dev.sms, st);
+        path = QGEMM_PATH_TCGEN05;
+        break;
+    case QGEMM_PATH_GENERIC:
+        e = launch_gemm_sequential(wtype, act, wgt, C, T, F, K, ldc_t, ldc_f, flags, st);
+        break;
+    default:
+        return QGEMM_E_BADARG;
+    }
+    t_last_path = path;
+    return e == cudaSuccess ? QGEMM_OK : QGEMM_E_CUDA;
+}
+
+}  // namespace qgemm
+
+using namespace qgemm;
+
+extern "C" {
+
+int qgemm_version(void) { return QGEMM_VERSION; }
+
+const char* qgemm_strerror(int code) {
+    switch (code) {
+    case QGEMM_OK: return "ok";
+    case QGEMM_E_BADARG: return "bad argument (null pointer, K % 32 != 0, unknown type or negative size)";
+    case QGEMM_E_ALIGN: return "pointer alignment below the format's minimum, or the forced path cannot take this layout";
+    case QGEMM_E_ARCH: return "current CUDA device is not sm_100 (B200); this library has no other code path";
+    case QGEMM_E_CUDA: return "a CUDA runtime call failed (see cudaGetLastError)";
+    case QGEMM_E_WORKSPACE: return "workspace missing or smaller than qgemm_workspace_bytes()";
+    default: return "unknown qgemm error code";
+    }
+}
+
+size_t qgemm_block_bytes(int type) { return (size_t)block_bytes(type); }
+int64_t qgemm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+void qgemm_reset_launch_count(void) { g_launches.store(0, std::memory_order_relaxed); }
+uint32_t qgemm_last_path(void) { return t_last_path; }
+
+int qgemm_quantize_q8_1(const float* x, void* y, int64_t rows, int64_t K, uint32_t flags, void* stream) {
+    if (rows < 0 || K < 0 || (K % kQK) != 0) return QGEMM_E_BADARG;
+    if (rows == 0 || K == 0) return QGEMM_OK;
+    if (!x || !y) return QGEMM_E_BADARG;
+    if (!aligned(x, 4) || !aligned(y, 4)) return QGEMM_E_ALIGN;
+    DeviceInfo dev;
+    if (int rc = device_check(&dev)) return rc;
+    return launch_quantize_q8_1(x, y, rows * (K / kQK), flags, (cudaStream_t)stream) == cudaSuccess ? QGEMM_OK
+                                                                                                   : QGEMM_E_CUDA;
+}
+
+int qgemm_quantize_weight(int wtype, const float* x, void* y, int64_t rows, int64_t K, uint32_t flags, void* stream) {
+    if (!is_weight_type(wtype) || rows < 0 || K < 0 || (K % kQK) != 0) return QGEMM_E_BADARG;
+    if (rows == 0 || K == 0) return QGEMM_OK;
+    if (!x || !y) return QGEMM_E_BADARG;
+    if (!aligned(x, 4) || !aligned(y, 2)) return QGEMM_E_ALIGN;
+    DeviceInfo dev;
+    if (int rc = device_check(&dev)) return rc;
+    return launch_quantize_weight(wtype, x, y, rows * (K / kQK), flags, (cudaStream_t)stream) == cudaSuccess
+               ? QGEMM_OK
+               : QGEMM_E_CUDA;
+}
+
+int qgemm_dequantize(int type, const void* x, float* y, int64_t rows, int64_t K, void* stream) {
+    if (!(is_weight_type(type) || type == QGEMM_TYPE_Q8_1) || rows < 0 || K < 0 || (K % kQK) != 0)
+        return QGEMM_E_BADARG;
+    if (rows == 0 || K == 0) return QGEMM_OK;
+    if (!x || !y) return QGEMM_E_BADARG;
+    if (!aligned(x, 2) || !aligned(y, 16)) return QGEMM_E_ALIGN;
+    DeviceInfo dev;
+    if (int rc = device_check(&dev)) return rc;
+    return launch_dequantize(type, x, y, rows * (K / kQK), (cudaStream_t)stream) == cudaSuccess ? QGEMM_OK
+                                                                                              : QGEMM_E_CUDA;
+}
+
+size_t qgemm_workspace_bytes(int wtype, int T, int F, int K, uint32_t flags) {
+    (void)flags;
+    if (!is_weight_type(wtype) || T <= 0 || F <= 0 || K <= 0 || (K % kQK) != 0) return 0;
+    // [ q8_1 copy of A for qgemm_gemm_f32act | path scratch ]
+    const size_t a_q = align_up((size_t)T * (K / kQK) * kQ81Bytes, 256);
+    return a_q + align_up(mmq_workspace_bytes(wtype, T, F, K), 256);
+}
+
+int qgemm_gemm(int wtype, const void* act_q8_1, const void* weight, float* C, int T, int F, int K, int64_t ldc_t,
+               int64_t ldc_f, uint32_t flags, void* workspace, size_t workspace_bytes, void* stream) {
+    if (int rc = check_gemm_args(wtype, act_q8_1, weight, C, T, F, K)) return rc;
+    if (T == 0 || F == 0) return QGEMM_OK;
+    DeviceInfo dev;
+    if (int rc = device_check(&dev)) return rc;
+    return run_gemm(wtype, act_q8_1, weight, C, T, F, K, ldc_t, ldc_f, flags, workspace, workspace_bytes,
+                    (cudaStream_t)stream, dev);
+}
+
+int qgemm_gemm_f32act(int wtype, const float* act_f32, const void* weight, float* C, int T, int F, int K,
+                      int64_t ldc_t, int64_t ldc_f, uint32_t flags, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+    if (int rc = check_gemm_args(wtype, act_f32, weight, C, T, F, K)) return rc;
+    if (T == 0 || F == 0) return QGEMM_OK;
+    DeviceInfo dev;
+    if (int rc = device_check(&dev)) return rc;
+    const size_t a_q = align_up((size_t)T * (K / kQK) * kQ81Bytes, 256);
+    if (K > 0 && (!workspace || workspace_bytes < a_q || !aligned(workspace, 16))) return QGEMM_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (K > 0 &&
+        launch_quantize_q8_1(act_f32, workspace, (int64_t)T * (K / kQK), (flags >> 16) & 0xffu, st) != cudaSuccess)
+        return QGEMM_E_CUDA;
+    return run_gemm(wtype, workspace, weight, C, T, F, K, ldc_t, ldc_f, flags & 0xffffu, (char*)workspace + a_q,
+                    workspace_bytes - a_q, st, dev);
+}
+
+int qgemm_sumi(int wtype, const void* act_q8_1, const void* weight, int32_t* sumi, int T, int F, int K, uint32_t flags,
+               void* workspace, size_t workspace_bytes, void* stream) {
+    if (int rc = check_gemm_args(wtype, act_q8_1, weight, sumi, T, F, K)) return rc;
+    if (T == 0 || F == 0 || K == 0) return QGEMM_OK;
+    DeviceInfo dev;
+    if (int rc = device_check(&dev)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t path = flags & QGEMM_PATH_MASK;
+    cudaError_t e;
+    if (path == QGEMM_PATH_TCGEN05 || path == QGEMM_PATH_MMA) {
+        if (!mmq_supported(wtype, act_q8_1, weight, T, F, K)) return QGEMM_E_ALIGN;
+        if (!workspace || workspace_bytes < mmq_workspace_bytes(wtype, T, F, K)) return QGEMM_E_WORKSPACE;
+        e = launch_mmq(wtype, act_q8_1, weight, nullptr, sumi, T, F, K, 0, 0, flags, workspace, workspace_bytes,
+                       dev.sms, st);
+    } else {
+        e = launch_sumi_generic(wtype, act_q8_1, weight, sumi, T, F, K, st);
+    }
+    return e == cudaSuccess ? QGEMM_OK : QGEMM_E_CUDA;
+}
+
+int qgemm_shard_range(int F, int world, int rank, int align, int* f0, int* f1) {
+    if (F < 0 || world < 1 || rank < 0 || rank >= world || align < 1 || !f0 || !f1) return QGEMM_E_BADARG;
+    const int64_t units = ((int64_t)F + align - 1) / align;  // align-sized row groups
+    const int64_t base = units / world, rem = units % world;
+    const int64_t u0 = rank * base + (rank < rem ? rank : rem);
+    const int64_t u1 = u0 + base + (rank < rem ? 1 : 0);
+    int64_t a = u0 * align, b = u1 * align;
+    if (a > F) a = F;
+    if (b > F) b = F;
+    *f0 = (int)a;
+    *f1 = (int)b;
+    return QGEMM_OK;
+}
+
+}  // extern "C"

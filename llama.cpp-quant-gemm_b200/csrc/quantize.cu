@@ -1,0 +1,263 @@
+// quantize.cu -- fp32 -> block_q8_1 (the activation quantizer on the hot path),
+// the weight quantizers used to make test data, and the dequantizers.
+//
+// Reference semantics: include/quantize.h:165-193 (CPU), :302-337 (GPU),
+// tests/framework/test_framework.cuh:195-225, python ext gemm_ops.cu:75-110.
+#include "qgemm_common.cuh"
+
+namespace qgemm {
+
+// roundf() for |v| < 2^23 without the libdevice slow path: truncate, then add
+// +-1 when the (exactly representable) remainder is at least one half.
+__device__ __forceinline__ int round_half_away(float v) {
+    const float t = truncf(v);
+    const float r = v - t;  // exact
+    int q = __float2int_rz(t);
+    if (fabsf(r) >= 0.5f) q += (v < 0.0f) ? -1 : 1;
+    return q;
+}
+
+// ---------------------------------------------------------------------------
+// quantize_q8_1: one warp owns 32 consecutive blocks (1024 floats).
+//   phase 1: 8 coalesced float4 loads per lane -> smem tile [32][33]
+//   phase 2: lane b walks row b IN ORDER (j = 0..31), so `sum` is the same
+//            sequential fp32 sum the reference computes (s must be bit-equal)
+//   phase 3: 36-byte blocks staged in smem, written back as coalesced words
+// HBM-bound: 4 B read + 1.125 B written per element.
+// ---------------------------------------------------------------------------
+constexpr int kQWarps = 8;
+
+template <bool kAlignedX>
+__global__ void __launch_bounds__(kQWarps * 32)
+quantize_q8_1_kernel(const float* __restrict__ x, uint32_t* __restrict__ y, int64_t nblocks, uint32_t flags) {
+    __shared__ float tile[kQWarps][32][33];
+    __shared__ uint32_t stage[kQWarps][32 * 9];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t b0 = ((int64_t)blockIdx.x * kQWarps + warp) * 32;
+    if (b0 >= nblocks) return;
+    const int nvalid = (int)min((int64_t)32, nblocks - b0);
+    const float* xb = x + b0 * 32;
+    float(*tw)[33] = tile[warp];
+
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+        const int v4 = it * 32 + lane;   // float4 index inside the 1024-float group
+        const int blk = v4 >> 3, j = (v4 & 7) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (blk < nvalid) {
+            if constexpr (kAlignedX) {
+                v = __ldcs(reinterpret_cast<const float4*>(xb) + v4);
+            } else {
+                v.x = xb[v4 * 4 + 0]; v.y = xb[v4 * 4 + 1]; v.z = xb[v4 * 4 + 2]; v.w = xb[v4 * 4 + 3];
+            }
+        }
+        tw[blk][j + 0] = v.x; tw[blk][j + 1] = v.y; tw[blk][j + 2] = v.z; tw[blk][j + 3] = v.w;
+    }
+    __syncwarp();
+
+    float amax = 0.0f, sum = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        const float v = tw[lane][j];
+        amax = fmaxf(amax, fabsf(v));
+        sum = __fadd_rn(sum, v);
+    }
+    const float d = __fdiv_rn(amax, 127.0f);
+    const float id = (d > 0.0f) ? __fdiv_rn(1.0f, d) : 0.0f;
+    const bool even = flags & QGEMM_Q81_ROUND_EVEN;
+    const int lo = (flags & QGEMM_Q81_CLAMP127) ? -127 : -128;
+
+    uint32_t* sw = stage[warp] + lane * 9;
+    int sum_q = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        uint32_t packed = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const float v = __fmul_rn(tw[lane][w * 4 + c], id);
+            int q = even ? __float2int_rn(v) : round_half_away(v);
+            q = max(lo, min(127, q));
+            sum_q += q;
+            packed |= (uint32_t)(q & 0xff) << (8 * c);
+        }
+        sw[1 + w] = packed;
+    }
+    const float s = (flags & QGEMM_Q81_S_FROM_QSUM) ? __fmul_rn(__int2float_rn(sum_q), d) : sum;
+    sw[0] = (uint32_t)__half_as_ushort(__float2half_rn(d)) | ((uint32_t)__half_as_ushort(__float2half_rn(s)) << 16);
+    __syncwarp();
+
+    uint32_t* yb = y + b0 * 9;
+    const uint32_t* st = stage[warp];
+    const int nwords = nvalid * 9;
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        const int wi = i * 32 + lane;
+        if (wi < nwords) __stcs(yb + wi, st[wi]);
+    }
+}
+
+cudaError_t launch_quantize_q8_1(const float* x, void* y, int64_t nblocks, uint32_t flags, cudaStream_t st) {
+    if (nblocks == 0) return cudaSuccess;
+    const int64_t per_cta = (int64_t)kQWarps * 32;
+    const unsigned grid = (unsigned)((nblocks + per_cta - 1) / per_cta);
+    if ((reinterpret_cast<uintptr_t>(x) & 15) == 0)
+        quantize_q8_1_kernel<true><<<grid, kQWarps * 32, 0, st>>>(x, (uint32_t*)y, nblocks, flags);
+    else
+        quantize_q8_1_kernel<false><<<grid, kQWarps * 32, 0, st>>>(x, (uint32_t*)y, nblocks, flags);
+    note_launch();
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Weight quantizers: test-data producers, one thread per block (not hot).
+//   q4_0: include/quantize.h:35-70 / test_framework.cuh:162-192
+//   q8_0: include/quantize.h:111-135 (clamp -128..127)
+//   q4_1/q5_0/q5_1: test_framework.cuh:256-367
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void st_u16(uint8_t* p, uint32_t v) { *reinterpret_cast<uint16_t*>(p) = (uint16_t)v; }
+__device__ __forceinline__ uint32_t f2h_bits(float f) { return __half_as_ushort(__float2half_rn(f)); }
+
+template <int WT>
+__global__ void quantize_weight_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, int64_t nblocks,
+                                       uint32_t flags) {
+    using F = Fmt<WT>;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nblocks) return;
+    const float* src = x + i * 32;
+    uint8_t* dst = y + i * F::bytes;
+    const bool even = flags & QGEMM_Q81_ROUND_EVEN;
+    auto rnd = [&](float v) { return even ? __float2int_rn(v) : round_half_away(v); };
+
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) v[j] = src[j];
+
+    if constexpr (WT == QGEMM_TYPE_Q8_0) {
+        float amax = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j++) amax = fmaxf(amax, fabsf(v[j]));
+        const float d = __fdiv_rn(amax, 127.0f);
+        const float id = (d > 0.f) ? __fdiv_rn(1.0f, d) : 0.f;
+        st_u16(dst, f2h_bits(d));
+#pragma unroll
+        for (int j = 0; j < 32; j++) dst[2 + j] = (uint8_t)(int8_t)max(-128, min(127, rnd(__fmul_rn(v[j], id))));
+    } else if constexpr (F::m < 0) {  // symmetric q4_0 / q5_0
+        constexpr int half_range = (F::bits == 4) ? 8 : 16;
+        constexpr float div = (F::bits == 4) ? 7.0f : 15.0f;
+        float amax = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j++) amax = fmaxf(amax, fabsf(v[j]));
+        const float d = __fdiv_rn(amax, div);
+        const float id = (d > 0.f) ? __fdiv_rn(1.0f, d) : 0.f;
+        st_u16(dst, f2h_bits(d));
+        uint32_t qh = 0;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            int q0 = rnd(__fmul_rn(v[j], id)) + half_range;
+            int q1 = rnd(__fmul_rn(v[j + 16], id)) + half_range;
+            q0 = max(0, min(2 * half_range - 1, q0));
+            q1 = max(0, min(2 * half_range - 1, q1));
+            dst[F::qs + j] = (uint8_t)(((q1 & 0xf) << 4) | (q0 & 0xf));
+            qh |= (uint32_t)((q0 >> 4) & 1) << j;
+            qh |= (uint32_t)((q1 >> 4) & 1) << (j + 16);
+        }
+        if constexpr (F::bits == 5) { st_u16(dst + F::qh, qh & 0xffff); st_u16(dst + F::qh + 2, qh >> 16); }
+    } else {  // asymmetric q4_1 / q5_1
+        constexpr int qmax = (F::bits == 4) ? 15 : 31;
+        float mn = v[0], mx = v[0];
+#pragma unroll
+        for (int j = 1; j < 32; j++) { mn = fminf(mn, v[j]); mx = fmaxf(mx, v[j]); }
+        const float d = __fdiv_rn(__fsub_rn(mx, mn), (float)qmax);
+        const float id = (d > 0.f) ? __fdiv_rn(1.0f, d) : 0.f;
+        st_u16(dst, f2h_bits(d));
+        st_u16(dst + F::m, f2h_bits(mn));
+        uint32_t qh = 0;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            int q0 = rnd(__fmul_rn(__fsub_rn(v[j], mn), id));
+            int q1 = rnd(__fmul_rn(__fsub_rn(v[j + 16], mn), id));
+            q0 = max(0, min(qmax, q0));
+            q1 = max(0, min(qmax, q1));
+            dst[F::qs + j] = (uint8_t)(((q1 & 0xf) << 4) | (q0 & 0xf));
+            qh |= (uint32_t)((q0 >> 4) & 1) << j;
+            qh |= (uint32_t)((q1 >> 4) & 1) << (j + 16);
+        }
+        if constexpr (F::bits == 5) { st_u16(dst + F::qh, qh & 0xffff); st_u16(dst + F::qh + 2, qh >> 16); }
+    }
+}
+
+cudaError_t launch_quantize_weight(int wtype, const float* x, void* y, int64_t nblocks, uint32_t flags,
+                                   cudaStream_t st) {
+    if (nblocks == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((nblocks + 127) / 128);
+    uint8_t* yb = (uint8_t*)y;
+    switch (wtype) {
+    case QGEMM_TYPE_Q4_0: quantize_weight_kernel<QGEMM_TYPE_Q4_0><<<grid, 128, 0, st>>>(x, yb, nblocks, flags); break;
+    case QGEMM_TYPE_Q4_1: quantize_weight_kernel<QGEMM_TYPE_Q4_1><<<grid, 128, 0, st>>>(x, yb, nblocks, flags); break;
+    case QGEMM_TYPE_Q5_0: quantize_weight_kernel<QGEMM_TYPE_Q5_0><<<grid, 128, 0, st>>>(x, yb, nblocks, flags); break;
+    case QGEMM_TYPE_Q5_1: quantize_weight_kernel<QGEMM_TYPE_Q5_1><<<grid, 128, 0, st>>>(x, yb, nblocks, flags); break;
+    case QGEMM_TYPE_Q8_0: quantize_weight_kernel<QGEMM_TYPE_Q8_0><<<grid, 128, 0, st>>>(x, yb, nblocks, flags); break;
+    default: return cudaErrorInvalidValue;
+    }
+    note_launch();
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Dequantize: 8 threads per block, 4 consecutive elements each, so a warp
+// writes 512 contiguous bytes.  include/quantize.h:84-102,140-153,198-211.
+// ---------------------------------------------------------------------------
+template <int TYPE>
+__global__ void dequantize_kernel(const uint8_t* __restrict__ x, float* __restrict__ y, int64_t nblocks) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t b = gid >> 3;
+    const int part = (int)(gid & 7);  // elements 4*part .. 4*part+3
+    if (b >= nblocks) return;
+    float out[4];
+    if constexpr (TYPE == QGEMM_TYPE_Q8_1 || TYPE == QGEMM_TYPE_Q8_0) {
+        constexpr int bytes = (TYPE == QGEMM_TYPE_Q8_1) ? 36 : 34;
+        constexpr int qs = (TYPE == QGEMM_TYPE_Q8_1) ? 4 : 2;
+        const uint8_t* blk = x + b * bytes;
+        const float d = ld_half(blk);
+#pragma unroll
+        for (int c = 0; c < 4; c++) out[c] = __fmul_rn((float)(int8_t)blk[qs + part * 4 + c], d);
+    } else {
+        using F = Fmt<TYPE>;
+        const uint8_t* blk = x + b * F::bytes;
+        const float d = ld_half(blk);
+        float m = 0.f;
+        if constexpr (F::m >= 0) m = ld_half(blk + F::m);
+        uint32_t qh = 0;
+        if constexpr (F::bits == 5) qh = ld_u32_a2(blk + F::qh);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int e = part * 4 + c;
+            const int byte = blk[F::qs + (e & 15)];
+            int q = (e < 16) ? (byte & 0xf) : (byte >> 4);
+            if constexpr (F::bits == 5) q |= ((qh >> e) & 1) << 4;
+            if constexpr (F::m >= 0) out[c] = __fadd_rn(__fmul_rn((float)q, d), m);
+            else out[c] = __fmul_rn((float)(q - (F::bits == 4 ? 8 : 16)), d);
+        }
+    }
+    reinterpret_cast<float4*>(y)[gid] = make_float4(out[0], out[1], out[2], out[3]);
+}
+
+cudaError_t launch_dequantize(int type, const void* x, float* y, int64_t nblocks, cudaStream_t st) {
+    if (nblocks == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((nblocks * 8 + 255) / 256);
+    const uint8_t* xb = (const uint8_t*)x;
+    switch (type) {
+    case QGEMM_TYPE_Q4_0: dequantize_kernel<QGEMM_TYPE_Q4_0><<<grid, 256, 0, st>>>(xb, y, nblocks); break;
+    case QGEMM_TYPE_Q4_1: dequantize_kernel<QGEMM_TYPE_Q4_1><<<grid, 256, 0, st>>>(xb, y, nblocks); break;
+    case QGEMM_TYPE_Q5_0: dequantize_kernel<QGEMM_TYPE_Q5_0><<<grid, 256, 0, st>>>(xb, y, nblocks); break;
+    case QGEMM_TYPE_Q5_1: dequantize_kernel<QGEMM_TYPE_Q5_1><<<grid, 256, 0, st>>>(xb, y, nblocks); break;
+    case QGEMM_TYPE_Q8_0: dequantize_kernel<QGEMM_TYPE_Q8_0><<<grid, 256, 0, st>>>(xb, y, nblocks); break;
+    case QGEMM_TYPE_Q8_1: dequantize_kernel<QGEMM_TYPE_Q8_1><<<grid, 256, 0, st>>>(xb, y, nblocks); break;
+    default: return cudaErrorInvalidValue;
+    }
+    note_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace qgemm

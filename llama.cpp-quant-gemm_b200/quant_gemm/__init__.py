@@ -1,0 +1,256 @@
+"""quant_gemm -- host-side mirror of the reference's PyTorch extension.
+
+Same names, argument meaning, shapes, dtypes and error behaviour as
+python/quant_gemm/__init__.py:33-89 + csrc/bindings.cpp:19-91 of
+qhy991/llama.cpp-quant-gemm, reaching the sm_100a kernels through the C ABI of
+libqgemm_sm100.so (include/qgemm.h) with ctypes.  torch is plumbing only:
+device memory, the current stream, and torch.distributed for the sharded path.
+
+    import quant_gemm
+    wq = quant_gemm.quantize_q4_0(weight)            # [M, K] f32 -> [M, K/32, 18] u8
+    aq = quant_gemm.quantize_q8_1(activation)        # [N, K] f32 -> [N, K/32, 36] u8
+    out = quant_gemm.gemm_q4_0_q8_1(wq, aq, M, N, K) # [M, N] f32   (M weight rows, N tokens)
+
+Differences from the reference, all supersets: the launch goes on torch's
+current stream (the reference uses stream 0, gemm_ops.cu:195,250); q4_1/q5_0/
+q5_1/q8_0 entry points exist; gemm_w4a8() fuses quantize_q8_1 of fp32
+activations with the GEMM.  There is no CPU path: without the CUDA library or
+a B200 the calls raise.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import (  # noqa: F401  (re-exported constants)
+    GEMM_MS_EXACT, GEMM_SEQUENTIAL, PATH_AUTO, PATH_GEMV, PATH_GENERIC, PATH_MMA, PATH_TCGEN05,
+    Q81_CLAMP127, Q81_ROUND_AWAY, Q81_ROUND_EVEN, Q81_S_FROM_QSUM,
+    TYPE_Q4_0, TYPE_Q4_1, TYPE_Q5_0, TYPE_Q5_1, TYPE_Q8_0, TYPE_Q8_1,
+)
+
+__version__ = "0.1.0"
+
+# Block sizes (python/quant_gemm/__init__.py:26-30)
+QK4_0 = 32
+QK8_1 = 32
+BLOCK_Q4_0_BYTES = 18
+BLOCK_Q8_1_BYTES = 36
+BLOCK_BYTES = {TYPE_Q4_0: 18, TYPE_Q4_1: 20, TYPE_Q5_0: 22, TYPE_Q5_1: 24, TYPE_Q8_0: 34, TYPE_Q8_1: 36}
+
+_workspaces: dict[tuple[int, int], torch.Tensor] = {}
+
+
+def _check(cond: bool, msg: str) -> None:
+    # TORCH_CHECK -> RuntimeError (bindings.cpp:20-67)
+    if not cond:
+        raise RuntimeError(msg)
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor | None:
+    """Per-(device, stream) scratch owned by the python shim (the library itself never allocates)."""
+    if nbytes == 0:
+        return None
+    key = (device.index or 0, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _quantize(x: torch.Tensor, qtype: int, flags: int) -> torch.Tensor:
+    _check(x.is_cuda, "Input must be a CUDA tensor")
+    _check(x.dtype == torch.float32, "Input must be float32")
+    _check(x.dim() >= 1, "Input must have at least 1 dimension")
+    K = x.shape[-1]
+    _check(K % 32 == 0, f"Last dimension must be divisible by 32, got {K}")
+    x = x.contiguous()
+    rows = x.numel() // K if K else 0
+    out = torch.empty(*x.shape[:-1], K // 32, BLOCK_BYTES[qtype], dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        if qtype == TYPE_Q8_1:
+            rc = _lib.lib().qgemm_quantize_q8_1(x.data_ptr(), out.data_ptr(), rows, K, flags, _stream(x))
+        else:
+            rc = _lib.lib().qgemm_quantize_weight(qtype, x.data_ptr(), out.data_ptr(), rows, K, flags, _stream(x))
+    _lib.raise_on_error(rc, "quantize")
+    return out
+
+
+def quantize_q4_0(x: torch.Tensor, flags: int = Q81_ROUND_AWAY) -> torch.Tensor:
+    """FP32 [..., K] -> Q4_0 bytes [..., K//32, 18] (python/quant_gemm/__init__.py:33-43)."""
+    return _quantize(x, TYPE_Q4_0, flags)
+
+
+def quantize_q8_1(x: torch.Tensor, flags: int = Q81_ROUND_AWAY) -> torch.Tensor:
+    """FP32 [..., K] -> Q8_1 bytes [..., K//32, 36] (python/quant_gemm/__init__.py:46-56).
+
+    Default flags reproduce include/quantize.h:165-193 byte for byte; pass
+    Q81_CLAMP127 for the reference python extension's clamp (gemm_ops.cu:106-108).
+    """
+    return _quantize(x, TYPE_Q8_1, flags)
+
+
+def quantize_q4_1(x, flags: int = 0):
+    return _quantize(x, TYPE_Q4_1, flags)
+
+
+def quantize_q5_0(x, flags: int = 0):
+    return _quantize(x, TYPE_Q5_0, flags)
+
+
+def quantize_q5_1(x, flags: int = 0):
+    return _quantize(x, TYPE_Q5_1, flags)
+
+
+def quantize_q8_0(x, flags: int = 0):
+    return _quantize(x, TYPE_Q8_0, flags)
+
+
+def dequantize(x_q: torch.Tensor, K: int, qtype: int) -> torch.Tensor:
+    _check(x_q.is_cuda, "Input must be a CUDA tensor")
+    _check(x_q.dtype == torch.uint8, "Input must be uint8")
+    _check(K % 32 == 0, f"K must be divisible by 32, got {K}")
+    x_q = x_q.contiguous()
+    bs = BLOCK_BYTES[qtype]
+    nblocks = x_q.numel() // bs
+    _check(nblocks * bs == x_q.numel() and (K == 0 or nblocks % (K // 32) == 0), "Input shape mismatch")
+    lead = x_q.shape[:-2]
+    out = torch.empty(*lead, K, dtype=torch.float32, device=x_q.device)
+    rows = nblocks // (K // 32) if K else 0
+    with torch.cuda.device(x_q.device):
+        rc = _lib.lib().qgemm_dequantize(qtype, x_q.data_ptr(), out.data_ptr(), rows, K, _stream(x_q))
+    _lib.raise_on_error(rc, "dequantize")
+    return out
+
+
+def dequantize_q4_0(x_q: torch.Tensor, K: int) -> torch.Tensor:
+    """Q4_0 bytes [..., K//32, 18] -> FP32 [..., K] (python/quant_gemm/__init__.py:78-89)."""
+    return dequantize(x_q, K, TYPE_Q4_0)
+
+
+def gemm(weight_q: torch.Tensor, activation_q: torch.Tensor, M: int, N: int, K: int, wtype: int,
+         flags: int = 0, out: torch.Tensor | None = None) -> torch.Tensor:
+    """C[M,N] = W[M,K] @ A[N,K]^T, M = weight rows, N = tokens (ggml convention).
+
+    Checks mirror bindings.cpp:49-70.
+    """
+    _check(weight_q.is_cuda, "Weight must be a CUDA tensor")
+    _check(activation_q.is_cuda, "Activation must be a CUDA tensor")
+    _check(weight_q.dtype == torch.uint8, "Weight must be uint8")
+    _check(activation_q.dtype == torch.uint8, "Activation must be uint8")
+    _check(K % 32 == 0, f"K must be divisible by 32, got {K}")
+    nb = K // 32
+    bs = BLOCK_BYTES[wtype]
+    _check(weight_q.numel() == M * nb * bs,
+           f"Weight shape mismatch: expected {M * nb * bs} elements, got {weight_q.numel()}")
+    _check(activation_q.numel() == N * nb * 36,
+           f"Activation shape mismatch: expected {N * nb * 36} elements, got {activation_q.numel()}")
+    weight_q = weight_q.contiguous()
+    activation_q = activation_q.contiguous()
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=weight_q.device)
+    else:
+        _check(out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.numel() == M * N,
+               "out must be a contiguous CUDA float32 tensor of M*N elements")
+    L = _lib.lib()
+    with torch.cuda.device(weight_q.device):
+        ws_bytes = L.qgemm_workspace_bytes(wtype, N, M, K, flags)
+        ws = _workspace(weight_q.device, ws_bytes)
+        rc = L.qgemm_gemm(wtype, activation_q.data_ptr(), weight_q.data_ptr(), out.data_ptr(), N, M, K,
+                          1, N, flags, ws.data_ptr() if ws is not None else None,
+                          ws.numel() if ws is not None else 0, _stream(weight_q))
+    _lib.raise_on_error(rc, "gemm")
+    return out
+
+
+def gemm_q4_0_q8_1(weight_q, activation_q, M, N, K, flags: int = 0):
+    """Q4_0 x Q8_1 GEMM -> [M, N] float32 (python/quant_gemm/__init__.py:59-75)."""
+    return gemm(weight_q, activation_q, M, N, K, TYPE_Q4_0, flags)
+
+
+def gemm_q4_1_q8_1(weight_q, activation_q, M, N, K, flags: int = 0):
+    return gemm(weight_q, activation_q, M, N, K, TYPE_Q4_1, flags)
+
+
+def gemm_q5_0_q8_1(weight_q, activation_q, M, N, K, flags: int = 0):
+    return gemm(weight_q, activation_q, M, N, K, TYPE_Q5_0, flags)
+
+
+def gemm_q5_1_q8_1(weight_q, activation_q, M, N, K, flags: int = 0):
+    return gemm(weight_q, activation_q, M, N, K, TYPE_Q5_1, flags)
+
+
+def gemm_q8_0_q8_1(weight_q, activation_q, M, N, K, flags: int = 0):
+    return gemm(weight_q, activation_q, M, N, K, TYPE_Q8_0, flags)
+
+
+def gemm_w4a8(weight_q: torch.Tensor, activation: torch.Tensor, M: int, N: int, K: int,
+              wtype: int = TYPE_Q4_0, flags: int = 0, q81_flags: int = Q81_ROUND_AWAY) -> torch.Tensor:
+    """One call: quantize_q8_1(activation fp32 [N,K]) then the GEMM -> [M, N].
+
+    The reference designs this entry (docs/analysis/W4A8_DATAFLOW_ANALYSIS.md:93-160)
+    but never wrote it; its FP16 precursor is kernels/gemm/gemm_fused.cuh:311-338.
+    """
+    _check(weight_q.is_cuda and activation.is_cuda, "Inputs must be CUDA tensors")
+    _check(weight_q.dtype == torch.uint8, "Weight must be uint8")
+    _check(activation.dtype == torch.float32, "Activation must be float32")
+    _check(K % 32 == 0, f"K must be divisible by 32, got {K}")
+    nb = K // 32
+    _check(weight_q.numel() == M * nb * BLOCK_BYTES[wtype], "Weight shape mismatch")
+    _check(activation.numel() == N * K, "Activation shape mismatch")
+    weight_q = weight_q.contiguous()
+    activation = activation.contiguous()
+    out = torch.empty((M, N), dtype=torch.float32, device=weight_q.device)
+    L = _lib.lib()
+    with torch.cuda.device(weight_q.device):
+        ws_bytes = L.qgemm_workspace_bytes(wtype, N, M, K, flags)
+        ws = _workspace(weight_q.device, ws_bytes)
+        rc = L.qgemm_gemm_f32act(wtype, activation.data_ptr(), weight_q.data_ptr(), out.data_ptr(), N, M, K,
+                                 1, N, (flags & 0xFFFF) | (q81_flags << 16),
+                                 ws.data_ptr() if ws is not None else None,
+                                 ws.numel() if ws is not None else 0, _stream(weight_q))
+    _lib.raise_on_error(rc, "gemm_w4a8")
+    return out
+
+
+def block_sumi(weight_q: torch.Tensor, activation_q: torch.Tensor, M: int, N: int, K: int, wtype: int,
+               flags: int = 0) -> torch.Tensor:
+    """Test hook: int32 sumi[N tokens, M rows, K/32] exactly as the selected path computes it."""
+    weight_q = weight_q.contiguous()
+    activation_q = activation_q.contiguous()
+    out = torch.empty((N, M, K // 32), dtype=torch.int32, device=weight_q.device)
+    L = _lib.lib()
+    with torch.cuda.device(weight_q.device):
+        ws_bytes = L.qgemm_workspace_bytes(wtype, N, M, K, flags)
+        ws = _workspace(weight_q.device, ws_bytes)
+        rc = L.qgemm_sumi(wtype, activation_q.data_ptr(), weight_q.data_ptr(), out.data_ptr(), N, M, K, flags,
+                          ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0,
+                          _stream(weight_q))
+    _lib.raise_on_error(rc, "sumi")
+    return out
+
+
+def launch_count() -> int:
+    return int(_lib.lib().qgemm_launch_count())
+
+
+def reset_launch_count() -> None:
+    _lib.lib().qgemm_reset_launch_count()
+
+
+def last_path() -> int:
+    return int(_lib.lib().qgemm_last_path())
+
+
+__all__ = [
+    "quantize_q4_0", "quantize_q8_1", "gemm_q4_0_q8_1", "dequantize_q4_0",
+    "QK4_0", "QK8_1", "BLOCK_Q4_0_BYTES", "BLOCK_Q8_1_BYTES",
+    # supersets
+    "quantize_q4_1", "quantize_q5_0", "quantize_q5_1", "quantize_q8_0", "dequantize",
+    "gemm", "gemm_q4_1_q8_1", "gemm_q5_0_q8_1", "gemm_q5_1_q8_1", "gemm_q8_0_q8_1", "gemm_w4a8",
+    "block_sumi", "launch_count", "reset_launch_count", "last_path",
+]

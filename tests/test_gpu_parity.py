@@ -1,0 +1,293 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI (ctypes on libqgemm_sm100.so via
+quant_gemm._lib, device memory from torch), against the CPU oracle on identical seeded inputs.
+
+Gates:
+  * integer sumi: bit-exact
+  * quantize_q8_1 / weight quantizers: bytes identical to the oracle
+  * C: max|dC|/max|C| <= 1e-5 and NMSE <= 1e-10 vs the oracle's CPU-order result; the
+    QGEMM_SEQUENTIAL path is additionally bit-identical to the oracle's FMA-order result
+    (= what nvcc builds from the reference's GPU kernel) and, when oracle/_ref is present,
+    to the reference's GPU kernel itself run on the same device.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import datagen
+import qgemm_oracle as qo
+
+pytestmark = pytest.mark.gpu
+
+TOL_MAXNORM = 1e-5   # north_star: <= 1e-5 relative (normalised) on identical quantized inputs
+TOL_NMSE = 1e-10
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
+
+
+@pytest.fixture(scope="module")
+def qg():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import quant_gemm
+    quant_gemm._lib.lib()  # raises if the CUDA library is missing: no silent fallback
+    return quant_gemm
+
+
+@pytest.fixture(scope="module")
+def O():
+    return qo.Oracle()
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    torch.cuda.synchronize()
+    return t.cpu().numpy()
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def check_c(c_gpu, c_ref, what=""):
+    assert np.isfinite(c_gpu).all(), what
+    e_max, e_nmse = qo.max_norm_err(c_gpu, c_ref), qo.nmse(c_gpu, c_ref)
+    assert e_max <= TOL_MAXNORM and e_nmse <= TOL_NMSE, f"{what}: max-norm {e_max:.3e} nmse {e_nmse:.3e}"
+
+
+# ------------------------------------------------------------------------------------------
+# quantize_q8_1
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("flags", [0, qo.Q81_ROUND_EVEN, qo.Q81_S_FROM_QSUM | qo.Q81_CLAMP127, qo.Q81_CLAMP127])
+@pytest.mark.parametrize("shape", [(1, 32), (3, 4096), (7, 11008), (33, 1056), (2, 5, 256)])
+def test_quantize_q8_1_bytes(qg, O, flags, shape):
+    rng = np.random.default_rng(sum(shape) + flags)
+    x = (rng.standard_normal(shape) * rng.choice([1e-3, 1.0, 50.0], size=shape[:-1] + (1,))).astype(np.float32)
+    x.reshape(-1)[:32] = 0.0                      # an all-zero block
+    x.reshape(-1, 32)[-1] = np.float32(0.5) * np.arange(-16, 16)  # exact .5 ties after scaling by 127/amax=...
+    tie = np.zeros(32, np.float32)
+    tie[:6] = [127.0, 0.5, 1.5, -0.5, -2.5, 126.5]
+    x.reshape(-1, 32)[x.size // 64] = tie         # d = 1 exactly: genuine round-half cases
+    got = host(qg.quantize_q8_1(dev(x), flags))
+    want = O.quantize_q8_1(x, flags)
+    assert got.shape == want.shape == shape[:-1] + (shape[-1] // 32, 36)
+    assert (got == want).all()
+
+
+def test_quantize_q8_1_golden(qg):
+    for name in ("g1", "g3"):
+        assert (host(qg.quantize_q8_1(dev(G[f"{name}_x"]))) == G[f"{name}_a_q8_1_ref"]).all()
+        fw = qo.Q81_S_FROM_QSUM | qo.Q81_CLAMP127
+        assert (host(qg.quantize_q8_1(dev(G[f"{name}_x"]), fw)) == G[f"{name}_a_q8_1_fw"]).all()
+    assert (host(qg.quantize_q8_1(dev(G["step4_a"]))) == G["step4_a_q8_1"]).all()
+
+
+def test_quantize_q8_1_unaligned_and_empty(qg, O):
+    x = np.random.default_rng(1).standard_normal((5, 96)).astype(np.float32)
+    base = dev(np.concatenate([np.zeros(1, np.float32), x.ravel()]))
+    view = base[1:].view(5, 96)  # 4-byte aligned only
+    assert (host(qg.quantize_q8_1(view)) == O.quantize_q8_1(x)).all()
+    assert qg.quantize_q8_1(torch.zeros((0, 64), device="cuda")).shape == (0, 2, 36)
+
+
+@pytest.mark.parametrize("wt", qo.WEIGHT_TYPES)
+def test_weight_quantizers_and_dequantize(qg, O, wt):
+    _, w = datagen.model_like(1, 9, 512, seed=wt)
+    w[3, 64:96] = 0
+    fn = {2: qg.quantize_q4_0, 3: qg.quantize_q4_1, 6: qg.quantize_q5_0, 7: qg.quantize_q5_1, 8: qg.quantize_q8_0}[wt]
+    got = host(fn(dev(w)))
+    want = O.quantize_weight(wt, w)
+    assert (got == want).all()
+    deq = host(qg.dequantize(dev(want), 512, wt))
+    assert (bits(deq) == bits(O.dequantize(wt, want))).all()
+    if wt in (2, 8):
+        assert (got == O.quantize_weight(wt, w, "include")).all()
+
+
+def test_dequantize_q4_0_reference_name(qg, O):
+    wq = G["g1_w_q4_0_inc"]
+    out = host(qg.dequantize_q4_0(dev(wq), 256))
+    assert (bits(out) == bits(G["g1_deq_q4_0_inc"])).all()
+
+
+# ------------------------------------------------------------------------------------------
+# sumi: bit-exact
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("wt", qo.WEIGHT_TYPES)
+def test_sumi_bit_exact_fuzz(qg, O, wt):
+    T, F, nb = 5, 67, 24
+    wq = datagen.fuzz_weight_blocks(wt, F, nb, seed=wt)
+    aq = datagen.fuzz_act_blocks(T, nb, seed=wt)
+    got = host(qg.block_sumi(dev(wq), dev(aq), F, T, nb * 32, wt))
+    assert (got == O.gemm_sumi(wt, aq, wq)).all()
+    a, w = datagen.extreme_blocks(wt)
+    got = host(qg.block_sumi(dev(w), dev(a), 2, 2, 4 * 32, wt))
+    assert (got == O.gemm_sumi(wt, a, w)).all()
+
+
+# ------------------------------------------------------------------------------------------
+# GEMM parity
+# ------------------------------------------------------------------------------------------
+PATHS = {"auto": 0, "gemv": 0x200, "generic": 0x100}
+
+
+def run_gemm(qg, wt, aq, wq, path, flags=0):
+    T, nb, _ = aq.shape
+    F = wq.shape[0]
+    out = qg.gemm(dev(wq), dev(aq), F, T, nb * 32, wt, flags | PATHS[path])
+    return host(out)  # [F, T]
+
+
+@pytest.mark.parametrize("wt", qo.WEIGHT_TYPES)
+def test_gemm_golden_fixtures(qg, wt):
+    n = qo.TYPE_NAMES[wt]
+    for name in ("g1", "g3"):
+        c = run_gemm(qg, wt, G[f"{name}_a_q8_1_ref"], G[f"{name}_w_{n}_fw"], "auto")
+        check_c(c, G[f"{name}_c_{n}_FT"], f"{name} {n}")
+    c = run_gemm(qg, wt, G[f"fuzz_a_{n}"], G[f"fuzz_w_{n}"], "auto")
+    check_c(c, G[f"fuzz_c_{n}_FT"], f"fuzz {n}")
+
+
+def test_step4_block_through_gpu(qg):
+    c = run_gemm(qg, qo.Q4_0, G["step4_a_q8_1"].reshape(1, 1, 36), G["step4_w_q4_0"].reshape(1, 1, 18), "auto")
+    assert abs(float(c[0, 0]) - (-0.335609674)) < 1e-7
+
+
+@pytest.mark.parametrize("wt", qo.WEIGHT_TYPES)
+@pytest.mark.parametrize("path", ["gemv", "generic"])
+@pytest.mark.parametrize("T,F,K", [(1, 256, 4096), (2, 193, 1024), (4, 512, 1024), (8, 130, 2048), (3, 64, 11008),
+                                   (11, 96, 512)])
+def test_gemm_vs_oracle_model_like(qg, O, wt, path, T, F, K):
+    x, w = datagen.model_like(T, F, K, seed=T * 7 + F)
+    aq, wq = O.quantize_q8_1(x), O.quantize_weight(wt, w)
+    c = run_gemm(qg, wt, aq, wq, path)
+    check_c(c, O.gemm(wt, aq, wq, layout="FT"), f"{path} {qo.TYPE_NAMES[wt]} {T}x{F}x{K}")
+    if path == "generic":  # sequential path == nvcc's FMA order of the reference GPU kernel, bit for bit
+        assert (bits(c) == bits(O.gemm(wt, aq, wq, layout="FT", flags=qo.GEMM_FMA))).all()
+
+
+@pytest.mark.parametrize("wt", qo.WEIGHT_TYPES)
+def test_gemm_fuzz_blocks_and_ms_exact(qg, O, wt):
+    T, F, nb = 4, 200, 64
+    wq = datagen.fuzz_weight_blocks(wt, F, nb, seed=10 + wt)
+    aq = datagen.fuzz_act_blocks(T, nb, seed=10 + wt, const_ds=False)
+    for path in ("gemv", "generic"):
+        c = run_gemm(qg, wt, aq, wq, path)
+        check_c(c, O.gemm(wt, aq, wq, layout="FT"), f"fuzz {path}")
+        c = run_gemm(qg, wt, aq, wq, path, flags=qo.GEMM_MS_EXACT)
+        check_c(c, O.gemm(wt, aq, wq, layout="FT", flags=qo.GEMM_MS_EXACT), f"fuzz ms_exact {path}")
+
+
+def test_gemm_include_convention_and_strides(qg, O):
+    """C[T,F] (include/ order) through the raw C ABI with explicit strides."""
+    from quant_gemm import _lib
+    T, F, K = 3, 160, 1024
+    x, w = datagen.uniform(T, F, K, seed=3)
+    aq, wq = O.quantize_q8_1(x), O.quantize_weight(qo.Q4_0, w, "include")
+    da, dw = dev(aq), dev(wq)
+    out = torch.full((T, F + 5), -7.0, device="cuda")  # padded rows: ldc_t = F + 5
+    rc = _lib.lib().qgemm_gemm(2, da.data_ptr(), dw.data_ptr(), out.data_ptr(), T, F, K, F + 5, 1, 0, None, 0,
+                               torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    o = host(out)
+    check_c(o[:, :F], O.gemm(qo.Q4_0, aq, wq, layout="TF"))
+    assert (o[:, F:] == -7.0).all()
+
+
+def test_gemm_edge_shapes(qg, O):
+    # K = 32 (one block), F = 1, odd block counts (generic path), T = 0
+    for (T, F, K) in [(1, 1, 32), (2, 3, 96), (5, 7, 160), (1, 1000, 32)]:
+        x, w = datagen.model_like(T, F, K, seed=K)
+        for wt in qo.WEIGHT_TYPES:
+            aq, wq = O.quantize_q8_1(x), O.quantize_weight(wt, w)
+            check_c(run_gemm(qg, wt, aq, wq, "auto"), O.gemm(wt, aq, wq, layout="FT"), f"edge {T},{F},{K}")
+    e = qg.gemm(torch.zeros((4, 2, 18), dtype=torch.uint8, device="cuda"),
+                torch.zeros((0, 2, 36), dtype=torch.uint8, device="cuda"), 4, 0, 64, 2)
+    assert e.shape == (4, 0)
+    with pytest.raises(RuntimeError, match="divisible by 32"):
+        qg.gemm_q4_0_q8_1(torch.zeros(18, dtype=torch.uint8, device="cuda"),
+                          torch.zeros(36, dtype=torch.uint8, device="cuda"), 1, 1, 33)
+    with pytest.raises(RuntimeError, match="shape mismatch"):
+        qg.gemm_q4_0_q8_1(torch.zeros(17, dtype=torch.uint8, device="cuda"),
+                          torch.zeros(36, dtype=torch.uint8, device="cuda"), 1, 1, 32)
+
+
+def test_fused_f32_activation_entry(qg, O):
+    T, F, K = 6, 256, 2048
+    x, w = datagen.model_like(T, F, K, seed=21)
+    for wt in (qo.Q4_0, qo.Q5_1):
+        wq = O.quantize_weight(wt, w)
+        c = host(qg.gemm_w4a8(dev(wq), dev(x), F, T, K, wt))
+        check_c(c, O.gemm(wt, O.quantize_q8_1(x), wq, layout="FT"))
+
+
+@pytest.mark.skipif(not qo.have_ref(), reason="oracle/_ref/libqgemm_ref.so not shipped")
+@pytest.mark.parametrize("wt", [qo.Q4_0, qo.Q4_1, qo.Q5_0, qo.Q5_1])
+def test_against_reference_gpu_kernels(qg, O, wt):
+    """Same bytes through the reference's own GPU kernel (kernels/gemm/gemm_quant_formats.cuh built
+    for sm_100a) and ours.  q8_0 is excluded: the reference kernel does a misaligned 4-byte load
+    there; include/gemm_w8a8_naive covers it below."""
+    R = qo.Reference()
+    T, F, K = 4, 300, 1024
+    x, w = datagen.model_like(T, F, K, seed=30 + wt)
+    aq, wq = O.quantize_q8_1(x), O.quantize_weight(wt, w)
+    da, dw = dev(aq), dev(wq)
+    ref_out = torch.empty((F, T), device="cuda")
+    torch.cuda.synchronize()
+    rc = R.lib.ref_gpu_gemm_quant(wt, dw.data_ptr(), da.data_ptr(), ref_out.data_ptr(), F, T, K, None)
+    assert rc == 0
+    r = host(ref_out)
+    assert (bits(run_gemm(qg, wt, aq, wq, "generic")) == bits(r)).all()
+    check_c(run_gemm(qg, wt, aq, wq, "gemv"), r, "vs reference GPU")
+
+
+@pytest.mark.skipif(not qo.have_ref(), reason="oracle/_ref/libqgemm_ref.so not shipped")
+def test_against_reference_gpu_include_kernels(qg, O):
+    R = qo.Reference()
+    from quant_gemm import _lib
+    T, F, K = 5, 128, 512
+    x, w = datagen.uniform(T, F, K, seed=40)
+    aq = O.quantize_q8_1(x)
+    for wt, fn in ((qo.Q4_0, R.lib.ref_gpu_gemm_w4a8_naive), (qo.Q8_0, R.lib.ref_gpu_gemm_w8a8_naive)):
+        wq = O.quantize_weight(wt, w, "include")
+        da, dw = dev(aq), dev(wq)
+        r = torch.empty((T, F), device="cuda")
+        torch.cuda.synchronize()
+        fn(da.data_ptr(), dw.data_ptr(), r.data_ptr(), T, F, K, None)
+        ours = torch.empty((T, F), device="cuda")
+        assert _lib.lib().qgemm_gemm(wt, da.data_ptr(), dw.data_ptr(), ours.data_ptr(), T, F, K, F, 1, 0, None, 0,
+                                     torch.cuda.current_stream().cuda_stream) == 0
+        check_c(host(ours), host(r), "include naive")
+    # reference GPU quantize_q8_1 kernel == our ROUND_EVEN mode
+    dx = dev(x)
+    y = torch.empty((T, K // 32, 36), dtype=torch.uint8, device="cuda")
+    R.lib.ref_gpu_quantize_q8_1(dx.data_ptr(), y.data_ptr(), T * K, None)
+    assert (host(y) == host(qg.quantize_q8_1(dx, qo.Q81_ROUND_EVEN))).all()
+
+
+# ------------------------------------------------------------------------------------------
+# full-size configs: size-independent properties (oracle would take minutes)
+# ------------------------------------------------------------------------------------------
+def test_full_size_decode_properties(qg, O):
+    """BASELINE config 1/2 sizes: spot-check rows against the oracle, plus linearity in the
+    activation scale and row-permutation equivariance."""
+    T, F, K = 8, 11008, 4096
+    x, w = datagen.model_like(T, F, K, seed=50)
+    aq = O.quantize_q8_1(x)
+    dw32 = dev(w)
+    for wt in qo.WEIGHT_TYPES:
+        fn = {2: qg.quantize_q4_0, 3: qg.quantize_q4_1, 6: qg.quantize_q5_0, 7: qg.quantize_q5_1, 8: qg.quantize_q8_0}[wt]
+        dwq = fn(dw32)
+        wq = host(dwq)
+        c = host(qg.gemm(dwq, dev(aq), F, T, K, wt))
+        rows = np.r_[0:8, 5000:5008, F - 8:F]
+        check_c(c[rows], O.gemm(wt, aq, wq[rows], layout="FT"), f"full decode {qo.TYPE_NAMES[wt]}")
+        perm = np.random.default_rng(wt).permutation(F)
+        c2 = host(qg.gemm(dev(wq[perm]), dev(aq), F, T, K, wt))
+        assert (bits(c2) == bits(c[perm])).all()
+        # T=1 slice equals column 0 of the T=8 run up to accumulation-order noise; sumi identical
+        c1 = host(qg.gemm(dwq, dev(aq[:1]), F, 1, K, wt))
+        check_c(c1[:, 0], c[:, 0], "T=1 vs T=8")
