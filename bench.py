@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark (BASELINE.json: "Q4_0 x Q8_1 GEMM ... HBM GB/s vs roofline;
+M=1 GEMV us at Llama shapes").
+
+One step = one decode token (M=1) pushed through every linear layer of a Llama-7B-shaped stack
+with Q4_0 weights x Q8_1 activations: 32 layers x {wq,wk,wv,wo: 4096x4096, gate,up: 11008x4096,
+down: 4096x11008} = 224 GEMV launches over 3.64 GB of distinct weight bytes (29x the 126 MB L2, so
+every launch streams from HBM), replayed as one CUDA graph.
+
+  value   = algorithmic bytes of all launches of all ranks / device time      [GB/s]
+            (weights once + q8_1 activations + fp32 outputs)
+  e2e     = the same step through the public python API (quant_gemm) with HOST buffers: pinned
+            fp32 activations H2D, quantize_q8_1, 224 GEMVs, all outputs D2H -- inside the timed region
+  N > 1   : weak scaling -- every rank owns the rows of its shard of an N-times wider model
+            (same per-GPU bytes) and the per-GEMV outputs are all-gathered over NCCL/NVLink.
+  --impl reference : the reference's own CPU implementation (oracle/_ref, all host threads) on
+            a bounded sample (one layer = 7 GEMVs per step) of the same workload.
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(ROOT, "llama.cpp-quant-gemm_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "q4_0_q8_1_decode_gemv_hbm_gbs"
+UNIT = "GB/s"
+LLAMA7B = [("wq", 4096, 4096), ("wk", 4096, 4096), ("wv", 4096, 4096), ("wo", 4096, 4096),
+           ("gate", 11008, 4096), ("up", 11008, 4096), ("down", 4096, 11008)]
+WTYPE = 2  # Q4_0
+BS = {2: 18, 3: 20, 6: 22, 7: 24, 8: 34}
+
+
+def algorithmic_bytes(wtype, T, F, K):
+    nb = K // 32
+    return F * nb * BS[wtype] + T * nb * 36 + 4 * T * F
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        out = self.p.communicate()[0]
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        # the busiest half of the samples = "under load"
+        sm.sort()
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU code on the host cores
+# ------------------------------------------------------------------------------------------
+def make_blocks_numpy(F, K, seed):
+    import numpy as np
+    import datagen
+    return datagen.fuzz_weight_blocks(WTYPE, F, K // 32, seed=seed)
+
+
+def cpu_reference_run(steps, warmup, sample_layers=1, budget_s=None):
+    """Times the reference's cpu_gemm_q4_0_q8_1 (tests/unit/test_gemm_all_quants.cu:23-59, compiled
+    unmodified into oracle/_ref) -- or the oracle port if that library is absent -- over
+    `sample_layers` layers of the workload per step, all host threads (weight-row slabs)."""
+    import numpy as np
+    import datagen
+    import qgemm_oracle as qo
+    cores = os.cpu_count() or 1
+    use_ref = qo.have_ref()
+    R = qo.Reference() if use_ref else None
+    O = qo.Oracle()
+    mats = []
+    for i, (_, F, K) in enumerate(LLAMA7B * sample_layers):
+        w = make_blocks_numpy(F, K, seed=i)
+        a = datagen.fuzz_act_blocks(1, K // 32, seed=i, const_ds=False)
+        mats.append((F, K, w, a))
+    step_bytes = sum(algorithmic_bytes(WTYPE, 1, F, K) for F, K, _, _ in mats)
+
+    def one_step():
+        for F, K, w, a in mats:
+            if use_ref:
+                R.cpu_gemm(WTYPE, w, a, threads=cores)
+            else:
+                # the oracle port, slabbed over weight rows with the same thread count
+                import threading
+                out = np.empty((F, 1), np.float32)
+                slab = (F + cores - 1) // cores
+                ths = []
+                for c in range(cores):
+                    f0, f1 = c * slab, min(F, (c + 1) * slab)
+                    if f0 >= f1:
+                        break
+                    th = threading.Thread(target=lambda f0=f0, f1=f1: O.lib.qo_gemm(
+                        WTYPE, a.ctypes.data, w[f0:f1].ctypes.data, out[f0:f1].ctypes.data, 1, f1 - f0, K, 1, 1, 0, 0, 1))
+                    th.start()
+                    ths.append(th)
+                for th in ths:
+                    th.join()
+
+    for _ in range(warmup):
+        one_step()
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        one_step()
+        done += 1
+        if budget_s and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": step_bytes * done / dt / 1e9, "unit": UNIT, "cores": cores,
+            "kind": "reference" if use_ref else "port",
+            "sample": f"{sample_layers} layer(s) = {7 * sample_layers} M=1 Q4_0 GEMVs per step "
+                      f"({step_bytes / 1e6:.1f} MB), {done} steps, weight-row slabs over {cores} threads",
+            "ms_per_step": dt / done * 1e3, "steps": done}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int8xint4->int32, fp32 fold", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus):
+    return {"workload": "Llama-7B decode GEMV stack: M=1, 32 layers x {4x 4096x4096, 2x 11008x4096, 1x 4096x11008}, "
+                        "Q4_0 weights x Q8_1 activations (BASELINE configs[1])",
+            "launches_per_step": 224, "weight_bytes_per_gpu": 32 * sum(F * (K // 32) * 18 for _, F, K in LLAMA7B),
+            "l2_defeat": "inputs larger than L2: 3.64 GB of distinct weights per step vs 126 MB L2",
+            "parallelism": f"weight rows (N) sharded x{n_gpus}, all-gather of C" if n_gpus > 1 else "1 GPU",
+            "timing": "CUDA events on the launch stream around K graph replays, max over ranks"}
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--layers", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--detail", default=None, help="write a per-shape sweep (all formats, M=1..8, prefill) to this JSON file")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import quant_gemm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    quant_gemm._lib.lib()
+
+    # ---- synthetic weight pool: raw-block fuzz (all nibble values), sane fp16 scales
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    mats = []
+    for layer in range(args.layers):
+        for name, F, K in LLAMA7B:
+            nb = K // 32
+            w = torch.randint(0, 256, (F, nb, 18), dtype=torch.uint8, device=dev, generator=g)
+            d = (torch.rand((F, nb), device=dev, generator=g) * 0.02 + 0.001).to(torch.float16)
+            w[:, :, 0:2] = d.view(torch.uint8).view(F, nb, 2)
+            mats.append((F, K, w))
+    acts_host = {K: torch.randn((1, K), generator=torch.Generator().manual_seed(7 + K)).pin_memory() for K in (4096, 11008)}
+    acts_dev = {K: v.to(dev) for K, v in acts_host.items()}
+    acts_q = {K: quant_gemm.quantize_q8_1(v) for K, v in acts_dev.items()}
+    outs = [torch.empty((F * world, 1), device=dev) for F, K, _ in mats]  # gathered C, [F_total, T=1]
+    total_out = sum(o.numel() for o in outs)
+    out_host = torch.empty(total_out, dtype=torch.float32).pin_memory()
+    step_bytes = sum(algorithmic_bytes(WTYPE, 1, F, K) for F, K, _ in mats)
+
+    def gemv_all():
+        for (F, K, w), o in zip(mats, outs):
+            mine = o[rank * F:(rank + 1) * F]
+            quant_gemm.gemm(w, acts_q[K], F, 1, K, WTYPE, out=mine)
+            if world > 1:
+                dist.all_gather_into_tensor(o, mine)
+
+    def e2e_step():
+        for K in acts_host:
+            acts_dev[K].copy_(acts_host[K], non_blocking=True)
+            acts_q[K] = quant_gemm.quantize_q8_1(acts_dev[K])
+        gemv_all()
+        off = 0
+        for o in outs:
+            out_host[off:off + o.numel()].copy_(o.view(-1), non_blocking=True)
+            off += o.numel()
+
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        gemv_all()  # warm: cudaFuncSetAttribute, NCCL channels
+        e2e_step()
+        stream.synchronize()
+        quant_gemm.reset_launch_count()
+        g_dev = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_dev, stream=stream):
+            gemv_all()
+        launches_per_step = quant_gemm.launch_count()
+        g_e2e = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_e2e, stream=stream):
+            e2e_step()
+        launches_per_e2e = quant_gemm.launch_count() - launches_per_step
+
+    def timed(graph, steps, warmup):
+        with torch.cuda.stream(stream):
+            for _ in range(warmup):
+                graph.replay()
+            stream.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(steps):
+                graph.replay()
+            e1.record(stream)
+            stream.synchronize()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_dev = timed(g_dev, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e = timed(g_e2e, args.steps, args.warmup)
+
+    # correctness spot check of the timed path against the oracle (rank 0, a few rows)
+    check = None
+    if rank == 0:
+        import qgemm_oracle as qo
+        O = qo.Oracle()
+        F, K, w = mats[4]
+        rows = np.r_[0:4, F - 4:F]
+        ref = O.gemm(WTYPE, acts_q[K].cpu().numpy(), w[torch.from_numpy(rows).to(dev)].cpu().numpy(), layout="FT")
+        got = outs[4][rank * F:(rank + 1) * F].cpu().numpy()[rows]
+        check = qo.max_norm_err(got, ref)
+        assert check <= 1e-5, f"timed path disagrees with the oracle: {check}"
+
+    value = step_bytes * world * args.steps / (ms_dev * 1e-3) / 1e9
+    e2e_value = step_bytes * world * args.steps / (ms_e2e * 1e-3) / 1e9
+    peak, peak_src = load_peaks()
+    per_launch_bytes = step_bytes / len(mats)
+    per_launch_us = ms_dev * 1e3 / (args.steps * len(mats))
+    achieved = per_launch_bytes / (per_launch_us * 1e-6) / 1e9
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u4 x s8 -> s32 (dp4a), fp32 fold", "data": "synthetic",
+        "config": workload_config(world),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT,
+                "h2d_bytes_per_step": sum(v.numel() * 4 for v in acts_host.values()),
+                "d2h_bytes_per_step": total_out * 4, "ms_per_step": ms_e2e / args.steps,
+                "api": "quant_gemm.quantize_q8_1 + quant_gemm.gemm (python mirror of the reference extension) "
+                       "-> C ABI; weights resident in HBM like the reference API (device pointers)"},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "gpu_launches_e2e": int(launches_per_e2e * args.steps),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "gemv_kernel<Q4_0,1>", "peak_source": peak_src,
+                     "avg_launch_us": per_launch_us, "algorithmic_bytes_per_launch": per_launch_bytes,
+                     "frac_of_nominal_8000": achieved / 8000.0},
+        "oracle_check_max_norm_err": check,
+    }
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_run(steps=10 ** 6, warmup=1, sample_layers=1, budget_s=12.0)
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if args.detail:
+            import bench_detail
+            bench_detail.run(args.detail)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
