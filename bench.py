@@ -38,6 +38,7 @@ UNIT = "GB/s"
 LLAMA7B = [("wq", 4096, 4096), ("wk", 4096, 4096), ("wv", 4096, 4096), ("wo", 4096, 4096),
            ("gate", 11008, 4096), ("up", 11008, 4096), ("down", 4096, 11008)]
 WTYPE = 2  # Q4_0
+GEMV_FLAGS = 0x10  # QGEMM_WEIGHTS_STATIC: model weights are never written while decoding
 BS = {2: 18, 3: 20, 6: 22, 7: 24, 8: 34}
 
 
@@ -240,7 +241,7 @@ def main():
     def gemv_all():
         for (F, K, w), o in zip(mats, outs):
             mine = o[rank * F:(rank + 1) * F]
-            quant_gemm.gemm(w, acts_q[K], F, 1, K, WTYPE, out=mine)
+            quant_gemm.gemm(w, acts_q[K], F, 1, K, WTYPE, GEMV_FLAGS, out=mine)
             if world > 1:
                 dist.all_gather_into_tensor(o, mine)
 

@@ -1,0 +1,107 @@
+#!/usr/bin/env python
+"""bench_detail.py -- per-shape sweep behind the headline number (not a bench line).
+
+For every (format, T, F, K) it rotates over a pool of distinct weight matrices >= 4x the L2 so each
+launch streams from HBM, replays the rotation as one CUDA graph, and reports us per launch, the
+algorithmic GB/s (SURVEY.md section 8d byte model) and, for T >= 64, TOPS = 2*T*F*K / t.
+
+    python bench_detail.py --out profiles/detail_r01.json [--quick]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(ROOT, "llama.cpp-quant-gemm_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+BS = {2: 18, 3: 20, 6: 22, 7: 24, 8: 34}
+NAMES = {2: "q4_0", 3: "q4_1", 6: "q5_0", 7: "q5_1", 8: "q8_0"}
+POOL_BYTES = 768 << 20
+
+
+def make_weights(torch, wtype, F, K, n, dev, seed=0):
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    nb = K // 32
+    w = torch.randint(0, 256, (n, F, nb, BS[wtype]), dtype=torch.uint8, device=dev, generator=g)
+    d = (torch.rand((n, F, nb), device=dev, generator=g) * 0.02 + 0.001).to(torch.float16)
+    w[..., 0:2] = d.view(torch.uint8).view(n, F, nb, 2)
+    if wtype in (3, 7):
+        m = (torch.rand((n, F, nb), device=dev, generator=g) - 0.5).to(torch.float16)
+        w[..., 2:4] = m.view(torch.uint8).view(n, F, nb, 2)
+    return w
+
+
+def time_shape(torch, quant_gemm, wtype, T, F, K, flags=0x10, reps=3, pool_bytes=POOL_BYTES):
+    dev = torch.device("cuda")
+    wbytes = F * (K // 32) * BS[wtype]
+    n = max(2, min(256, pool_bytes // wbytes))
+    w = make_weights(torch, wtype, F, K, n, dev)
+    x = torch.randn((T, K), device=dev)
+    aq = quant_gemm.quantize_q8_1(x)
+    out = torch.empty((F, T), device=dev)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        quant_gemm.gemm(w[0], aq, F, T, K, wtype, flags, out=out)
+        stream.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            for i in range(n):
+                quant_gemm.gemm(w[i], aq, F, T, K, wtype, flags, out=out)
+        for _ in range(2):
+            g.replay()
+        best = 1e30
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            g.replay()
+            e1.record(stream)
+            stream.synchronize()
+            best = min(best, e0.elapsed_time(e1) * 1e3 / n)
+        # single hot launch (weights in L2): the latency floor
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(3):
+            quant_gemm.gemm(w[0], aq, F, T, K, wtype, flags, out=out)
+        e0.record(stream)
+        for _ in range(20):
+            quant_gemm.gemm(w[0], aq, F, T, K, wtype, flags, out=out)
+        e1.record(stream)
+        stream.synchronize()
+        hot = e0.elapsed_time(e1) * 1e3 / 20
+    nb = K // 32
+    abytes = F * nb * BS[wtype] + T * nb * 36 + 4 * T * F
+    return {"type": NAMES[wtype], "T": T, "F": F, "K": K, "us": best, "us_hot_l2": hot,
+            "gbs": abytes / best / 1e3, "tops": 2.0 * T * F * K / best / 1e6, "pool": n,
+            "path": hex(quant_gemm.last_path())}
+
+
+def run(out_path, quick=False, flags=0x10):
+    import torch
+    import quant_gemm
+    rows = []
+    types = [2] if quick else [2, 3, 6, 7, 8]
+    shapes = [(4096, 4096), (11008, 4096)] + ([] if quick else [(4096, 11008)])
+    for wt in types:
+        for F, K in shapes:
+            for T in ([1, 8] if quick else [1, 2, 4, 8]):
+                r = time_shape(torch, quant_gemm, wt, T, F, K, flags)
+                rows.append(r)
+                print(json.dumps(r), flush=True)
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    with open(out_path, "w") as f:
+        json.dump({"peaks": peaks, "rows": rows}, f, indent=1)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default="gpurun_out/detail.json")
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--flags", type=lambda v: int(v, 0), default=0x10)
+    a = ap.parse_args()
+    run(a.out, a.quick, a.flags)

@@ -68,6 +68,10 @@ extern "C" {
                                    b = 0..K/32-1 with the reference GPU kernel's exact FMA
                                    sequence: bit-identical to kernels/gemm/
                                    gemm_quant_formats.cuh:312-334 built by nvcc.  Slow.      */
+#define QGEMM_WEIGHTS_STATIC 0x10u /* caller promises no work still in flight on `stream` writes the
+                                   weight buffer: the decode path then launches with programmatic
+                                   dependent launch and prefetches weights under the previous
+                                   kernel's tail (activations / C are still ordered normally)       */
 #define QGEMM_PATH_MASK 0xF00u
 #define QGEMM_PATH_AUTO 0x000u
 #define QGEMM_PATH_GENERIC 0x100u /* same kernel as QGEMM_SEQUENTIAL                         */

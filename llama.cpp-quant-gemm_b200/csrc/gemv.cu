@@ -7,30 +7,33 @@
 // their GPU's DRAM bandwidth.
 //
 // Design (B200):
-//   * one persistent CTA per SM; weight rows are grouped R at a time and a
-//     row group is cut into K-chunks of <= 128 blocks; (group, chunk) = one tile
-//   * a producer warp streams tiles HBM -> smem with 1-D bulk async copies
-//     (cp.async.bulk, the TMA engine; one copy per row segment, all landing on
-//     one mbarrier) through a ring of `stages` buffers -- tens of KB in flight
-//     per SM with no registers or L1 involved
-//   * the T x K activations are staged once per CTA in smem, re-laid out so
-//     that consecutive lanes read consecutive 16-byte quads (conflict-free)
-//   * 8 consumer warps: warp -> (row, K-slice) of the tile, lane -> pairs of
-//     adjacent blocks (a pair starts 4-byte aligned in every format, which a
-//     single 18/22/34-byte block does not); integer dot by dp4a on UN-offset
-//     weights, then the reference's exact per-block fold (qgemm_common.cuh)
-//   * per-row partial sums: lane-sequential over K, butterfly across lanes,
-//     fixed-order across the warps of a row -> deterministic
+//   * one persistent CTA per SM owns a CONTIGUOUS span of weight rows (F split
+//     to one-row granularity: at most 1 row of imbalance per SM); since rows are
+//     contiguous in memory the span is one byte range, cut into tiles of RT rows
+//   * a producer warp streams tiles HBM -> smem with ONE 1-D bulk async copy
+//     per tile (cp.async.bulk, the TMA engine) through a ring of mbarrier-guarded
+//     stages: tens of KB in flight per SM, no registers or L1 involved
+//   * 8 consumer warps; a warp (or WPR warps for long rows) owns a row of the
+//     tile, a lane owns fixed K positions: pairs of adjacent blocks (a pair starts
+//     4-byte aligned in every format, a single 18/22/34-byte block does not)
+//   * because a lane's K positions never change, its q8_1 activations live in
+//     REGISTERS for the whole kernel (T*PPL <= 6 pairs); larger T keep them in smem,
+//     re-laid out so consecutive lanes read consecutive 16-byte quads
+//   * integer dot by dp4a on UN-offset weights, then the reference's exact
+//     per-block fold (qgemm_common.cuh); lane-sequential over K, butterfly across
+//     lanes, fixed order across the warps of a row -> deterministic
+//   * optional programmatic dependent launch (QGEMM_WEIGHTS_STATIC): the weight
+//     prefetch of launch n+1 overlaps the tail of launch n
 #include "ptx.cuh"
 #include "qgemm_common.cuh"
 
 namespace qgemm {
 
-constexpr int kGemvWarps = 8;                       // consumer warps
-constexpr int kGemvThreads = (kGemvWarps + 1) * 32; // + 1 producer warp
+constexpr int kGemvWarps = 8;                        // consumer warps
+constexpr int kGemvThreads = (kGemvWarps + 1) * 32;  // + 1 producer warp
 constexpr int kGemvMaxStages = 8;
-constexpr int kGemvChunkBlocks = 128;               // K-chunk, in 32-element blocks
-constexpr int kGemvSmemBudget = 200 * 1024;
+constexpr int kGemvSmemBudget = 208 * 1024;
+constexpr int kGemvTileTarget = 24 * 1024;           // bytes per tile we aim for
 
 // ---- a pair of adjacent weight blocks as 32-bit words --------------------------
 template <int WT> struct Pair { static constexpr int words = Fmt<WT>::bytes / 2; };
@@ -116,32 +119,50 @@ __device__ __forceinline__ void expand_pair(const uint32_t (&x)[Pair<WT>::words]
     }
 }
 
+// q8_1 activations of one pair of blocks (72 bytes, 4-byte aligned) for one token
+struct ActPair {
+    int q[2][8];
+    ActScale s[2];
+};
+
 struct GemvParams {
     const uint8_t* act;   // q8_1, first token of this pass
     const uint8_t* wgt;
     float* C;             // already offset to the first token of this pass
     int F, nb;
     int64_t ldc_t, ldc_f;
-    int R;                // weight rows per tile: 1, 2, 4 or 8
+    int RT;               // weight rows per tile (multiple of 8 / WPR)
+    int WPR;              // warps sharing one row: 1, 2, 4 or 8
     int stages;
     int stage_bytes;      // 128-byte multiple
+    int pdl;              // programmatic dependent launch in use
 };
 
-template <int WT, int TT, bool kMsExact>
+// PPL > 0: activations in registers, PPL pairs per lane.  PPL == 0: activations in smem.
+template <int WT, int TT, int PPL, bool kMsExact>
 __global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const GemvParams p) {
     using Fm = Fmt<WT>;
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nb = p.nb, np = nb >> 1;
 
-    // ---- carve shared memory
+    // ---- carve shared memory (integer offsets from the __shared__ base keep every access an LDS)
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);          // [kGemvMaxStages]
     uint64_t* empty = full + kGemvMaxStages;                     // [kGemvMaxStages]
-    float* red = reinterpret_cast<float*>(smem + 128);           // [2][kGemvWarps][8]
-    float4* a_scale = reinterpret_cast<float4*>(smem + 1024);    // [TT][np]   (d0,s0,d1,s1) of a pair
-    uint4* a_qs = reinterpret_cast<uint4*>(a_scale + (size_t)TT * np);  // [TT][4][np] 16-byte quads
-    uint8_t* stage0 = reinterpret_cast<uint8_t*>(
-        (reinterpret_cast<uintptr_t>(a_qs + (size_t)TT * 4 * np) + 127) & ~uintptr_t(127));
+    float* slots = reinterpret_cast<float*>(smem + 128);         // [2][kGemvWarps][8] cross-warp partials
+    // PPL > 0 : raw q8_1 copy [TT][nb][36 B];  PPL == 0 : [TT][np] float4 scales + [TT][4][np] quads
+    uint8_t* a_raw = smem + 1024;
+    float4* a_scale = reinterpret_cast<float4*>(smem + 1024);
+    uint4* a_qs = reinterpret_cast<uint4*>(smem + 1024 + (size_t)TT * np * 16);
+    const uint32_t act_bytes = (PPL > 0) ? (uint32_t)TT * nb * 36u : (uint32_t)TT * nb * 40u;
+    uint8_t* stage0 = smem + ((1024u + act_bytes + 127u) & ~127u);
+
+    // ---- this CTA's contiguous span of weight rows
+    const int r_begin = (int)(((int64_t)p.F * blockIdx.x) / gridDim.x);
+    const int r_end = (int)(((int64_t)p.F * (blockIdx.x + 1)) / gridDim.x);
+    const int RT = p.RT;
+    const int ntiles = (r_end - r_begin + RT - 1) / RT;
+    const size_t rowbytes = (size_t)nb * Fm::bytes;
 
     if (tid == 0) {
         for (int s = 0; s < p.stages; s++) {
@@ -150,220 +171,303 @@ __global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const GemvParams 
         }
         ptx::fence_mbar_init();
     }
-    // ---- stage the activations: q8_1 AoS -> quad-interleaved SoA + fp32 scales
-    {
-        const uint32_t* a32 = reinterpret_cast<const uint32_t*>(p.act);
-        float* sc = reinterpret_cast<float*>(a_scale);
-        uint32_t* qs = reinterpret_cast<uint32_t*>(a_qs);
-        const int total = TT * nb * 9;
-        for (int i = tid; i < total; i += kGemvThreads) {
-            const int blk = i / 9, wd = i - blk * 9;
-            const int t = blk / nb, b = blk - t * nb;
-            const uint32_t v = __ldg(a32 + i);
-            if (wd == 0) {
-                float* d = sc + ((size_t)t * np + (b >> 1)) * 4 + (b & 1) * 2;
-                d[0] = half_bits_to_float(v);
-                d[1] = half_bits_to_float(v >> 16);
-            } else {
-                const int e = wd - 1;                       // word 0..7 of the block's qs
-                const int quad = (b & 1) * 2 + (e >> 2);    // 4 quads per pair
-                qs[(((size_t)t * 4 + quad) * np + (b >> 1)) * 4 + (e & 3)] = v;
-            }
-        }
-    }
     __syncthreads();
-
-    const int R = p.R;
-    const int G = (p.F + R - 1) / R;
-    const int nchunks = (nb + kGemvChunkBlocks - 1) / kGemvChunkBlocks;
-    const size_t rowbytes = (size_t)nb * Fm::bytes;
+    if (p.pdl) ptx::griddep_launch_dependents();  // dependents may start their own weight prefetch
 
     if (warp == kGemvWarps) {
-        // ================= producer warp =================
-        int it = 0;
-        for (int g = blockIdx.x; g < G; g += gridDim.x) {
-            for (int c = 0; c < nchunks; c++, it++) {
-                const int s = it % p.stages;
-                const uint32_t ph = (it / p.stages) & 1;
-                const int cb = min(kGemvChunkBlocks, nb - c * kGemvChunkBlocks);
-                const uint32_t seg = (uint32_t)cb * Fm::bytes;
+        // ================= producer warp: weights do not depend on the previous launch
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = 0; t < ntiles; t++) {
+                const int r0 = r_begin + t * RT;
+                const uint32_t bytes = (uint32_t)(min(RT, r_end - r0) * rowbytes);
                 ptx::mbar_wait(&empty[s], ph ^ 1);
-                if (lane == 0) ptx::mbar_arrive_expect_tx(&full[s], seg * R);
-                __syncwarp();
-                if (lane < R) {
-                    const int f = min(g * R + lane, p.F - 1);
-                    ptx::bulk_g2s(stage0 + (size_t)s * p.stage_bytes + (size_t)lane * seg,
-                                  p.wgt + (size_t)f * rowbytes + (size_t)c * kGemvChunkBlocks * Fm::bytes, seg,
-                                  &full[s]);
-                }
+                ptx::mbar_arrive_expect_tx(&full[s], bytes);
+                ptx::bulk_g2s(stage0 + (size_t)s * p.stage_bytes, p.wgt + (size_t)r0 * rowbytes, bytes, &full[s]);
+                if (++s == p.stages) { s = 0; ph ^= 1; }
             }
         }
         return;
     }
 
     // ================= consumer warps =================
-    const int WPR = kGemvWarps / R;          // warps sharing one row
-    const int row = warp / WPR, sub = warp - row * WPR;
-    float acc[TT];
-#pragma unroll
-    for (int t = 0; t < TT; t++) acc[t] = 0.f;
+    if (p.pdl) ptx::griddep_wait();  // activations / C may belong to the previous launch
+    const int WPR = p.WPR;
+    const int rpp = kGemvWarps / WPR;            // rows per pass
+    const int rslot = warp / WPR, sub = warp - rslot * WPR;
 
-    int it = 0, gpar = 0;
-    for (int g = blockIdx.x; g < G; g += gridDim.x, gpar ^= 1) {
-        for (int c = 0; c < nchunks; c++, it++) {
-            const int s = it % p.stages;
-            const uint32_t ph = (it / p.stages) & 1;
-            const int cb = min(kGemvChunkBlocks, nb - c * kGemvChunkBlocks);
-            const int npc = cb >> 1;
-            const int pair0 = (c * kGemvChunkBlocks) >> 1;
-            ptx::mbar_wait(&full[s], ph);
-            const uint8_t* rowp = stage0 + (size_t)s * p.stage_bytes + (size_t)row * cb * Fm::bytes;
-            for (int pp = sub * 32 + lane; pp < npc; pp += WPR * 32) {
-                uint32_t x[Pair<WT>::words];
-                uint32_t w[2][8];
-                WScale ws[2];
-                load_pair<WT>(rowp + (size_t)pp * (2 * Fm::bytes), x);
-                expand_pair<WT>(x, w, ws);
-                const int pg = pair0 + pp;
+    ActPair areg[PPL > 0 ? TT : 1][PPL > 0 ? PPL : 1];
+    if constexpr (PPL > 0) {
+        // one coalesced pass global -> smem (every word once per CTA), then each lane lifts the
+        // pairs it owns into registers for the rest of the kernel
+        const uint32_t* a32 = reinterpret_cast<const uint32_t*>(p.act);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(a_raw);
+        const int total = TT * nb * 9;
+        for (int i = tid; i < total; i += kGemvWarps * 32) dst[i] = __ldg(a32 + i);
+        ptx::bar_sync(1, kGemvWarps * 32);
 #pragma unroll
-                for (int t = 0; t < TT; t++) {
-                    const float4 sc = a_scale[(size_t)t * np + pg];
-                    int a0[8], a1[8];
-                    {
-                        const uint4 q0 = a_qs[((size_t)t * 4 + 0) * np + pg];
-                        const uint4 q1 = a_qs[((size_t)t * 4 + 1) * np + pg];
-                        const uint4 q2 = a_qs[((size_t)t * 4 + 2) * np + pg];
-                        const uint4 q3 = a_qs[((size_t)t * 4 + 3) * np + pg];
-                        a0[0] = q0.x; a0[1] = q0.y; a0[2] = q0.z; a0[3] = q0.w;
-                        a0[4] = q1.x; a0[5] = q1.y; a0[6] = q1.z; a0[7] = q1.w;
-                        a1[0] = q2.x; a1[1] = q2.y; a1[2] = q2.z; a1[3] = q2.w;
-                        a1[4] = q3.x; a1[5] = q3.y; a1[6] = q3.z; a1[7] = q3.w;
+        for (int j = 0; j < PPL; j++) {
+            const int pg = (j * WPR + sub) * 32 + lane;
+#pragma unroll
+            for (int t = 0; t < TT; t++) {
+                if (pg < np) {
+                    const uint32_t* w = dst + ((size_t)t * nb + 2 * pg) * 9;
+#pragma unroll
+                    for (int b = 0; b < 2; b++) {
+                        const uint32_t ds = w[9 * b];
+                        areg[t][j].s[b] = prep_act_scale<WT, kMsExact>(half_bits_to_float(ds), half_bits_to_float(ds >> 16));
+#pragma unroll
+                        for (int i = 0; i < 8; i++) areg[t][j].q[b][i] = (int)w[9 * b + 1 + i];
                     }
-                    const int s0 = block_sumi<WT>(w[0], a0);
-                    const int s1 = block_sumi<WT>(w[1], a1);
-                    acc[t] = fold_block<WT, kMsExact>(acc[t], s0, ws[0], ActScale{sc.x, sc.y});
-                    acc[t] = fold_block<WT, kMsExact>(acc[t], s1, ws[1], ActScale{sc.z, sc.w});
                 }
             }
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&empty[s]);
         }
-        // ---- row group finished: combine lanes, then the warps of each row
-        float* rbuf = red + gpar * (kGemvWarps * 8);
-#pragma unroll
-        for (int t = 0; t < TT; t++) {
-            float v = acc[t];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) rbuf[warp * 8 + t] = v;
-            acc[t] = 0.f;
+    } else {
+        // stage q8_1 AoS -> quad-interleaved SoA + fp32 scales (consumer warps only)
+        const uint32_t* a32 = reinterpret_cast<const uint32_t*>(p.act);
+        float* sc = reinterpret_cast<float*>(a_scale);
+        uint32_t* qs = reinterpret_cast<uint32_t*>(a_qs);
+        const int total = TT * nb * 9;
+        for (int i = tid; i < total; i += kGemvWarps * 32) {
+            const int blk = i / 9, wd = i - blk * 9;
+            const int t = blk / nb, b = blk - t * nb;
+            const uint32_t v = __ldg(a32 + i);
+            if (wd == 0) {
+                const ActScale ps = prep_act_scale<WT, kMsExact>(half_bits_to_float(v), half_bits_to_float(v >> 16));
+                float* d = sc + ((size_t)t * np + (b >> 1)) * 4 + (b & 1) * 2;
+                d[0] = ps.d;
+                d[1] = ps.s;
+            } else {
+                const int e = wd - 1;
+                const int quad = (b & 1) * 2 + (e >> 2);
+                qs[(((size_t)t * 4 + quad) * np + (b >> 1)) * 4 + (e & 3)] = v;
+            }
         }
         ptx::bar_sync(1, kGemvWarps * 32);
-        if (tid < R * TT) {
-            const int r = tid / TT, t = tid - r * TT;
-            float v = 0.f;
-            for (int k = 0; k < WPR; k++) v += rbuf[(r * WPR + k) * 8 + t];
-            const int f = g * R + r;
-            if (f < p.F) p.C[(int64_t)t * p.ldc_t + (int64_t)f * p.ldc_f] = v;
+    }
+
+    int s = 0, spar = 0;
+    uint32_t ph = 0;
+    const int npl = (PPL > 0) ? PPL : (np + WPR * 32 - 1) / (WPR * 32);  // pairs per lane
+    for (int t = 0; t < ntiles; t++) {
+        const int r0 = r_begin + t * RT;
+        const int rows = min(RT, r_end - r0);
+        ptx::mbar_wait(&full[s], ph);
+        const uint8_t* tile = stage0 + (size_t)s * p.stage_bytes;
+        for (int pass = 0; pass * rpp < rows; pass++) {
+            const int r = pass * rpp + rslot;
+            float acc[TT];
+#pragma unroll
+            for (int tt = 0; tt < TT; tt++) acc[tt] = 0.f;
+            if (r < rows) {
+                const uint8_t* rowp = tile + (size_t)r * rowbytes;
+                auto do_pair = [&](int j, int pg) {
+                    uint32_t x[Pair<WT>::words];
+                    uint32_t w[2][8];
+                    WScale ws[2];
+                    load_pair<WT>(rowp + (size_t)pg * (2 * Fm::bytes), x);
+                    expand_pair<WT>(x, w, ws);
+#pragma unroll
+                    for (int tt = 0; tt < TT; tt++) {
+                        if constexpr (PPL > 0) {
+                            const ActPair& a = areg[tt][j];
+                            acc[tt] = fold_block_pre<WT>(acc[tt], block_sumi<WT>(w[0], a.q[0]), ws[0], a.s[0]);
+                            acc[tt] = fold_block_pre<WT>(acc[tt], block_sumi<WT>(w[1], a.q[1]), ws[1], a.s[1]);
+                        } else {
+                            const float4 sc = a_scale[(size_t)tt * np + pg];
+                            int a0[8], a1[8];
+                            const uint4 q0 = a_qs[((size_t)tt * 4 + 0) * np + pg];
+                            const uint4 q1 = a_qs[((size_t)tt * 4 + 1) * np + pg];
+                            const uint4 q2 = a_qs[((size_t)tt * 4 + 2) * np + pg];
+                            const uint4 q3 = a_qs[((size_t)tt * 4 + 3) * np + pg];
+                            a0[0] = q0.x; a0[1] = q0.y; a0[2] = q0.z; a0[3] = q0.w;
+                            a0[4] = q1.x; a0[5] = q1.y; a0[6] = q1.z; a0[7] = q1.w;
+                            a1[0] = q2.x; a1[1] = q2.y; a1[2] = q2.z; a1[3] = q2.w;
+                            a1[4] = q3.x; a1[5] = q3.y; a1[6] = q3.z; a1[7] = q3.w;
+                            acc[tt] = fold_block_pre<WT>(acc[tt], block_sumi<WT>(w[0], a0), ws[0], ActScale{sc.x, sc.y});
+                            acc[tt] = fold_block_pre<WT>(acc[tt], block_sumi<WT>(w[1], a1), ws[1], ActScale{sc.z, sc.w});
+                        }
+                    }
+                };
+                if constexpr (PPL > 0) {
+#pragma unroll
+                    for (int j = 0; j < PPL; j++) {
+                        const int pg = (j * WPR + sub) * 32 + lane;
+                        if (pg < np) do_pair(j, pg);
+                    }
+                } else {
+                    for (int j = 0; j < npl; j++) {
+                        const int pg = (j * WPR + sub) * 32 + lane;
+                        if (pg < np) do_pair(0, pg);
+                    }
+                }
+            }
+#pragma unroll
+            for (int tt = 0; tt < TT; tt++) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[tt] += __shfl_xor_sync(0xffffffffu, acc[tt], o);
+            }
+            if (WPR == 1) {
+                if (r < rows && lane < TT) {
+                    float v = acc[0];
+#pragma unroll
+                    for (int tt = 1; tt < TT; tt++) v = (lane == tt) ? acc[tt] : v;
+                    p.C[(int64_t)lane * p.ldc_t + (int64_t)(r0 + r) * p.ldc_f] = v;
+                }
+            } else {
+                float* sl = slots + spar * (kGemvWarps * 8);
+                if (lane == 0) {
+#pragma unroll
+                    for (int tt = 0; tt < TT; tt++) sl[warp * 8 + tt] = acc[tt];
+                }
+                ptx::bar_sync(1, kGemvWarps * 32);
+                if (tid < rpp * TT) {
+                    const int rs = tid / TT, tt = tid - rs * TT;
+                    const int rr = pass * rpp + rs;
+                    if (rr < rows) {
+                        float v = 0.f;
+                        for (int k = 0; k < WPR; k++) v += sl[(rs * WPR + k) * 8 + tt];
+                        p.C[(int64_t)tt * p.ldc_t + (int64_t)(r0 + rr) * p.ldc_f] = v;
+                    }
+                }
+                spar ^= 1;
+            }
         }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&empty[s]);
+        if (++s == p.stages) { s = 0; ph ^= 1; }
     }
 }
 
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
-static size_t gemv_act_bytes(int tt, int nb) { return (size_t)tt * nb * 40; }
+struct GemvPlan {
+    int tt;      // tokens per pass
+    int ppl;     // pairs per lane held in registers (0: activations in smem)
+    int wpr;     // warps per row
+    int rt;      // rows per tile
+    int stages, stage_bytes;
+    size_t smem;
+};
 
-// Can the fast path take this problem at all?  Rows must be bulk-copyable.
+// Rows must be bulk-copyable: whole rows 16-byte multiples from a 16-byte aligned base.
 bool gemv_supported(int wtype, const void* act, const void* wgt, int F, int K) {
     const int nb = K / 32;
     const size_t rowbytes = (size_t)nb * block_bytes(wtype);
     if (F < 1 || nb < 2 || (nb & 1)) return false;
-    if (rowbytes % 16 != 0) return false;
-    if (((size_t)kGemvChunkBlocks * block_bytes(wtype)) % 16 != 0) return false;
+    if (rowbytes % 16 != 0 || rowbytes > 64 * 1024) return false;
     if (reinterpret_cast<uintptr_t>(wgt) % 16 != 0) return false;
     if (reinterpret_cast<uintptr_t>(act) % 4 != 0) return false;
-    // at least one token's activations plus two stages must fit
-    const size_t tile = (size_t)min(nb, kGemvChunkBlocks) * block_bytes(wtype);
-    return 1024 + gemv_act_bytes(1, nb) + 128 + 2 * ((tile + 127) / 128 * 128) <= (size_t)kGemvSmemBudget;
+    return true;
 }
 
-// Tokens per pass (<= 8) that still leave room for a useful ring.
-int gemv_tokens_per_pass(int wtype, int T, int K) {
-    const int nb = K / 32;
-    const size_t tile = (size_t)min(nb, kGemvChunkBlocks) * block_bytes(wtype) * 4;
-    int tt = min(T, 8);
-    while (tt > 1 && 1024 + gemv_act_bytes(tt, nb) + 128 + 3 * tile > (size_t)kGemvSmemBudget) tt--;
-    return tt;
+static bool gemv_plan(int wtype, int T, int F, int K, int grid, bool pdl, GemvPlan* pl) {
+    const int nb = K / 32, np = nb / 2;
+    const size_t rowbytes = (size_t)nb * block_bytes(wtype);
+    for (int tt = min(T, 8); tt >= 1; tt--) {
+        // register-resident activations when T*PPL <= 6 with the fewest warps per row
+        int ppl = 0, wpr = 1;
+        for (int w = 1; w <= kGemvWarps; w <<= 1) {
+            const int need = (np + 32 * w - 1) / (32 * w);
+            if (need * tt <= 6) { ppl = need; wpr = w; break; }
+        }
+        if (ppl == 0) {  // smem activations: spread long rows over more warps
+            wpr = 1;
+            while (wpr < kGemvWarps && np > 64 * wpr) wpr <<= 1;
+        }
+        const int rpp = kGemvWarps / wpr;
+        int rt = rpp;
+        while (rt < 8 && (size_t)(2 * rt) * rowbytes <= (size_t)kGemvTileTarget) rt <<= 1;
+        const int stage_bytes = (int)(((size_t)rt * rowbytes + 127) / 128 * 128);
+        const size_t fixed = 1024 + (size_t)tt * nb * (ppl == 0 ? 40 : 36) + 128;
+        if (fixed + 2 * (size_t)stage_bytes > (size_t)kGemvSmemBudget) continue;
+        int stages = (int)(((size_t)kGemvSmemBudget - fixed) / stage_bytes);
+        stages = max(2, min(kGemvMaxStages, stages));
+        // no point in more ring than one CTA can ever use; with PDL stay under half an SM's
+        // shared memory when possible so the next launch's CTA can move in early
+        const int rows_per_cta = (F + grid - 1) / grid;
+        stages = max(2, min(stages, (rows_per_cta + rt - 1) / rt));
+        if (pdl) {
+            const int cap = (int)((110 * 1024 - (long)fixed) / stage_bytes);
+            if (cap >= 2) stages = min(stages, cap);
+        }
+        *pl = {tt, ppl, wpr, rt, stages, stage_bytes, fixed + (size_t)stages * stage_bytes};
+        return true;
+    }
+    return false;
 }
 
-template <int WT, int TT>
-static cudaError_t launch_gemv_tt(const GemvParams& p, size_t smem, int grid, bool ms_exact, cudaStream_t st) {
+template <int WT, int TT, int PPL>
+static cudaError_t launch_gemv_inst(const GemvParams& p, size_t smem, int grid, bool ms_exact, cudaStream_t st) {
+    auto launch = [&](auto kernel) -> cudaError_t {
+        static size_t attr_set = 0;  // per instantiation; grows monotonically
+        if (smem > attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            attr_set = smem;
+        }
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kGemvThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = p.pdl ? 1 : 0;
+        return cudaLaunchKernelEx(&cfg, kernel, p);
+    };
     cudaError_t e;
-    if (ms_exact) {
-        auto k = gemv_kernel<WT, TT, true>;
-        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k<<<grid, kGemvThreads, smem, st>>>(p);
+    if constexpr (Fmt<WT>::m >= 0) {  // only q4_1 / q5_1 have an m*s term
+        e = ms_exact ? launch(gemv_kernel<WT, TT, PPL, true>) : launch(gemv_kernel<WT, TT, PPL, false>);
     } else {
-        auto k = gemv_kernel<WT, TT, false>;
-        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k<<<grid, kGemvThreads, smem, st>>>(p);
+        e = launch(gemv_kernel<WT, TT, PPL, false>);
     }
     note_launch();
-    return cudaGetLastError();
+    return e;
 }
 
 template <int WT>
-static cudaError_t launch_gemv_wt(int tt, const GemvParams& p, size_t smem, int grid, bool ms, cudaStream_t st) {
-    switch (tt) {
-    case 1: return launch_gemv_tt<WT, 1>(p, smem, grid, ms, st);
-    case 2: return launch_gemv_tt<WT, 2>(p, smem, grid, ms, st);
-    case 3: return launch_gemv_tt<WT, 3>(p, smem, grid, ms, st);
-    case 4: return launch_gemv_tt<WT, 4>(p, smem, grid, ms, st);
-    case 5: return launch_gemv_tt<WT, 5>(p, smem, grid, ms, st);
-    case 6: return launch_gemv_tt<WT, 6>(p, smem, grid, ms, st);
-    case 7: return launch_gemv_tt<WT, 7>(p, smem, grid, ms, st);
-    case 8: return launch_gemv_tt<WT, 8>(p, smem, grid, ms, st);
-    default: return cudaErrorInvalidValue;
-    }
+static cudaError_t launch_gemv_wt(const GemvPlan& pl, const GemvParams& p, int grid, bool ms, cudaStream_t st) {
+#define QG_CASE(TTv, PPLv) \
+    if (pl.tt == TTv && pl.ppl == PPLv) return launch_gemv_inst<WT, TTv, PPLv>(p, pl.smem, grid, ms, st);
+    QG_CASE(1, 1) QG_CASE(1, 2) QG_CASE(1, 3) QG_CASE(1, 4) QG_CASE(1, 5) QG_CASE(1, 6)
+    QG_CASE(2, 1) QG_CASE(2, 2) QG_CASE(2, 3)
+    QG_CASE(3, 1) QG_CASE(3, 2)
+    QG_CASE(4, 1) QG_CASE(5, 1) QG_CASE(6, 1)
+    QG_CASE(1, 0) QG_CASE(2, 0) QG_CASE(3, 0) QG_CASE(4, 0) QG_CASE(5, 0) QG_CASE(6, 0) QG_CASE(7, 0) QG_CASE(8, 0)
+#undef QG_CASE
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
                         int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t st) {
     const int nb = K / 32;
-    const int bs = block_bytes(wtype);
     const bool ms = flags & QGEMM_MS_EXACT;
-    const int tpp = gemv_tokens_per_pass(wtype, T, K);
-
-    // rows per tile: as many as keeps >= 3 row groups per SM (load balance beats tile size)
-    int R = 4;
-    while (R > 1 && (F + R - 1) / R < 3 * num_sms) R >>= 1;
-    const int cb = min(nb, kGemvChunkBlocks);
-    const int stage_bytes = (int)(((size_t)R * cb * bs + 127) / 128 * 128);
-    const int G = (F + R - 1) / R;
-    const int grid = min(G, num_sms);
-
-    for (int t0 = 0; t0 < T; t0 += tpp) {
-        const int tt = min(tpp, T - t0);
-        const size_t fixed = 1024 + gemv_act_bytes(tt, nb) + 128;
-        int stages = (int)(((size_t)kGemvSmemBudget - fixed) / stage_bytes);
-        stages = max(2, min(kGemvMaxStages, stages));
+    GemvPlan pl;
+    const int grid = min(F, num_sms);
+    const bool pdl = flags & QGEMM_WEIGHTS_STATIC;
+    if (!gemv_plan(wtype, T, F, K, grid, pdl, &pl)) return cudaErrorInvalidValue;
+    for (int t0 = 0; t0 < T; t0 += pl.tt) {
+        GemvPlan cur = pl;
+        if (T - t0 < pl.tt && !gemv_plan(wtype, T - t0, F, K, grid, pdl, &cur)) return cudaErrorInvalidValue;
         GemvParams p;
         p.act = (const uint8_t*)act + (size_t)t0 * nb * kQ81Bytes;
         p.wgt = (const uint8_t*)wgt;
         p.C = C + (int64_t)t0 * ldc_t;
         p.F = F; p.nb = nb; p.ldc_t = ldc_t; p.ldc_f = ldc_f;
-        p.R = R; p.stages = stages; p.stage_bytes = stage_bytes;
-        const size_t smem = fixed + (size_t)stages * stage_bytes;
+        p.RT = cur.rt; p.WPR = cur.wpr; p.stages = cur.stages; p.stage_bytes = cur.stage_bytes;
+        p.pdl = pdl ? 1 : 0;
         cudaError_t e;
         switch (wtype) {
-        case QGEMM_TYPE_Q4_0: e = launch_gemv_wt<QGEMM_TYPE_Q4_0>(tt, p, smem, grid, ms, st); break;
-        case QGEMM_TYPE_Q4_1: e = launch_gemv_wt<QGEMM_TYPE_Q4_1>(tt, p, smem, grid, ms, st); break;
-        case QGEMM_TYPE_Q5_0: e = launch_gemv_wt<QGEMM_TYPE_Q5_0>(tt, p, smem, grid, ms, st); break;
-        case QGEMM_TYPE_Q5_1: e = launch_gemv_wt<QGEMM_TYPE_Q5_1>(tt, p, smem, grid, ms, st); break;
-        case QGEMM_TYPE_Q8_0: e = launch_gemv_wt<QGEMM_TYPE_Q8_0>(tt, p, smem, grid, ms, st); break;
+        case QGEMM_TYPE_Q4_0: e = launch_gemv_wt<QGEMM_TYPE_Q4_0>(cur, p, grid, ms, st); break;
+        case QGEMM_TYPE_Q4_1: e = launch_gemv_wt<QGEMM_TYPE_Q4_1>(cur, p, grid, ms, st); break;
+        case QGEMM_TYPE_Q5_0: e = launch_gemv_wt<QGEMM_TYPE_Q5_0>(cur, p, grid, ms, st); break;
+        case QGEMM_TYPE_Q5_1: e = launch_gemv_wt<QGEMM_TYPE_Q5_1>(cur, p, grid, ms, st); break;
+        case QGEMM_TYPE_Q8_0: e = launch_gemv_wt<QGEMM_TYPE_Q8_0>(cur, p, grid, ms, st); break;
         default: e = cudaErrorInvalidValue;
         }
         if (e != cudaSuccess) return e;

@@ -134,6 +134,30 @@ __device__ __forceinline__ float fold_block(float acc, int sumi, WScale w, ActSc
     }
 }
 
+// Same fold with the activation-only factor hoisted out of the row loop: the decode path
+// keeps one activation block in registers for thousands of weight rows, so
+//   q4_0/q5_0:  a.s := -(off * s_a)         (exact: power-of-two times a half)
+//   q4_1/q5_1:  a.s := s_a / 4  (or s_a with QGEMM_MS_EXACT; (m*s)/4 == m*(s/4) exactly)
+// is computed once by prep_act_scale().  Rounding sequence per block is unchanged.
+template <int WT, bool kMsExact>
+__device__ __forceinline__ ActScale prep_act_scale(float d_a, float s_a) {
+    if constexpr (WT == QGEMM_TYPE_Q4_0) return {d_a, -__fmul_rn(8.0f, s_a)};
+    else if constexpr (WT == QGEMM_TYPE_Q5_0) return {d_a, -__fmul_rn(16.0f, s_a)};
+    else if constexpr (WT == QGEMM_TYPE_Q4_1 || WT == QGEMM_TYPE_Q5_1) return {d_a, kMsExact ? s_a : __fmul_rn(s_a, 0.25f)};
+    else return {d_a, 0.0f};
+}
+template <int WT>
+__device__ __forceinline__ float fold_block_pre(float acc, int sumi, WScale w, ActScale a) {
+    const float fs = __int2float_rn(sumi);
+    if constexpr (WT == QGEMM_TYPE_Q4_0 || WT == QGEMM_TYPE_Q5_0) {
+        return __fmaf_rn(w.d, __fmaf_rn(a.d, fs, a.s), acc);
+    } else if constexpr (WT == QGEMM_TYPE_Q4_1 || WT == QGEMM_TYPE_Q5_1) {
+        return __fadd_rn(acc, __fmaf_rn(__fmul_rn(w.d, a.d), fs, __fmul_rn(w.m, a.s)));
+    } else {
+        return __fmaf_rn(__fmul_rn(w.d, a.d), fs, acc);
+    }
+}
+
 template <int WT>
 __device__ __forceinline__ WScale load_wscale(const uint8_t* blk) {
     WScale s;
