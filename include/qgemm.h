@@ -88,6 +88,8 @@ QGEMM_API int64_t qgemm_launch_count(void);
 QGEMM_API void qgemm_reset_launch_count(void);
 /* QGEMM_PATH_* actually taken by the calling thread's most recent qgemm_gemm*(). */
 QGEMM_API uint32_t qgemm_last_path(void);
+/* Text of the calling thread's most recent QGEMM_E_CUDA failure (CUDA error name and where). */
+QGEMM_API const char *qgemm_last_error_detail(void);
 
 /* ---- quantize / dequantize -------------------------------------------------- */
 /*

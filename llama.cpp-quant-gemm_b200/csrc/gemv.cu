@@ -7,8 +7,8 @@
 // their GPU's DRAM bandwidth.
 //
 // Design (B200):
-//   * one persistent CTA per SM owns a CONTIGUOUS span of weight rows (F split
-//     to one-row granularity: at most 1 row of imbalance per SM); since rows are
+//   * two CTAs per SM (<= 110 KB smem, <= 113 registers each), every CTA owns a CONTIGUOUS
+//     span of weight rows (F split to one-row granularity: at most 1 row of imbalance); since rows are
 //     contiguous in memory the span is one byte range, cut into tiles of RT rows
 //   * a producer warp streams tiles HBM -> smem with ONE 1-D bulk async copy
 //     per tile (cp.async.bulk, the TMA engine) through a ring of mbarrier-guarded
@@ -17,13 +17,15 @@
 //     tile, a lane owns fixed K positions: pairs of adjacent blocks (a pair starts
 //     4-byte aligned in every format, a single 18/22/34-byte block does not)
 //   * because a lane's K positions never change, its q8_1 activations live in
-//     REGISTERS for the whole kernel (T*PPL <= 6 pairs); larger T keep them in smem,
+//     REGISTERS for the whole kernel (T*PPL <= 3 pairs); larger T keep them in smem,
 //     re-laid out so consecutive lanes read consecutive 16-byte quads
 //   * integer dot by dp4a on UN-offset weights, then the reference's exact
 //     per-block fold (qgemm_common.cuh); lane-sequential over K, butterfly across
 //     lanes, fixed order across the warps of a row -> deterministic
 //   * optional programmatic dependent launch (QGEMM_WEIGHTS_STATIC): the weight
 //     prefetch of launch n+1 overlaps the tail of launch n
+#include <cstdlib>
+
 #include "ptx.cuh"
 #include "qgemm_common.cuh"
 
@@ -32,7 +34,9 @@ namespace qgemm {
 constexpr int kGemvWarps = 8;                        // consumer warps
 constexpr int kGemvThreads = (kGemvWarps + 1) * 32;  // + 1 producer warp
 constexpr int kGemvMaxStages = 8;
-constexpr int kGemvSmemBudget = 208 * 1024;
+constexpr int kGemvActOff = (128 + 2 * kGemvWarps * 8 * 4 + 127) / 128 * 128;  // barriers + slots
+constexpr int kGemvSmemBudget = 110 * 1024;          // two CTAs per SM, always
+constexpr int kGemvCtasPerSm = 2;
 constexpr int kGemvTileTarget = 24 * 1024;           // bytes per tile we aim for
 
 // ---- a pair of adjacent weight blocks as 32-bit words --------------------------
@@ -61,11 +65,26 @@ __device__ __forceinline__ void load_pair(const uint8_t* p, uint32_t (&x)[Pair<W
     }
 }
 
+// 4-bit: high nibbles stay in place as 16*hi (a valid u8 < 256); sumi4() undoes the factor exactly.
 __device__ __forceinline__ void expand4(const uint32_t (&q)[4], uint32_t (&w)[8]) {
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         w[i] = q[i] & 0x0f0f0f0fu;
-        w[i + 4] = (q[i] >> 4) & 0x0f0f0f0fu;
+        w[i + 4] = q[i] & 0xf0f0f0f0u;
+    }
+}
+template <int WT>
+__device__ __forceinline__ int pair_sumi(const uint32_t (&w)[8], const int (&a)[8]) {
+    if constexpr (Fmt<WT>::bits == 4) {
+        int lo = 0, hi = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            lo = dp4a_us(w[i], a[i], lo);
+            hi = dp4a_us(w[i + 4], a[i + 4], hi);
+        }
+        return lo + (hi >> 4);  // hi is a multiple of 16: exact
+    } else {
+        return block_sumi<WT>(w, a);
     }
 }
 __device__ __forceinline__ void expand5(const uint32_t (&q)[4], uint32_t qh, uint32_t (&w)[8]) {
@@ -136,11 +155,14 @@ struct GemvParams {
     int stages;
     int stage_bytes;      // 128-byte multiple
     int pdl;              // programmatic dependent launch in use
+    int nocompute;        // tuning aid: stream the tiles, skip the math (memory-system ceiling)
 };
 
 // PPL > 0: activations in registers, PPL pairs per lane.  PPL == 0: activations in smem.
-template <int WT, int TT, int PPL, bool kMsExact>
-__global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const GemvParams p) {
+// kFull: every lane owns exactly PPL valid pairs (np == PPL * WPR * 32): no bounds checks, so the
+// compiler can interleave the independent pairs of a row.
+template <int WT, int TT, int PPL, bool kMsExact, bool kFull>
+__global__ void __launch_bounds__(kGemvThreads, kGemvCtasPerSm) gemv_kernel(const GemvParams p) {
     using Fm = Fmt<WT>;
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -151,11 +173,11 @@ __global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const GemvParams 
     uint64_t* empty = full + kGemvMaxStages;                     // [kGemvMaxStages]
     float* slots = reinterpret_cast<float*>(smem + 128);         // [2][kGemvWarps][8] cross-warp partials
     // PPL > 0 : raw q8_1 copy [TT][nb][36 B];  PPL == 0 : [TT][np] float4 scales + [TT][4][np] quads
-    uint8_t* a_raw = smem + 1024;
-    float4* a_scale = reinterpret_cast<float4*>(smem + 1024);
-    uint4* a_qs = reinterpret_cast<uint4*>(smem + 1024 + (size_t)TT * np * 16);
+    uint8_t* a_raw = smem + kGemvActOff;
+    float4* a_scale = reinterpret_cast<float4*>(smem + kGemvActOff);
+    uint4* a_qs = reinterpret_cast<uint4*>(smem + kGemvActOff + (size_t)TT * np * 16);
     const uint32_t act_bytes = (PPL > 0) ? (uint32_t)TT * nb * 36u : (uint32_t)TT * nb * 40u;
-    uint8_t* stage0 = smem + ((1024u + act_bytes + 127u) & ~127u);
+    uint8_t* stage0 = smem + (((uint32_t)kGemvActOff + act_bytes + 127u) & ~127u);
 
     // ---- this CTA's contiguous span of weight rows
     const int r_begin = (int)(((int64_t)p.F * blockIdx.x) / gridDim.x);
@@ -211,7 +233,7 @@ __global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const GemvParams 
             const int pg = (j * WPR + sub) * 32 + lane;
 #pragma unroll
             for (int t = 0; t < TT; t++) {
-                if (pg < np) {
+                if (kFull || pg < np) {
                     const uint32_t* w = dst + ((size_t)t * nb + 2 * pg) * 9;
 #pragma unroll
                     for (int b = 0; b < 2; b++) {
@@ -255,7 +277,7 @@ __global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const GemvParams 
         const int rows = min(RT, r_end - r0);
         ptx::mbar_wait(&full[s], ph);
         const uint8_t* tile = stage0 + (size_t)s * p.stage_bytes;
-        for (int pass = 0; pass * rpp < rows; pass++) {
+        for (int pass = 0; pass * rpp < rows && !p.nocompute; pass++) {
             const int r = pass * rpp + rslot;
             float acc[TT];
 #pragma unroll
@@ -272,8 +294,8 @@ __global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const GemvParams 
                     for (int tt = 0; tt < TT; tt++) {
                         if constexpr (PPL > 0) {
                             const ActPair& a = areg[tt][j];
-                            acc[tt] = fold_block_pre<WT>(acc[tt], block_sumi<WT>(w[0], a.q[0]), ws[0], a.s[0]);
-                            acc[tt] = fold_block_pre<WT>(acc[tt], block_sumi<WT>(w[1], a.q[1]), ws[1], a.s[1]);
+                            acc[tt] = fold_block_pre<WT>(acc[tt], pair_sumi<WT>(w[0], a.q[0]), ws[0], a.s[0]);
+                            acc[tt] = fold_block_pre<WT>(acc[tt], pair_sumi<WT>(w[1], a.q[1]), ws[1], a.s[1]);
                         } else {
                             const float4 sc = a_scale[(size_t)tt * np + pg];
                             int a0[8], a1[8];
@@ -285,8 +307,8 @@ __global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const GemvParams 
                             a0[4] = q1.x; a0[5] = q1.y; a0[6] = q1.z; a0[7] = q1.w;
                             a1[0] = q2.x; a1[1] = q2.y; a1[2] = q2.z; a1[3] = q2.w;
                             a1[4] = q3.x; a1[5] = q3.y; a1[6] = q3.z; a1[7] = q3.w;
-                            acc[tt] = fold_block_pre<WT>(acc[tt], block_sumi<WT>(w[0], a0), ws[0], ActScale{sc.x, sc.y});
-                            acc[tt] = fold_block_pre<WT>(acc[tt], block_sumi<WT>(w[1], a1), ws[1], ActScale{sc.z, sc.w});
+                            acc[tt] = fold_block_pre<WT>(acc[tt], pair_sumi<WT>(w[0], a0), ws[0], ActScale{sc.x, sc.y});
+                            acc[tt] = fold_block_pre<WT>(acc[tt], pair_sumi<WT>(w[1], a1), ws[1], ActScale{sc.z, sc.w});
                         }
                     }
                 };
@@ -294,7 +316,7 @@ __global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const GemvParams 
 #pragma unroll
                     for (int j = 0; j < PPL; j++) {
                         const int pg = (j * WPR + sub) * 32 + lane;
-                        if (pg < np) do_pair(j, pg);
+                        if (kFull || pg < np) do_pair(j, pg);
                     }
                 } else {
                     for (int j = 0; j < npl; j++) {
@@ -371,8 +393,9 @@ static bool gemv_plan(int wtype, int T, int F, int K, int grid, bool pdl, GemvPl
         int ppl = 0, wpr = 1;
         for (int w = 1; w <= kGemvWarps; w <<= 1) {
             const int need = (np + 32 * w - 1) / (32 * w);
-            if (need * tt <= 6) { ppl = need; wpr = w; break; }
+            if (need * tt <= 3) { ppl = need; wpr = w; break; }  // <= 60 activation registers
         }
+        if (getenv("QGEMM_GEMV_FORCE_SMEM")) ppl = 0;  // tuning aid
         if (ppl == 0) {  // smem activations: spread long rows over more warps
             wpr = 1;
             while (wpr < kGemvWarps && np > 64 * wpr) wpr <<= 1;
@@ -380,8 +403,9 @@ static bool gemv_plan(int wtype, int T, int F, int K, int grid, bool pdl, GemvPl
         const int rpp = kGemvWarps / wpr;
         int rt = rpp;
         while (rt < 8 && (size_t)(2 * rt) * rowbytes <= (size_t)kGemvTileTarget) rt <<= 1;
+        if (const char* e = getenv("QGEMM_GEMV_RT")) rt = max(rpp, atoi(e) / rpp * rpp);  // tuning aid
         const int stage_bytes = (int)(((size_t)rt * rowbytes + 127) / 128 * 128);
-        const size_t fixed = 1024 + (size_t)tt * nb * (ppl == 0 ? 40 : 36) + 128;
+        const size_t fixed = kGemvActOff + (size_t)tt * nb * (ppl == 0 ? 40 : 36) + 128;
         if (fixed + 2 * (size_t)stage_bytes > (size_t)kGemvSmemBudget) continue;
         int stages = (int)(((size_t)kGemvSmemBudget - fixed) / stage_bytes);
         stages = max(2, min(kGemvMaxStages, stages));
@@ -389,10 +413,8 @@ static bool gemv_plan(int wtype, int T, int F, int K, int grid, bool pdl, GemvPl
         // shared memory when possible so the next launch's CTA can move in early
         const int rows_per_cta = (F + grid - 1) / grid;
         stages = max(2, min(stages, (rows_per_cta + rt - 1) / rt));
-        if (pdl) {
-            const int cap = (int)((110 * 1024 - (long)fixed) / stage_bytes);
-            if (cap >= 2) stages = min(stages, cap);
-        }
+        (void)pdl;
+        if (const char* e = getenv("QGEMM_GEMV_STAGES")) stages = max(2, min(kGemvMaxStages, atoi(e)));  // tuning aid
         *pl = {tt, ppl, wpr, rt, stages, stage_bytes, fixed + (size_t)stages * stage_bytes};
         return true;
     }
@@ -401,12 +423,13 @@ static bool gemv_plan(int wtype, int T, int F, int K, int grid, bool pdl, GemvPl
 
 template <int WT, int TT, int PPL>
 static cudaError_t launch_gemv_inst(const GemvParams& p, size_t smem, int grid, bool ms_exact, cudaStream_t st) {
-    auto launch = [&](auto kernel) -> cudaError_t {
-        static size_t attr_set = 0;  // per instantiation; grows monotonically
-        if (smem > attr_set) {
+    auto launch = [&](auto kernel, int variant) -> cudaError_t {
+        static size_t attr_set[4] = {0, 0, 0, 0};  // per (WT,TT,PPL) x variant; grows monotonically
+        size_t& cur = attr_set[variant];
+        if (smem > cur) {
             cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            attr_set = smem;
+            cur = smem;
         }
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(grid);
@@ -421,10 +444,12 @@ static cudaError_t launch_gemv_inst(const GemvParams& p, size_t smem, int grid, 
         return cudaLaunchKernelEx(&cfg, kernel, p);
     };
     cudaError_t e;
+    const bool full = PPL > 0 && (p.nb / 2) == PPL * p.WPR * 32;
     if constexpr (Fmt<WT>::m >= 0) {  // only q4_1 / q5_1 have an m*s term
-        e = ms_exact ? launch(gemv_kernel<WT, TT, PPL, true>) : launch(gemv_kernel<WT, TT, PPL, false>);
+        if (full) e = ms_exact ? launch(gemv_kernel<WT, TT, PPL, true, true>, 2) : launch(gemv_kernel<WT, TT, PPL, false, true>, 3);
+        else e = ms_exact ? launch(gemv_kernel<WT, TT, PPL, true, false>, 1) : launch(gemv_kernel<WT, TT, PPL, false, false>, 0);
     } else {
-        e = launch(gemv_kernel<WT, TT, PPL, false>);
+        e = full ? launch(gemv_kernel<WT, TT, PPL, false, true>, 3) : launch(gemv_kernel<WT, TT, PPL, false, false>, 0);
     }
     note_launch();
     return e;
@@ -434,10 +459,7 @@ template <int WT>
 static cudaError_t launch_gemv_wt(const GemvPlan& pl, const GemvParams& p, int grid, bool ms, cudaStream_t st) {
 #define QG_CASE(TTv, PPLv) \
     if (pl.tt == TTv && pl.ppl == PPLv) return launch_gemv_inst<WT, TTv, PPLv>(p, pl.smem, grid, ms, st);
-    QG_CASE(1, 1) QG_CASE(1, 2) QG_CASE(1, 3) QG_CASE(1, 4) QG_CASE(1, 5) QG_CASE(1, 6)
-    QG_CASE(2, 1) QG_CASE(2, 2) QG_CASE(2, 3)
-    QG_CASE(3, 1) QG_CASE(3, 2)
-    QG_CASE(4, 1) QG_CASE(5, 1) QG_CASE(6, 1)
+    QG_CASE(1, 1) QG_CASE(1, 2) QG_CASE(1, 3) QG_CASE(2, 1) QG_CASE(3, 1)
     QG_CASE(1, 0) QG_CASE(2, 0) QG_CASE(3, 0) QG_CASE(4, 0) QG_CASE(5, 0) QG_CASE(6, 0) QG_CASE(7, 0) QG_CASE(8, 0)
 #undef QG_CASE
     return cudaErrorInvalidValue;
@@ -448,7 +470,7 @@ cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, i
     const int nb = K / 32;
     const bool ms = flags & QGEMM_MS_EXACT;
     GemvPlan pl;
-    const int grid = min(F, num_sms);
+    const int grid = min(F, kGemvCtasPerSm * num_sms);
     const bool pdl = flags & QGEMM_WEIGHTS_STATIC;
     if (!gemv_plan(wtype, T, F, K, grid, pdl, &pl)) return cudaErrorInvalidValue;
     for (int t0 = 0; t0 < T; t0 += pl.tt) {
@@ -461,6 +483,7 @@ cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, i
         p.F = F; p.nb = nb; p.ldc_t = ldc_t; p.ldc_f = ldc_f;
         p.RT = cur.rt; p.WPR = cur.wpr; p.stages = cur.stages; p.stage_bytes = cur.stage_bytes;
         p.pdl = pdl ? 1 : 0;
+        p.nocompute = getenv("QGEMM_GEMV_NOCOMPUTE") ? 1 : 0;
         cudaError_t e;
         switch (wtype) {
         case QGEMM_TYPE_Q4_0: e = launch_gemv_wt<QGEMM_TYPE_Q4_0>(cur, p, grid, ms, st); break;

@@ -1,6 +1,7 @@
 // qgemm_abi.cu -- the extern "C" surface of libqgemm_sm100.so (include/qgemm.h):
 // argument validation, device check, path selection, launch bookkeeping.
 #include <atomic>
+#include <cstdio>
 #include <mutex>
 
 #include "qgemm_common.cuh"
@@ -28,6 +29,12 @@ static std::atomic<int64_t> g_launches{0};
 void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 static thread_local uint32_t t_last_path = 0;
+static thread_local char t_detail[256] = "";
+
+static int cuda_fail(cudaError_t e, const char* where) {
+    snprintf(t_detail, sizeof(t_detail), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
+    return QGEMM_E_CUDA;
+}
 
 struct DeviceInfo {
     int cc_major = -1, cc_minor = -1, sms = 0;
@@ -118,7 +125,7 @@ static int run_gemm(int wtype, const void* act, const void* wgt, float* C, int T
         return QGEMM_E_BADARG;
     }
     t_last_path = path;
-    return e == cudaSuccess ? QGEMM_OK : QGEMM_E_CUDA;
+    return e == cudaSuccess ? QGEMM_OK : cuda_fail(e, "gemm launch");
 }
 
 }  // namespace qgemm
@@ -145,6 +152,7 @@ size_t qgemm_block_bytes(int type) { return (size_t)block_bytes(type); }
 int64_t qgemm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 void qgemm_reset_launch_count(void) { g_launches.store(0, std::memory_order_relaxed); }
 uint32_t qgemm_last_path(void) { return t_last_path; }
+const char* qgemm_last_error_detail(void) { return t_detail; }
 
 int qgemm_quantize_q8_1(const float* x, void* y, int64_t rows, int64_t K, uint32_t flags, void* stream) {
     if (rows < 0 || K < 0 || (K % kQK) != 0) return QGEMM_E_BADARG;

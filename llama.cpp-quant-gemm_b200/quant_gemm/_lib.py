@@ -22,6 +22,7 @@ SYMBOLS = {
     "qgemm_launch_count": (_i64, []),
     "qgemm_reset_launch_count": (None, []),
     "qgemm_last_path": (_u32, []),
+    "qgemm_last_error_detail": (C.c_char_p, []),
     "qgemm_quantize_q8_1": (_i, [_p, _p, _i64, _i64, _u32, _p]),
     "qgemm_quantize_weight": (_i, [_i, _p, _p, _i64, _i64, _u32, _p]),
     "qgemm_dequantize": (_i, [_i, _p, _p, _i64, _i64, _p]),
@@ -57,7 +58,8 @@ def strerror(code: int) -> str:
 
 def raise_on_error(rc: int, what: str) -> None:
     if rc != 0:
-        raise RuntimeError(f"qgemm {what} failed: {strerror(rc)} (code {rc})")
+        detail = lib().qgemm_last_error_detail().decode() if rc == -4 else ""
+        raise RuntimeError(f"qgemm {what} failed: {strerror(rc)} (code {rc}) {detail}")
 
 
 def shard_range(F: int, world: int, rank: int, align: int = 1) -> tuple[int, int]:
