@@ -1,8 +1,447 @@
-// mmq.cu -- prefill path placeholder: filled in by the tcgen05 kernel.
+// mmq.cu -- prefill path (T >= 64): block-quantized GEMM on the 5th-gen tensor cores.
+//
+// Replaces the reference's many-token kernels (include/gemm_cuda_naive.cuh:158-249,
+// gemm_cuda_tiled.cuh:191-269, gemm_cuda_dp4a.cuh:158-403,
+// kernels/gemm/gemm_quant_formats.cuh:312-334), all CUDA-core dp4a/scalar code.
+//
+// One tcgen05.mma kind::i8 instruction has K = 32 for 8-bit operands = exactly one
+// quantization block, so sumi[t,f,b] falls out of each instruction unmodified:
+//   D(TMEM, s32)[128 tokens x BN rows] = A(smem, s8 activations) . B(smem, u8/s8 weights)^T
+// with the weights fed UN-offset (0..15 / 0..31), like the reference's integer sum
+// (include/gemm_reference.h:199-212).  The per-block scale fold
+//   acc[t,f] = fma(d_w, fma(d_a, float(sumi), -8*s_a), acc)       (q4_0; see qgemm_common.cuh)
+// runs on the CUDA cores from registers, in block order b = 0..nb-1, with the exact
+// FMA sequence of the reference GPU kernel -- C is bit-identical to it.
+//
+// Pipeline (one persistent CTA per SM, 12 warps):
+//   warp 0      producer: 1-D bulk async copies (TMA engine) of pre-swizzled operand tiles
+//               + scale slabs into a 4-stage smem ring (stage = 128 K-elements = 4 blocks)
+//   warp 1      one elected thread issues the MMAs; each block gets its own TMEM
+//               accumulator buffer out of a ring of 512/BN, tcgen05.commit -> mbarrier
+//   warp 2      TMEM allocator
+//   warps 4-11  epilogue: tcgen05.ld the s32 tile (lane = token, 64 columns per thread),
+//               release the TMEM buffer at once, fold into 64 fp32 register accumulators
+//
+// Operands come from a prepass (qgemm workspace): q8_1 AoS -> s8 K-major tiles + (d, c)
+// slabs; weight blocks -> u8 K-major tiles + d (+m) slabs, both already in the 128-byte
+// swizzle image the UMMA smem descriptor expects, so the producer needs no tensor map.
+#include "ptx.cuh"
 #include "qgemm_common.cuh"
+
 namespace qgemm {
-bool mmq_supported(int, const void*, const void*, int, int, int) { return false; }
-size_t mmq_workspace_bytes(int, int, int, int) { return 0; }
-cudaError_t launch_mmq(int, const void*, const void*, float*, int32_t*, int, int, int, int64_t, int64_t, uint32_t,
-                       void*, size_t, int, cudaStream_t) { return cudaErrorNotSupported; }
+
+constexpr int kBM = 128;        // tokens per tile = TMEM lanes
+constexpr int kBN = 128;        // weight rows per tile = TMEM columns per buffer
+constexpr int kTmemCols = 512;
+constexpr int kTmemBufs = kTmemCols / kBN;
+constexpr int kKC = 128;        // K elements per smem stage (4 blocks), one 128-byte swizzle row
+constexpr int kBlocksPerStage = kKC / 32;
+constexpr int kMmqStages = 4;
+constexpr int kEpiWarps = 8;
+constexpr int kMmqThreads = (4 + kEpiWarps) * 32;
+
+// stage layout (bytes); operand tiles 1024-byte aligned for SWIZZLE_128B
+constexpr int kStageA = 0;                                   // [128 tokens][128 B]
+constexpr int kStageW = kStageA + kBM * kKC;                 // [kBN rows][128 B]
+constexpr int kStageAS = kStageW + kBN * kKC;                // [4 blocks][128 tokens] float2 (d_a, c_a)
+constexpr int kStageWS = kStageAS + kBlocksPerStage * kBM * 8;   // [4 blocks][kBN] float d_w
+constexpr int kStageWM = kStageWS + kBlocksPerStage * kBN * 4;   // [4 blocks][kBN] float m_w
+constexpr int kStageBytes = kStageWM + kBlocksPerStage * kBN * 4;
+static_assert(kStageBytes % 1024 == 0, "stage must keep 1024-byte alignment");
+constexpr int kMmqSmem = 1024 /*align slack*/ + kMmqStages * kStageBytes + 256 /*barriers*/;
+
+// ---------------------------------------------------------------------------
+// workspace layout (all offsets 1024-byte aligned)
+// ---------------------------------------------------------------------------
+struct MmqWs {
+    size_t a8, as, w8, ws, wm, total;
+    int Tpad, Fpad, nkc;
+};
+static MmqWs mmq_layout(int T, int F, int K) {
+    MmqWs L;
+    L.Tpad = (T + kBM - 1) / kBM * kBM;
+    L.Fpad = (F + kBN - 1) / kBN * kBN;
+    L.nkc = (K + kKC - 1) / kKC;
+    const int nbp = L.nkc * kBlocksPerStage;  // blocks, padded to whole stages
+    auto up = [](size_t v) { return (v + 1023) / 1024 * 1024; };
+    size_t o = 0;
+    L.a8 = o; o = up(o + (size_t)L.nkc * L.Tpad * kKC);
+    L.as = o; o = up(o + (size_t)nbp * L.Tpad * 8);
+    L.w8 = o; o = up(o + (size_t)L.nkc * L.Fpad * kKC);
+    L.ws = o; o = up(o + (size_t)nbp * L.Fpad * 4);
+    L.wm = o; o = up(o + (size_t)nbp * L.Fpad * 4);
+    L.total = o;
+    return L;
+}
+
+// ---------------------------------------------------------------------------
+// prepass 1: q8_1 AoS -> swizzled s8 tiles + (d_a, c_a) slabs
+//   a8[kc][t][16-byte chunk c ^ (t & 7)]            (chunk c = (b & 3) * 2 + {0, 1})
+//   as[t / 128][b][t % 128] = (d_a, coef * s_a)     coef: -8 (q4_0), -16 (q5_0), 1/4 or 1 (q4_1/q5_1), 0 (q8_0)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mmq_repack_act_kernel(const uint8_t* __restrict__ act, uint8_t* __restrict__ a8, float2* __restrict__ as, int T,
+                      int Tpad, int nb, int nbp, float coef) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (int64_t)Tpad * nbp) return;
+    const int t = (int)(gid % Tpad), b = (int)(gid / Tpad);
+    uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+    float2 sc = make_float2(0.f, 0.f);
+    if (t < T && b < nb) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(act + ((size_t)t * nb + b) * kQ81Bytes);
+        const uint32_t ds = __ldg(src);
+        sc.x = half_bits_to_float(ds);
+        sc.y = __fmul_rn(coef, half_bits_to_float(ds >> 16));
+        q0 = make_uint4(__ldg(src + 1), __ldg(src + 2), __ldg(src + 3), __ldg(src + 4));
+        q1 = make_uint4(__ldg(src + 5), __ldg(src + 6), __ldg(src + 7), __ldg(src + 8));
+    }
+    const int kc = b >> 2, c = (b & 3) * 2;
+    uint8_t* row = a8 + ((size_t)kc * Tpad + t) * kKC;
+    *reinterpret_cast<uint4*>(row + ((c ^ (t & 7)) << 4)) = q0;
+    *reinterpret_cast<uint4*>(row + (((c + 1) ^ (t & 7)) << 4)) = q1;
+    as[((size_t)(t / kBM) * nbp + b) * kBM + (t % kBM)] = sc;
+}
+
+// ---------------------------------------------------------------------------
+// prepass 2: weight blocks -> swizzled u8 (s8 for q8_0) tiles + d (+m) slabs
+//   w8[kc][f][chunk ^ (f & 7)],  ws[f / BN][b][f % BN] = d_w,  wm[...] = m_w
+// ---------------------------------------------------------------------------
+template <int WT>
+__global__ void __launch_bounds__(256)
+mmq_unpack_weight_kernel(const uint8_t* __restrict__ wgt, uint8_t* __restrict__ w8, float* __restrict__ ws,
+                         float* __restrict__ wm, int F, int Fpad, int nb, int nbp) {
+    using Fm = Fmt<WT>;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (int64_t)Fpad * nbp) return;
+    const int f = (int)(gid % Fpad), b = (int)(gid / Fpad);
+    uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    WScale sc{0.f, 0.f};
+    if (f < F && b < nb) {
+        const uint8_t* blk = wgt + ((size_t)f * nb + b) * Fm::bytes;
+        unpack_block<WT>(blk, w);
+        sc = load_wscale<WT>(blk);
+    }
+    const int kc = b >> 2, c = (b & 3) * 2;
+    uint8_t* row = w8 + ((size_t)kc * Fpad + f) * kKC;
+    *reinterpret_cast<uint4*>(row + ((c ^ (f & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(row + (((c + 1) ^ (f & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+    const size_t so = ((size_t)(f / kBN) * nbp + b) * kBN + (f % kBN);
+    ws[so] = sc.d;
+    if constexpr (Fm::m >= 0) wm[so] = sc.m;
+}
+
+// ---------------------------------------------------------------------------
+// tcgen05 wrappers
+// ---------------------------------------------------------------------------
+namespace t5 {
+__device__ __forceinline__ void alloc(uint32_t* smem_slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(smem_slot)),
+                 "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     ptx::smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] = A[smem] . B[smem]^T, 8-bit integer operands, s32 accumulate; overwrite (no accumulate)
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 32 lanes x 32 consecutive columns -> 32 registers per thread
+__device__ __forceinline__ void ld32(uint32_t taddr, int (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+// K-major operand tile, 128-byte rows, SWIZZLE_128B, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)(1024u >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+}  // namespace t5
+
+struct MmqParams {
+    const uint8_t* a8;
+    const float2* as;
+    const uint8_t* w8;
+    const float* ws;
+    const float* wm;
+    float* C;
+    int32_t* sumi;   // non-null: dump the raw s32 block sums instead of folding
+    int T, F, nb, nkc, Tpad, Fpad;
+    int64_t ldc_t, ldc_f;
+    int tiles_m, tiles_n;
+};
+
+template <int WT>
+__global__ void __launch_bounds__(kMmqThreads, 1) mmq_kernel(const MmqParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte aligned base (SWIZZLE_128B atoms); offset arithmetic keeps the shared address space
+    const uint32_t raw = ptx::smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kMmqStages * kStageBytes);  // [stages]
+    uint64_t* empty = full + kMmqStages;                                            // [stages]
+    uint64_t* tfull = empty + kMmqStages;                                           // [kTmemBufs]
+    uint64_t* tempty = tfull + kTmemBufs;                                           // [kTmemBufs]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kTmemBufs);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkc = p.nkc;
+    const int nbp = nkc * kBlocksPerStage;
+    const int ntiles = p.tiles_m * p.tiles_n;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kMmqStages; s++) {
+            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&empty[s], 1 + kEpiWarps);  // MMA commit + every epilogue warp
+        }
+        for (int i = 0; i < kTmemBufs; i++) {
+            ptx::mbar_init(&tfull[i], 1);
+            ptx::mbar_init(&tempty[i], kEpiWarps);
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) t5::alloc(tmem_slot, kTmemCols);
+    t5::fence_before();
+    __syncthreads();
+    t5::fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== producer =====================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int mt = tile % p.tiles_m, nt = tile / p.tiles_m;
+                for (int kc = 0; kc < nkc; kc++) {
+                    ptx::mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* st = smem + s * kStageBytes;
+                    constexpr uint32_t bytes = kBM * kKC + kBN * kKC + kBlocksPerStage * kBM * 8 +
+                                               kBlocksPerStage * kBN * 4 * (Fmt<WT>::m >= 0 ? 2 : 1);
+                    ptx::mbar_arrive_expect_tx(&full[s], bytes);
+                    ptx::bulk_g2s(st + kStageA, p.a8 + ((size_t)kc * p.Tpad + (size_t)mt * kBM) * kKC, kBM * kKC, &full[s]);
+                    ptx::bulk_g2s(st + kStageW, p.w8 + ((size_t)kc * p.Fpad + (size_t)nt * kBN) * kKC, kBN * kKC, &full[s]);
+                    ptx::bulk_g2s(st + kStageAS, p.as + ((size_t)mt * nbp + (size_t)kc * kBlocksPerStage) * kBM,
+                                  kBlocksPerStage * kBM * 8, &full[s]);
+                    ptx::bulk_g2s(st + kStageWS, p.ws + ((size_t)nt * nbp + (size_t)kc * kBlocksPerStage) * kBN,
+                                  kBlocksPerStage * kBN * 4, &full[s]);
+                    if constexpr (Fmt<WT>::m >= 0)
+                        ptx::bulk_g2s(st + kStageWM, p.wm + ((size_t)nt * nbp + (size_t)kc * kBlocksPerStage) * kBN,
+                                      kBlocksPerStage * kBN * 4, &full[s]);
+                    if (++s == kMmqStages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        // instruction descriptor: D = s32, A = s8 (activations), B = u8 (s8 for q8_0), both K-major
+        constexpr uint32_t idesc = (2u << 4) | (1u << 7) | ((Fmt<WT>::bits == 8 ? 1u : 0u) << 10) |
+                                   ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+        int s = 0, buf = 0;
+        uint32_t ph = 0, tph = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int kc = 0; kc < nkc; kc++) {
+                ptx::mbar_wait(&full[s], ph);
+                t5::fence_after();
+                const uint32_t sa = ptx::smem_u32(smem + s * kStageBytes + kStageA);
+                const uint32_t sw = ptx::smem_u32(smem + s * kStageBytes + kStageW);
+                const uint64_t adesc = t5::smem_desc(sa), bdesc = t5::smem_desc(sw);
+#pragma unroll
+                for (int j = 0; j < kBlocksPerStage; j++) {
+                    ptx::mbar_wait(&tempty[buf], tph ^ 1);
+                    t5::fence_after();
+                    if (lane == 0) {
+                        // one instruction = one quantization block (K = 32 bytes = +2 in the >>4 address field)
+                        t5::mma_i8(tmem_base + buf * kBN, adesc + 2 * j, bdesc + 2 * j, idesc, 0u);
+                        t5::commit(&tfull[buf]);
+                    }
+                    __syncwarp();
+                    if (++buf == kTmemBufs) { buf = 0; tph ^= 1; }
+                }
+                if (lane == 0) t5::commit(&empty[s]);  // operand tiles consumed once these MMAs retire
+                __syncwarp();
+                if (++s == kMmqStages) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int ew = warp - 4;
+        const int quarter = warp & 3;           // TMEM lane quarter this warp may touch
+        const int chalf = ew >> 2;              // which 64 of the 128 columns
+        const int row = quarter * 32 + lane;    // token row inside the tile
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        int s = 0, buf = 0;
+        uint32_t ph = 0, tph = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int mt = tile % p.tiles_m, nt = tile / p.tiles_m;
+            float acc[64];
+#pragma unroll
+            for (int i = 0; i < 64; i++) acc[i] = 0.f;
+            for (int kc = 0; kc < nkc; kc++) {
+                ptx::mbar_wait(&full[s], ph);  // scale slabs of this stage are visible
+                const uint8_t* st = smem + s * kStageBytes;
+#pragma unroll 1
+                for (int j = 0; j < kBlocksPerStage; j++) {
+                    const int b = kc * kBlocksPerStage + j;
+                    ptx::mbar_wait(&tfull[buf], tph);
+                    t5::fence_after();
+                    int x[64];
+                    {
+                        int lo[32], hi[32];
+                        const uint32_t ta = tmem_base + lane_addr + buf * kBN + chalf * 64;
+                        t5::ld32(ta, lo);
+                        t5::ld32(ta + 32, hi);
+                        t5::wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; i++) { x[i] = lo[i]; x[32 + i] = hi[i]; }
+                    }
+                    t5::fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tempty[buf]);  // values are in registers: free the buffer
+                    if (++buf == kTmemBufs) { buf = 0; tph ^= 1; }
+
+                    if (p.sumi) {
+                        const int t = mt * kBM + row;
+                        if (t < p.T && b < p.nb) {
+#pragma unroll
+                            for (int i = 0; i < 64; i++) {
+                                const int f = nt * kBN + chalf * 64 + i;
+                                if (f < p.F) p.sumi[((size_t)t * p.F + f) * p.nb + b] = x[i];
+                            }
+                        }
+                        continue;
+                    }
+                    const float2 a = reinterpret_cast<const float2*>(st + kStageAS)[j * kBM + row];
+                    const float4* dw4 = reinterpret_cast<const float4*>(st + kStageWS) + (j * kBN + chalf * 64) / 4;
+                    const float4* mw4 = reinterpret_cast<const float4*>(st + kStageWM) + (j * kBN + chalf * 64) / 4;
+#pragma unroll
+                    for (int i4 = 0; i4 < 16; i4++) {
+                        const float4 dw = dw4[i4];
+                        const float dwv[4] = {dw.x, dw.y, dw.z, dw.w};
+                        float mwv[4] = {0.f, 0.f, 0.f, 0.f};
+                        if constexpr (Fmt<WT>::m >= 0) {
+                            const float4 mw = mw4[i4];
+                            mwv[0] = mw.x; mwv[1] = mw.y; mwv[2] = mw.z; mwv[3] = mw.w;
+                        }
+#pragma unroll
+                        for (int c = 0; c < 4; c++)
+                            acc[i4 * 4 + c] = fold_block_pre<WT>(acc[i4 * 4 + c], x[i4 * 4 + c], WScale{dwv[c], mwv[c]},
+                                                                 ActScale{a.x, a.y});
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&empty[s]);  // scale slabs consumed
+                if (++s == kMmqStages) { s = 0; ph ^= 1; }
+            }
+            if (!p.sumi) {
+                const int t = mt * kBM + row;
+                if (t < p.T) {
+                    float* crow = p.C + (int64_t)t * p.ldc_t;
+#pragma unroll
+                    for (int i = 0; i < 64; i++) {
+                        const int f = nt * kBN + chalf * 64 + i;
+                        if (f < p.F) crow[(int64_t)f * p.ldc_f] = acc[i];
+                    }
+                }
+            }
+        }
+    }
+    t5::fence_before();
+    __syncthreads();
+    if (warp == 2) t5::dealloc(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+bool mmq_supported(int wtype, const void* act, const void* wgt, int T, int F, int K) {
+    (void)wgt;
+    if (block_bytes(wtype) == 0 || T < 1 || F < 1 || K < 32) return false;
+    return reinterpret_cast<uintptr_t>(act) % 4 == 0;
+}
+
+size_t mmq_workspace_bytes(int wtype, int T, int F, int K) {
+    (void)wtype;
+    if (T < 1 || F < 1 || K < 32) return 0;
+    return mmq_layout(T, F, K).total;
+}
+
+template <int WT>
+static cudaError_t launch_mmq_t(const void* act, const void* wgt, float* C, int32_t* sumi, int T, int F, int K,
+                                int64_t ldc_t, int64_t ldc_f, uint32_t flags, void* ws, int num_sms, cudaStream_t st) {
+    const MmqWs L = mmq_layout(T, F, K);
+    const int nb = K / 32, nbp = L.nkc * kBlocksPerStage;
+    uint8_t* base = (uint8_t*)ws;
+    float coef = 0.f;
+    if (WT == QGEMM_TYPE_Q4_0) coef = -8.f;
+    else if (WT == QGEMM_TYPE_Q5_0) coef = -16.f;
+    else if (WT == QGEMM_TYPE_Q4_1 || WT == QGEMM_TYPE_Q5_1) coef = (flags & QGEMM_MS_EXACT) ? 1.f : 0.25f;
+    {
+        const int64_t n = (int64_t)L.Tpad * nbp;
+        mmq_repack_act_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+            (const uint8_t*)act, base + L.a8, (float2*)(base + L.as), T, L.Tpad, nb, nbp, coef);
+        note_launch();
+    }
+    {
+        const int64_t n = (int64_t)L.Fpad * nbp;
+        mmq_unpack_weight_kernel<WT><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+            (const uint8_t*)wgt, base + L.w8, (float*)(base + L.ws), (float*)(base + L.wm), F, L.Fpad, nb, nbp);
+        note_launch();
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    static bool attr_done = false;
+    if (!attr_done) {
+        e = cudaFuncSetAttribute(mmq_kernel<WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmqSmem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    MmqParams p;
+    p.a8 = base + L.a8; p.as = (const float2*)(base + L.as);
+    p.w8 = base + L.w8; p.ws = (const float*)(base + L.ws); p.wm = (const float*)(base + L.wm);
+    p.C = C; p.sumi = sumi;
+    p.T = T; p.F = F; p.nb = nb; p.nkc = L.nkc; p.Tpad = L.Tpad; p.Fpad = L.Fpad;
+    p.ldc_t = ldc_t; p.ldc_f = ldc_f;
+    p.tiles_m = L.Tpad / kBM; p.tiles_n = L.Fpad / kBN;
+    const int ntiles = p.tiles_m * p.tiles_n;
+    mmq_kernel<WT><<<min(ntiles, num_sms), kMmqThreads, kMmqSmem, st>>>(p);
+    note_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mmq(int wtype, const void* act, const void* wgt, float* C, int32_t* sumi_out, int T, int F, int K,
+                       int64_t ldc_t, int64_t ldc_f, uint32_t flags, void* ws, size_t ws_bytes, int num_sms,
+                       cudaStream_t st) {
+    if (ws_bytes < mmq_workspace_bytes(wtype, T, F, K) || reinterpret_cast<uintptr_t>(ws) % 256 != 0)
+        return cudaErrorInvalidValue;
+    switch (wtype) {
+    case QGEMM_TYPE_Q4_0: return launch_mmq_t<QGEMM_TYPE_Q4_0>(act, wgt, C, sumi_out, T, F, K, ldc_t, ldc_f, flags, ws, num_sms, st);
+    case QGEMM_TYPE_Q4_1: return launch_mmq_t<QGEMM_TYPE_Q4_1>(act, wgt, C, sumi_out, T, F, K, ldc_t, ldc_f, flags, ws, num_sms, st);
+    case QGEMM_TYPE_Q5_0: return launch_mmq_t<QGEMM_TYPE_Q5_0>(act, wgt, C, sumi_out, T, F, K, ldc_t, ldc_f, flags, ws, num_sms, st);
+    case QGEMM_TYPE_Q5_1: return launch_mmq_t<QGEMM_TYPE_Q5_1>(act, wgt, C, sumi_out, T, F, K, ldc_t, ldc_f, flags, ws, num_sms, st);
+    case QGEMM_TYPE_Q8_0: return launch_mmq_t<QGEMM_TYPE_Q8_0>(act, wgt, C, sumi_out, T, F, K, ldc_t, ldc_f, flags, ws, num_sms, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
 }  // namespace qgemm

@@ -25,6 +25,8 @@ cudaError_t launch_mmq(int wtype, const void* act, const void* wgt, float* C, in
                        int64_t ldc_t, int64_t ldc_f, uint32_t flags, void* ws, size_t ws_bytes, int num_sms,
                        cudaStream_t);
 
+constexpr int kMmqMinTokens = 64;  // AUTO switches from the weight-streaming path to tensor cores here
+
 static std::atomic<int64_t> g_launches{0};
 void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
@@ -98,7 +100,7 @@ static int run_gemm(int wtype, const void* act, const void* wgt, float* C, int T
     uint32_t path = flags & QGEMM_PATH_MASK;
     if (flags & QGEMM_SEQUENTIAL) path = QGEMM_PATH_GENERIC;
     if (path == QGEMM_PATH_AUTO) {
-        if (T >= 64 && mmq_supported(wtype, act, wgt, T, F, K) && ws && ws_bytes >= mmq_workspace_bytes(wtype, T, F, K))
+        if (T >= kMmqMinTokens && mmq_supported(wtype, act, wgt, T, F, K) && ws && ws_bytes >= mmq_workspace_bytes(wtype, T, F, K))
             path = QGEMM_PATH_TCGEN05;
         else if (gemv_supported(wtype, act, wgt, F, K))
             path = QGEMM_PATH_GEMV;
@@ -190,11 +192,13 @@ int qgemm_dequantize(int type, const void* x, float* y, int64_t rows, int64_t K,
 }
 
 size_t qgemm_workspace_bytes(int wtype, int T, int F, int K, uint32_t flags) {
-    (void)flags;
     if (!is_weight_type(wtype) || T <= 0 || F <= 0 || K <= 0 || (K % kQK) != 0) return 0;
-    // [ q8_1 copy of A for qgemm_gemm_f32act | path scratch ]
+    // [ q8_1 copy of A for qgemm_gemm_f32act | tensor-core path scratch (only where that path can run) ]
     const size_t a_q = align_up((size_t)T * (K / kQK) * kQ81Bytes, 256);
-    return a_q + align_up(mmq_workspace_bytes(wtype, T, F, K), 256);
+    const uint32_t path = flags & QGEMM_PATH_MASK;
+    const bool mmq = (path == QGEMM_PATH_TCGEN05 || path == QGEMM_PATH_MMA || (path == QGEMM_PATH_AUTO && T >= kMmqMinTokens)) &&
+                     !(flags & QGEMM_SEQUENTIAL);
+    return a_q + (mmq ? align_up(mmq_workspace_bytes(wtype, T, F, K), 256) : 0);
 }
 
 int qgemm_gemm(int wtype, const void* act_q8_1, const void* weight, float* C, int T, int F, int K, int64_t ldc_t,

@@ -291,3 +291,80 @@ def test_full_size_decode_properties(qg, O):
         # T=1 slice equals column 0 of the T=8 run up to accumulation-order noise; sumi identical
         c1 = host(qg.gemm(dwq, dev(aq[:1]), F, 1, K, wt))
         check_c(c1[:, 0], c[:, 0], "T=1 vs T=8")
+
+
+# ------------------------------------------------------------------------------------------
+# prefill path: tcgen05.mma kind::i8 with TMEM accumulators (QGEMM_PATH_TCGEN05)
+# ------------------------------------------------------------------------------------------
+PATHS["tcgen05"] = 0x400
+MMQ_SHAPES = [(128, 128, 128), (64, 256, 4096), (200, 300, 1056), (130, 129, 32), (512, 384, 2048)]
+
+
+@pytest.mark.parametrize("wt", qo.WEIGHT_TYPES)
+@pytest.mark.parametrize("T,F,K", MMQ_SHAPES[:4])
+def test_mmq_sumi_bit_exact(qg, O, wt, T, F, K):
+    """The s32 tile each UTCIMMA leaves in TMEM is the reference's integer block sum, bit for bit."""
+    nb = K // 32
+    wq = datagen.fuzz_weight_blocks(wt, F, nb, seed=wt + T)
+    aq = datagen.fuzz_act_blocks(T, nb, seed=wt + F)
+    got = host(qg.block_sumi(dev(wq), dev(aq), F, T, K, wt, flags=0x400))
+    assert (got == O.gemm_sumi(wt, aq, wq)).all()
+
+
+@pytest.mark.parametrize("wt", qo.WEIGHT_TYPES)
+@pytest.mark.parametrize("T,F,K", MMQ_SHAPES)
+def test_mmq_gemm_vs_oracle(qg, O, wt, T, F, K):
+    x, w = datagen.model_like(T, F, K, seed=T + F + K)
+    aq, wq = O.quantize_q8_1(x), O.quantize_weight(wt, w)
+    c = run_gemm(qg, wt, aq, wq, "tcgen05")
+    assert qg.last_path() == 0x400
+    check_c(c, O.gemm(wt, aq, wq, layout="FT"), f"tcgen05 {qo.TYPE_NAMES[wt]} {T}x{F}x{K}")
+    # blocks are folded in order b = 0..nb-1 with the reference GPU kernel's FMA sequence: bit-identical
+    assert (bits(c) == bits(O.gemm(wt, aq, wq, layout="FT", flags=qo.GEMM_FMA))).all()
+
+
+@pytest.mark.parametrize("wt", [qo.Q4_0, qo.Q5_1, qo.Q8_0])
+def test_mmq_fuzz_ms_exact_and_layouts(qg, O, wt):
+    from quant_gemm import _lib
+    T, F, nb = 96, 200, 24
+    wq = datagen.fuzz_weight_blocks(wt, F, nb, seed=77 + wt)
+    aq = datagen.fuzz_act_blocks(T, nb, seed=77 + wt, const_ds=False)
+    for fl in (0, qo.GEMM_MS_EXACT):
+        c = run_gemm(qg, wt, aq, wq, "tcgen05", flags=fl)
+        check_c(c, O.gemm(wt, aq, wq, layout="FT", flags=fl), "mmq fuzz")
+    # AUTO takes the tensor-core path from 64 tokens up, and the include/ [T,F] layout works too
+    c = run_gemm(qg, wt, aq, wq, "auto")
+    assert qg.last_path() == 0x400
+    da, dw = dev(aq), dev(wq)
+    L = _lib.lib()
+    nws = L.qgemm_workspace_bytes(wt, T, F, nb * 32, 0)
+    ws = torch.empty(nws, dtype=torch.uint8, device="cuda")
+    out = torch.empty((T, F), device="cuda")
+    assert L.qgemm_gemm(wt, da.data_ptr(), dw.data_ptr(), out.data_ptr(), T, F, nb * 32, F, 1, 0, ws.data_ptr(), nws,
+                        torch.cuda.current_stream().cuda_stream) == 0
+    assert (bits(host(out).T) == bits(c)).all()
+    # without a workspace AUTO must still answer (weight-streaming path), and a forced path must say so
+    assert L.qgemm_gemm(wt, da.data_ptr(), dw.data_ptr(), out.data_ptr(), T, F, nb * 32, F, 1, 0, None, 0,
+                        torch.cuda.current_stream().cuda_stream) == 0
+    check_c(host(out).T, c, "auto without workspace")
+    assert L.qgemm_gemm(wt, da.data_ptr(), dw.data_ptr(), out.data_ptr(), T, F, nb * 32, F, 1, 0x400, None, 0,
+                        torch.cuda.current_stream().cuda_stream) == -5
+
+
+def test_mmq_full_size_prefill_properties(qg, O):
+    """BASELINE config 3 (Q4_0, M=512 N=4096 K=4096): sampled rows against the oracle, bit-identical
+    to the sequential path on a slab, and token-permutation equivariance."""
+    T, F, K = 512, 4096, 4096
+    x, w = datagen.model_like(T, F, K, seed=60)
+    dwq = qg.quantize_q4_0(dev(w))
+    daq = qg.quantize_q8_1(dev(x))
+    aq, wq = host(daq), host(dwq)
+    c = host(qg.gemm(dwq, daq, F, T, K, qo.Q4_0))
+    assert qg.last_path() == 0x400
+    rows = np.r_[0:4, 2047:2051, F - 4:F]
+    ref = O.gemm(qo.Q4_0, aq, wq[rows], layout="FT", flags=qo.GEMM_FMA)
+    assert (bits(c[rows]) == bits(ref)).all()
+    check_c(c[rows], O.gemm(qo.Q4_0, aq, wq[rows], layout="FT"), "prefill vs CPU-order oracle")
+    perm = np.random.default_rng(1).permutation(T)
+    c2 = host(qg.gemm(dwq, dev(aq[perm]), F, T, K, qo.Q4_0))
+    assert (bits(c2) == bits(c[:, perm])).all()
