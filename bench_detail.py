@@ -80,6 +80,46 @@ def time_shape(torch, quant_gemm, wtype, T, F, K, flags=0x10, reps=3, pool_bytes
             "path": hex(quant_gemm.last_path())}
 
 
+def time_prefill(torch, quant_gemm, wtype, T, F, K, flags=0, reps=5, fused_f32=False):
+    """Whole-call time (prepass + tensor-core kernel [+ quantize_q8_1 when fused_f32]), L2 flushed between reps."""
+    dev = torch.device("cuda")
+    w = make_weights(torch, wtype, F, K, 1, dev)[0]
+    x = torch.randn((T, K), device=dev)
+    aq = quant_gemm.quantize_q8_1(x)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    call = (lambda: quant_gemm.gemm_w4a8(w, x, F, T, K, wtype, flags)) if fused_f32 else \
+           (lambda: quant_gemm.gemm(w, aq, F, T, K, wtype, flags))
+    for _ in range(2):
+        call()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        call()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1) * 1e3)
+    best = min(times)
+    return {"type": NAMES[wtype], "T": T, "F": F, "K": K, "us": best, "us_median": sorted(times)[len(times) // 2],
+            "tops": 2.0 * T * F * K / best / 1e6, "fused_quantize": fused_f32, "path": hex(quant_gemm.last_path())}
+
+
+def run_prefill(out_path):
+    import torch
+    import quant_gemm
+    rows = []
+    for (wt, T, F, K, fused) in [(2, 512, 4096, 4096, False), (2, 2048, 4096, 4096, False), (7, 2048, 14336, 4096, True),
+                                 (2, 4096, 28672, 8192, False), (8, 512, 4096, 4096, False), (2, 128, 4096, 4096, False),
+                                 (2, 64, 4096, 4096, False)]:
+        r = time_prefill(torch, quant_gemm, wt, T, F, K, fused_f32=fused)
+        rows.append(r)
+        print(json.dumps(r), flush=True)
+    with open(out_path, "w") as f:
+        json.dump({"rows": rows}, f, indent=1)
+
+
 def run(out_path, quick=False, flags=0x10):
     import torch
     import quant_gemm
@@ -103,5 +143,9 @@ if __name__ == "__main__":
     ap.add_argument("--out", default="gpurun_out/detail.json")
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--flags", type=lambda v: int(v, 0), default=0x10)
+    ap.add_argument("--prefill", action="store_true")
     a = ap.parse_args()
-    run(a.out, a.quick, a.flags)
+    if a.prefill:
+        run_prefill(a.out)
+    else:
+        run(a.out, a.quick, a.flags)

@@ -25,6 +25,8 @@
 // Operands come from a prepass (qgemm workspace): q8_1 AoS -> s8 K-major tiles + (d, c)
 // slabs; weight blocks -> u8 K-major tiles + d (+m) slabs, both already in the 128-byte
 // swizzle image the UMMA smem descriptor expects, so the producer needs no tensor map.
+#include <cstdlib>
+
 #include "ptx.cuh"
 #include "qgemm_common.cuh"
 
@@ -179,6 +181,54 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
 }
 }  // namespace t5
 
+// ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2: one issue slot, two IEEE results) ----
+__device__ __forceinline__ uint64_t pk(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpk(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// s32 -> f32, exact for |x| < 2^22 (|sumi| <= 524288): integer add on the ALU pipe builds the
+// bits of 12582912 + x, one packed FADD removes the bias exactly.  kCvtMagic = 0 uses I2FP.
+#ifndef QGEMM_MMQ_CVT_MAGIC
+#define QGEMM_MMQ_CVT_MAGIC 1
+#endif
+__device__ __forceinline__ uint64_t cvt2(int x0, int x1) {
+#if QGEMM_MMQ_CVT_MAGIC
+    const uint64_t biased = pk(__int_as_float(x0 + 0x4B400000), __int_as_float(x1 + 0x4B400000));
+    return fadd2(biased, pk(-12582912.0f, -12582912.0f));
+#else
+    return pk(__int2float_rn(x0), __int2float_rn(x1));
+#endif
+}
+// Two outputs of one token: same rounding sequence per element as fold_block_pre() (qgemm_common.cuh).
+template <int WT>
+__device__ __forceinline__ uint64_t fold_pair(uint64_t acc, int x0, int x1, uint64_t dw, uint64_t mw, uint64_t da, uint64_t ca) {
+    const uint64_t f = cvt2(x0, x1);
+    if constexpr (WT == QGEMM_TYPE_Q4_0 || WT == QGEMM_TYPE_Q5_0) {
+        return ffma2(dw, ffma2(da, f, ca), acc);
+    } else if constexpr (WT == QGEMM_TYPE_Q4_1 || WT == QGEMM_TYPE_Q5_1) {
+        return fadd2(acc, ffma2(fmul2(dw, da), f, fmul2(mw, ca)));
+    } else {
+        return ffma2(fmul2(dw, da), f, acc);
+    }
+}
+
 struct MmqParams {
     const uint8_t* a8;
     const float2* as;
@@ -190,6 +240,7 @@ struct MmqParams {
     int T, F, nb, nkc, Tpad, Fpad;
     int64_t ldc_t, ldc_f;
     int tiles_m, tiles_n;
+    int dbg;  // tuning aid: 1 = skip the fold, 2 = also load only half of the TMEM columns, 3 = no TMEM load
 };
 
 template <int WT>
@@ -294,9 +345,9 @@ __global__ void __launch_bounds__(kMmqThreads, 1) mmq_kernel(const MmqParams p) 
         uint32_t ph = 0, tph = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int mt = tile % p.tiles_m, nt = tile / p.tiles_m;
-            float acc[64];
+            uint64_t acc[32];  // 64 fp32 accumulators as 32 packed pairs (columns 2i, 2i+1)
 #pragma unroll
-            for (int i = 0; i < 64; i++) acc[i] = 0.f;
+            for (int i = 0; i < 32; i++) acc[i] = 0ull;
             for (int kc = 0; kc < nkc; kc++) {
                 ptx::mbar_wait(&full[s], ph);  // scale slabs of this stage are visible
                 const uint8_t* st = smem + s * kStageBytes;
@@ -309,8 +360,8 @@ __global__ void __launch_bounds__(kMmqThreads, 1) mmq_kernel(const MmqParams p) 
                     {
                         int lo[32], hi[32];
                         const uint32_t ta = tmem_base + lane_addr + buf * kBN + chalf * 64;
-                        t5::ld32(ta, lo);
-                        t5::ld32(ta + 32, hi);
+                        if (p.dbg < 3) t5::ld32(ta, lo);
+                        if (p.dbg < 2) t5::ld32(ta + 32, hi);
                         t5::wait_ld();
 #pragma unroll
                         for (int i = 0; i < 32; i++) { x[i] = lo[i]; x[32 + i] = hi[i]; }
@@ -331,22 +382,21 @@ __global__ void __launch_bounds__(kMmqThreads, 1) mmq_kernel(const MmqParams p) 
                         }
                         continue;
                     }
+                    if (p.dbg) {
+                        if (x[0] == 0x7fffffff && x[63] == 0x12345) acc[0] = 1ull;  // keep the loads alive
+                        continue;
+                    }
                     const float2 a = reinterpret_cast<const float2*>(st + kStageAS)[j * kBM + row];
-                    const float4* dw4 = reinterpret_cast<const float4*>(st + kStageWS) + (j * kBN + chalf * 64) / 4;
-                    const float4* mw4 = reinterpret_cast<const float4*>(st + kStageWM) + (j * kBN + chalf * 64) / 4;
+                    const uint64_t da = pk(a.x, a.x), ca = pk(a.y, a.y);
+                    const ulonglong2* dw2 = reinterpret_cast<const ulonglong2*>(st + kStageWS) + (j * kBN + chalf * 64) / 4;
+                    const ulonglong2* mw2 = reinterpret_cast<const ulonglong2*>(st + kStageWM) + (j * kBN + chalf * 64) / 4;
 #pragma unroll
                     for (int i4 = 0; i4 < 16; i4++) {
-                        const float4 dw = dw4[i4];
-                        const float dwv[4] = {dw.x, dw.y, dw.z, dw.w};
-                        float mwv[4] = {0.f, 0.f, 0.f, 0.f};
-                        if constexpr (Fmt<WT>::m >= 0) {
-                            const float4 mw = mw4[i4];
-                            mwv[0] = mw.x; mwv[1] = mw.y; mwv[2] = mw.z; mwv[3] = mw.w;
-                        }
-#pragma unroll
-                        for (int c = 0; c < 4; c++)
-                            acc[i4 * 4 + c] = fold_block_pre<WT>(acc[i4 * 4 + c], x[i4 * 4 + c], WScale{dwv[c], mwv[c]},
-                                                                 ActScale{a.x, a.y});
+                        const ulonglong2 dw = dw2[i4];  // d_w of columns 4*i4 .. 4*i4+3 (broadcast read)
+                        ulonglong2 mw = make_ulonglong2(0ull, 0ull);
+                        if constexpr (Fmt<WT>::m >= 0) mw = mw2[i4];
+                        acc[2 * i4] = fold_pair<WT>(acc[2 * i4], x[4 * i4], x[4 * i4 + 1], dw.x, mw.x, da, ca);
+                        acc[2 * i4 + 1] = fold_pair<WT>(acc[2 * i4 + 1], x[4 * i4 + 2], x[4 * i4 + 3], dw.y, mw.y, da, ca);
                     }
                 }
                 __syncwarp();
@@ -358,9 +408,12 @@ __global__ void __launch_bounds__(kMmqThreads, 1) mmq_kernel(const MmqParams p) 
                 if (t < p.T) {
                     float* crow = p.C + (int64_t)t * p.ldc_t;
 #pragma unroll
-                    for (int i = 0; i < 64; i++) {
-                        const int f = nt * kBN + chalf * 64 + i;
-                        if (f < p.F) crow[(int64_t)f * p.ldc_f] = acc[i];
+                    for (int i = 0; i < 32; i++) {
+                        float v0, v1;
+                        unpk(acc[i], v0, v1);
+                        const int f = nt * kBN + chalf * 64 + 2 * i;
+                        if (f < p.F) crow[(int64_t)f * p.ldc_f] = v0;
+                        if (f + 1 < p.F) crow[(int64_t)(f + 1) * p.ldc_f] = v1;
                     }
                 }
             }
@@ -423,6 +476,7 @@ static cudaError_t launch_mmq_t(const void* act, const void* wgt, float* C, int3
     p.T = T; p.F = F; p.nb = nb; p.nkc = L.nkc; p.Tpad = L.Tpad; p.Fpad = L.Fpad;
     p.ldc_t = ldc_t; p.ldc_f = ldc_f;
     p.tiles_m = L.Tpad / kBM; p.tiles_n = L.Fpad / kBN;
+    p.dbg = getenv("QGEMM_MMQ_DBG") ? atoi(getenv("QGEMM_MMQ_DBG")) : 0;
     const int ntiles = p.tiles_m * p.tiles_n;
     mmq_kernel<WT><<<min(ntiles, num_sms), kMmqThreads, kMmqSmem, st>>>(p);
     note_launch();

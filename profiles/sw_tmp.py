@@ -1,6 +1,11 @@
-import sys
-sys.path.insert(0,'profiles')
-import sweep_gemv as s
-for env in [{}, {"QGEMM_GEMV_NOCOMPUTE":"1"}]:
-  for shape in [(2, 1, 32768, 4096, 0x10), (2, 1, 11008, 4096, 0x10), (2, 1, 4096, 4096, 0x10), (2, 1, 4096, 11008, 0x10), (2, 1, 4096, 4096, 0), (8, 1, 11008, 4096, 0x10),(7, 1, 11008, 4096, 0x10), (2, 2, 11008, 4096, 0x10), (2, 4, 11008, 4096, 0x10), (2, 8, 11008, 4096, 0x10)]:
-    s.run(shape, env)
+import os, subprocess, sys
+code = '''
+import sys; sys.path[:0]=["llama.cpp-quant-gemm_b200","."]
+import torch, quant_gemm, bench_detail
+r = bench_detail.time_prefill(torch, quant_gemm, 2, 4096, 8192, 8192, reps=3)
+print("us=%.0f tops=%.0f" % (r["us"], r["tops"]))
+'''
+for dbg in ["0", "1", "2", "3"]:
+    e = dict(os.environ); e["QGEMM_MMQ_DBG"] = dbg
+    out = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True)
+    print("dbg", dbg, out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-300:], flush=True)
