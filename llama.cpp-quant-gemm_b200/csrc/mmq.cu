@@ -39,7 +39,8 @@ constexpr int kTmemBufs = kTmemCols / kBN;
 constexpr int kKC = 128;        // K elements per smem stage (4 blocks), one 128-byte swizzle row
 constexpr int kBlocksPerStage = kKC / 32;
 constexpr int kMmqStages = 4;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;       // 4 per TMEM lane quarter, 32 columns each
+constexpr int kEpiCols = kBN / (kEpiWarps / 4);
 constexpr int kMmqThreads = (4 + kEpiWarps) * 32;
 
 // stage layout (bytes); operand tiles 1024-byte aligned for SWIZZLE_128B
@@ -206,7 +207,7 @@ __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
 // s32 -> f32, exact for |x| < 2^22 (|sumi| <= 524288): integer add on the ALU pipe builds the
 // bits of 12582912 + x, one packed FADD removes the bias exactly.  kCvtMagic = 0 uses I2FP.
 #ifndef QGEMM_MMQ_CVT_MAGIC
-#define QGEMM_MMQ_CVT_MAGIC 1
+#define QGEMM_MMQ_CVT_MAGIC 0
 #endif
 __device__ __forceinline__ uint64_t cvt2(int x0, int x1) {
 #if QGEMM_MMQ_CVT_MAGIC
@@ -243,7 +244,7 @@ struct MmqParams {
     int dbg;  // tuning aid: 1 = skip the fold, 2 = also load only half of the TMEM columns, 3 = no TMEM load
 };
 
-template <int WT>
+template <int WT, bool kDump>
 __global__ void __launch_bounds__(kMmqThreads, 1) mmq_kernel(const MmqParams p) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte aligned base (SWIZZLE_128B atoms); offset arithmetic keeps the shared address space
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(kMmqThreads, 1) mmq_kernel(const MmqParams p) 
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int mt = tile % p.tiles_m, nt = tile / p.tiles_m;
                 for (int kc = 0; kc < nkc; kc++) {
-                    ptx::mbar_wait(&empty[s], ph ^ 1);
+                    ptx::mbar_wait_backoff(&empty[s], ph ^ 1);
                     uint8_t* st = smem + s * kStageBytes;
                     constexpr uint32_t bytes = kBM * kKC + kBN * kKC + kBlocksPerStage * kBM * 8 +
                                                kBlocksPerStage * kBN * 4 * (Fmt<WT>::m >= 0 ? 2 : 1);
@@ -312,14 +313,14 @@ __global__ void __launch_bounds__(kMmqThreads, 1) mmq_kernel(const MmqParams p) 
         uint32_t ph = 0, tph = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             for (int kc = 0; kc < nkc; kc++) {
-                ptx::mbar_wait(&full[s], ph);
+                ptx::mbar_wait_backoff(&full[s], ph);
                 t5::fence_after();
                 const uint32_t sa = ptx::smem_u32(smem + s * kStageBytes + kStageA);
                 const uint32_t sw = ptx::smem_u32(smem + s * kStageBytes + kStageW);
                 const uint64_t adesc = t5::smem_desc(sa), bdesc = t5::smem_desc(sw);
 #pragma unroll
                 for (int j = 0; j < kBlocksPerStage; j++) {
-                    ptx::mbar_wait(&tempty[buf], tph ^ 1);
+                    ptx::mbar_wait_backoff(&tempty[buf], tph ^ 1);
                     t5::fence_after();
                     if (lane == 0) {
                         // one instruction = one quantization block (K = 32 bytes = +2 in the >>4 address field)
@@ -338,16 +339,17 @@ __global__ void __launch_bounds__(kMmqThreads, 1) mmq_kernel(const MmqParams p) 
         // ===================== epilogue =====================
         const int ew = warp - 4;
         const int quarter = warp & 3;           // TMEM lane quarter this warp may touch
-        const int chalf = ew >> 2;              // which 64 of the 128 columns
+        const int cgrp = ew >> 2;               // which kEpiCols-wide column group
         const int row = quarter * 32 + lane;    // token row inside the tile
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        static_assert(kEpiCols == 32, "one tcgen05.ld.x32 per block per thread");
         int s = 0, buf = 0;
         uint32_t ph = 0, tph = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int mt = tile % p.tiles_m, nt = tile / p.tiles_m;
-            uint64_t acc[32];  // 64 fp32 accumulators as 32 packed pairs (columns 2i, 2i+1)
+            uint64_t acc[kEpiCols / 2];  // fp32 accumulators as packed pairs (columns 2i, 2i+1)
 #pragma unroll
-            for (int i = 0; i < 32; i++) acc[i] = 0ull;
+            for (int i = 0; i < kEpiCols / 2; i++) acc[i] = 0ull;
             for (int kc = 0; kc < nkc; kc++) {
                 ptx::mbar_wait(&full[s], ph);  // scale slabs of this stage are visible
                 const uint8_t* st = smem + s * kStageBytes;
@@ -356,42 +358,31 @@ __global__ void __launch_bounds__(kMmqThreads, 1) mmq_kernel(const MmqParams p) 
                     const int b = kc * kBlocksPerStage + j;
                     ptx::mbar_wait(&tfull[buf], tph);
                     t5::fence_after();
-                    int x[64];
-                    {
-                        int lo[32], hi[32];
-                        const uint32_t ta = tmem_base + lane_addr + buf * kBN + chalf * 64;
-                        if (p.dbg < 3) t5::ld32(ta, lo);
-                        if (p.dbg < 2) t5::ld32(ta + 32, hi);
-                        t5::wait_ld();
-#pragma unroll
-                        for (int i = 0; i < 32; i++) { x[i] = lo[i]; x[32 + i] = hi[i]; }
-                    }
+                    int x[kEpiCols];
+                    t5::ld32(tmem_base + lane_addr + buf * kBN + cgrp * kEpiCols, x);
+                    t5::wait_ld();
                     t5::fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&tempty[buf]);  // values are in registers: free the buffer
                     if (++buf == kTmemBufs) { buf = 0; tph ^= 1; }
 
-                    if (p.sumi) {
+                    if constexpr (kDump) {
                         const int t = mt * kBM + row;
                         if (t < p.T && b < p.nb) {
 #pragma unroll
-                            for (int i = 0; i < 64; i++) {
-                                const int f = nt * kBN + chalf * 64 + i;
+                            for (int i = 0; i < kEpiCols; i++) {
+                                const int f = nt * kBN + cgrp * kEpiCols + i;
                                 if (f < p.F) p.sumi[((size_t)t * p.F + f) * p.nb + b] = x[i];
                             }
                         }
                         continue;
                     }
-                    if (p.dbg) {
-                        if (x[0] == 0x7fffffff && x[63] == 0x12345) acc[0] = 1ull;  // keep the loads alive
-                        continue;
-                    }
                     const float2 a = reinterpret_cast<const float2*>(st + kStageAS)[j * kBM + row];
                     const uint64_t da = pk(a.x, a.x), ca = pk(a.y, a.y);
-                    const ulonglong2* dw2 = reinterpret_cast<const ulonglong2*>(st + kStageWS) + (j * kBN + chalf * 64) / 4;
-                    const ulonglong2* mw2 = reinterpret_cast<const ulonglong2*>(st + kStageWM) + (j * kBN + chalf * 64) / 4;
+                    const ulonglong2* dw2 = reinterpret_cast<const ulonglong2*>(st + kStageWS) + (j * kBN + cgrp * kEpiCols) / 4;
+                    const ulonglong2* mw2 = reinterpret_cast<const ulonglong2*>(st + kStageWM) + (j * kBN + cgrp * kEpiCols) / 4;
 #pragma unroll
-                    for (int i4 = 0; i4 < 16; i4++) {
+                    for (int i4 = 0; i4 < kEpiCols / 4; i4++) {
                         const ulonglong2 dw = dw2[i4];  // d_w of columns 4*i4 .. 4*i4+3 (broadcast read)
                         ulonglong2 mw = make_ulonglong2(0ull, 0ull);
                         if constexpr (Fmt<WT>::m >= 0) mw = mw2[i4];
@@ -403,15 +394,15 @@ __global__ void __launch_bounds__(kMmqThreads, 1) mmq_kernel(const MmqParams p) 
                 if (lane == 0) ptx::mbar_arrive(&empty[s]);  // scale slabs consumed
                 if (++s == kMmqStages) { s = 0; ph ^= 1; }
             }
-            if (!p.sumi) {
+            if constexpr (!kDump) {
                 const int t = mt * kBM + row;
                 if (t < p.T) {
                     float* crow = p.C + (int64_t)t * p.ldc_t;
 #pragma unroll
-                    for (int i = 0; i < 32; i++) {
+                    for (int i = 0; i < kEpiCols / 2; i++) {
                         float v0, v1;
                         unpk(acc[i], v0, v1);
-                        const int f = nt * kBN + chalf * 64 + 2 * i;
+                        const int f = nt * kBN + cgrp * kEpiCols + 2 * i;
                         if (f < p.F) crow[(int64_t)f * p.ldc_f] = v0;
                         if (f + 1 < p.F) crow[(int64_t)(f + 1) * p.ldc_f] = v1;
                     }
@@ -465,7 +456,8 @@ static cudaError_t launch_mmq_t(const void* act, const void* wgt, float* C, int3
     if (e != cudaSuccess) return e;
     static bool attr_done = false;
     if (!attr_done) {
-        e = cudaFuncSetAttribute(mmq_kernel<WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmqSmem);
+        e = cudaFuncSetAttribute(mmq_kernel<WT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmqSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(mmq_kernel<WT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmqSmem);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
@@ -478,7 +470,8 @@ static cudaError_t launch_mmq_t(const void* act, const void* wgt, float* C, int3
     p.tiles_m = L.Tpad / kBM; p.tiles_n = L.Fpad / kBN;
     p.dbg = getenv("QGEMM_MMQ_DBG") ? atoi(getenv("QGEMM_MMQ_DBG")) : 0;
     const int ntiles = p.tiles_m * p.tiles_n;
-    mmq_kernel<WT><<<min(ntiles, num_sms), kMmqThreads, kMmqSmem, st>>>(p);
+    if (sumi) mmq_kernel<WT, true><<<min(ntiles, num_sms), kMmqThreads, kMmqSmem, st>>>(p);
+    else mmq_kernel<WT, false><<<min(ntiles, num_sms), kMmqThreads, kMmqSmem, st>>>(p);
     note_launch();
     return cudaGetLastError();
 }

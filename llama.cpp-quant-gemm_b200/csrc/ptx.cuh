@@ -36,6 +36,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }
+// for single-thread role warps that share a scheduler with busy math warps: sleep between polls
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(32);
+}
 
 // ---- 1-D bulk async copy global -> shared (TMA engine, no tensor map) ---------
 // dst/src 16-byte aligned, bytes % 16 == 0; completion = complete_tx on `bar`.
