@@ -238,12 +238,13 @@ def main():
     out_host = torch.empty(total_out, dtype=torch.float32).pin_memory()
     step_bytes = sum(algorithmic_bytes(WTYPE, 1, F, K) for F, K, _ in mats)
 
+    from quant_gemm import sharded
+    # every rank owns rows [rank*F, (rank+1)*F) of an (N*F)-row matrix; C is all-gathered in place
+    ops = [sharded.ShardedGemm(w, F * world, K, WTYPE, flags=GEMV_FLAGS) for F, K, w in mats]
+
     def gemv_all():
-        for (F, K, w), o in zip(mats, outs):
-            mine = o[rank * F:(rank + 1) * F]
-            quant_gemm.gemm(w, acts_q[K], F, 1, K, WTYPE, GEMV_FLAGS, out=mine)
-            if world > 1:
-                dist.all_gather_into_tensor(o, mine)
+        for op, (F, K, w), o in zip(ops, mats, outs):
+            op(acts_q[K], out=o)
 
     def e2e_step():
         for K in acts_host:

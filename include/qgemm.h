@@ -146,6 +146,14 @@ QGEMM_API int qgemm_gemm(int wtype, const void *act_q8_1, const void *weight, fl
                void *stream);
 
 /*
+ * Optional: device scratch the library may use, on the CURRENT device, whenever a qgemm_gemm*()
+ * call passes workspace == NULL (the reference's launcher signatures have no workspace
+ * argument, so the drop-in C++ headers always do).  The caller still owns the memory and must
+ * keep it alive and un-shared between concurrently running streams.  (NULL, 0) unregisters.
+ */
+QGEMM_API int qgemm_set_default_workspace(void *workspace, size_t workspace_bytes);
+
+/*
  * Same, with fp32 activations act_f32[T][K]: quantize_q8_1 (flags' QGEMM_Q81_*
  * bits, shifted left by 16) runs first into the workspace, then the GEMM.
  * Successor of gemm_q4_0_fp16_fused() (kernels/gemm/gemm_fused.cuh:311-338) and of

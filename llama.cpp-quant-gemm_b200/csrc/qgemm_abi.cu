@@ -43,6 +43,8 @@ struct DeviceInfo {
     bool ok = false;
 };
 static DeviceInfo g_dev[64];
+struct DefaultWs { void* ptr = nullptr; size_t bytes = 0; };
+static DefaultWs g_default_ws[64];
 static std::mutex g_dev_mu;
 
 // 0 on success; fills *info for the current device.
@@ -96,6 +98,14 @@ static int run_gemm(int wtype, const void* act, const void* wgt, float* C, int T
         note_launch();
         t_last_path = QGEMM_PATH_GENERIC;
         return cudaGetLastError() == cudaSuccess ? QGEMM_OK : QGEMM_E_CUDA;
+    }
+    if (!ws) {  // caller registered scratch for the signature-compatible shims
+        int d = 0;
+        if (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < 64) {
+            std::lock_guard<std::mutex> lk(g_dev_mu);
+            ws = g_default_ws[d].ptr;
+            ws_bytes = g_default_ws[d].bytes;
+        }
     }
     uint32_t path = flags & QGEMM_PATH_MASK;
     if (flags & QGEMM_SEQUENTIAL) path = QGEMM_PATH_GENERIC;
@@ -199,6 +209,16 @@ size_t qgemm_workspace_bytes(int wtype, int T, int F, int K, uint32_t flags) {
     const bool mmq = (path == QGEMM_PATH_TCGEN05 || path == QGEMM_PATH_MMA || (path == QGEMM_PATH_AUTO && T >= kMmqMinTokens)) &&
                      !(flags & QGEMM_SEQUENTIAL);
     return a_q + (mmq ? align_up(mmq_workspace_bytes(wtype, T, F, K), 256) : 0);
+}
+
+int qgemm_set_default_workspace(void* workspace, size_t workspace_bytes) {
+    if ((workspace == nullptr) != (workspace_bytes == 0) || !aligned(workspace, 256)) return QGEMM_E_BADARG;
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return QGEMM_E_CUDA;
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    g_default_ws[d].ptr = workspace;
+    g_default_ws[d].bytes = workspace_bytes;
+    return QGEMM_OK;
 }
 
 int qgemm_gemm(int wtype, const void* act_q8_1, const void* weight, float* C, int T, int F, int K, int64_t ldc_t,

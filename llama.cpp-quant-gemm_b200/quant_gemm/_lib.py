@@ -26,6 +26,7 @@ SYMBOLS = {
     "qgemm_quantize_q8_1": (_i, [_p, _p, _i64, _i64, _u32, _p]),
     "qgemm_quantize_weight": (_i, [_i, _p, _p, _i64, _i64, _u32, _p]),
     "qgemm_dequantize": (_i, [_i, _p, _p, _i64, _i64, _p]),
+    "qgemm_set_default_workspace": (_i, [_p, _sz]),
     "qgemm_workspace_bytes": (_sz, [_i, _i, _i, _i, _u32]),
     "qgemm_gemm": (_i, [_i, _p, _p, _p, _i, _i, _i, _i64, _i64, _u32, _p, _sz, _p]),
     "qgemm_gemm_f32act": (_i, [_i, _p, _p, _p, _i, _i, _i, _i64, _i64, _u32, _p, _sz, _p]),
