@@ -215,8 +215,12 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    ctl = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # control-plane collectives (barriers, max over ranks) use gloo: eager NCCL calls on the communicator
+        # that is also replayed from CUDA graphs hung on this stack
+        ctl = dist.new_group(backend="gloo")
     quant_gemm._lib.lib()
 
     # ---- synthetic weight pool: raw-block fuzz (all nibble values), sane fp16 scales
@@ -277,7 +281,7 @@ def main():
                 graph.replay()
             stream.synchronize()
             if world > 1:
-                dist.barrier()
+                dist.barrier(group=ctl)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
@@ -287,11 +291,11 @@ def main():
             stream.synchronize()
             torch.cuda.synchronize()
             if world > 1:
-                dist.barrier()
+                dist.barrier(group=ctl)
             ms = e0.elapsed_time(e1)
         if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t = torch.tensor([ms])
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=ctl)
             ms = float(t.item())
         return ms
 
@@ -339,7 +343,7 @@ def main():
         "oracle_check_max_norm_err": check,
     }
     if world > 1:
-        dist.barrier()
+        dist.barrier(group=ctl)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_run(steps=10 ** 6, warmup=1, sample_layers=1, budget_s=12.0)
@@ -347,9 +351,11 @@ def main():
         if args.detail:
             import bench_detail
             bench_detail.run(args.detail)
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        dist.barrier(group=ctl)
+        sys.stdout.flush()
+        os._exit(0)  # skip NCCL teardown: communicators that were captured into graphs can hang in destroy
 
 
 if __name__ == "__main__":
