@@ -1,0 +1,284 @@
+// gemv_mma.cu -- skinny path, 3 <= T <= 8 tokens per pass: the decode weight stream of gemv.cu
+// with the integer dots on the legacy tensor path (mma.sync.m16n8k32, s32 += u8 x s8, IMMA.16832).
+//
+// Why: the dp4a GEMV spends ~20 instructions per block per TOKEN and turns compute-bound from
+// T = 3 (hard part 4).  One m16n8k32 does 16 weight rows x 8 tokens x one
+// quantization block; tokens sit on the 8-wide N side, so T = 3..8 costs the same as T = 1.
+// K = 32 per instruction = one block, so the s32 fragment IS sumi[16 rows][8 tokens] of that block
+// and the reference's per-block fold (qgemm_common.cuh) is applied to it in registers.
+//
+//   * two CTAs per SM; producer warp streams tiles of 16 weight rows (one bulk copy per row into a
+//     padded smem pitch, so the 8 row-groups of a fragment load hit different banks)
+//   * 8 consumer warps split K: warp w owns blocks [w*NBW, (w+1)*NBW) of all 16 rows, its
+//     activation fragments (2 registers per block) live in registers for the whole kernel
+//   * per tile: 8 partial 16x8 tiles are combined through smem in warp order (deterministic)
+#include "ptx.cuh"
+#include "qgemm_common.cuh"
+
+namespace qgemm {
+
+constexpr int kMmaWarps = 8;
+constexpr int kMmaThreads = (kMmaWarps + 1) * 32;
+constexpr int kMmaRows = 16;          // weight rows per tile = MMA M
+constexpr int kMmaStagesMax = 4;
+constexpr int kMmaSmemBudget = 110 * 1024;   // two CTAs per SM when two stages fit in this
+constexpr int kMmaSmemMax = 200 * 1024;      // otherwise one CTA per SM (long or 8-bit rows)
+
+struct GemvMmaParams {
+    const uint8_t* act;
+    const uint8_t* wgt;
+    float* C;
+    int T, F, nb;
+    int64_t ldc_t, ldc_f;
+    int pitch;        // smem bytes per weight row (row bytes + 16: pitch % 128 == 16)
+    int stages;
+    int pdl;
+};
+
+__device__ __forceinline__ void mma_u8s8(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_s8s8(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// A-fragment registers of one weight row for thread-in-group `tig`:
+//   lo = elements 4*tig .. 4*tig+3, hi = elements 16+4*tig .. 16+4*tig+3   (un-offset u8, or s8 for q8_0)
+template <int WT>
+__device__ __forceinline__ void row_frag(const uint8_t* blk, int tig, uint32_t& lo, uint32_t& hi, WScale& ws) {
+    using Fm = Fmt<WT>;
+    ws = load_wscale<WT>(blk);
+    if constexpr (Fm::bits == 8) {
+        lo = ld_u32_a2(blk + Fm::qs + 4 * tig);
+        hi = ld_u32_a2(blk + Fm::qs + 16 + 4 * tig);
+    } else {
+        const uint32_t v = ld_u32_a2(blk + Fm::qs + 4 * tig);
+        lo = v & 0x0f0f0f0fu;
+        hi = (v >> 4) & 0x0f0f0f0fu;
+        if constexpr (Fm::bits == 5) {
+            const uint32_t qh = ld_u32_a2(blk + Fm::qh);
+            lo |= spread_qh4(qh, 4 * tig);
+            hi |= spread_qh4(qh, 16 + 4 * tig);
+        }
+    }
+}
+
+// NBW = K-blocks per warp held as register fragments
+template <int WT, int NBW, bool kMsExact>
+__global__ void __launch_bounds__(kMmaThreads, 2) gemv_mma_kernel(const GemvMmaParams p) {
+    using Fm = Fmt<WT>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tig = lane & 3;
+    const int nb = p.nb;
+
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);         // [kMmaStagesMax]
+    uint64_t* empty = full + kMmaStagesMax;                     // [kMmaStagesMax]
+    float* red = reinterpret_cast<float*>(smem + 128);          // [2][kMmaWarps][16 rows][8 tokens]
+    float2* a_sc = reinterpret_cast<float2*>(smem + 128 + 2 * kMmaWarps * 128 * 4);  // [nb][8] (d_a, c_a)
+    const uint32_t stage_bytes = (uint32_t)kMmaRows * p.pitch;
+    uint8_t* stage0 = smem + ((128u + 2u * kMmaWarps * 128u * 4u + (uint32_t)nb * 64u + 127u) & ~127u);
+
+    const int ntiles_total = (p.F + kMmaRows - 1) / kMmaRows;
+    const int t_begin = (int)(((int64_t)ntiles_total * blockIdx.x) / gridDim.x);
+    const int t_end = (int)(((int64_t)ntiles_total * (blockIdx.x + 1)) / gridDim.x);
+    const size_t rowbytes = (size_t)nb * Fm::bytes;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.stages; s++) {
+            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&empty[s], kMmaWarps);
+        }
+        ptx::fence_mbar_init();
+    }
+    __syncthreads();
+    if (p.pdl) ptx::griddep_launch_dependents();
+
+    if (warp == kMmaWarps) {
+        // ===== producer: one bulk copy per weight row into the padded pitch
+        int s = 0;
+        uint32_t ph = 0;
+        for (int t = t_begin; t < t_end; t++) {
+            ptx::mbar_wait(&empty[s], ph ^ 1);
+            if (lane == 0) ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(kMmaRows * rowbytes));
+            __syncwarp();
+            if (lane < kMmaRows) {
+                const int f = min(t * kMmaRows + lane, p.F - 1);  // tail tile: re-read a valid row, never stored
+                ptx::bulk_g2s(stage0 + (size_t)s * stage_bytes + (size_t)lane * p.pitch, p.wgt + (size_t)f * rowbytes,
+                              (uint32_t)rowbytes, &full[s]);
+            }
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+        return;
+    }
+
+    // ===== consumers
+    if (p.pdl) ptx::griddep_wait();
+    const int b0 = warp * NBW;
+    // B fragments: token g (zero beyond T), elements 4*tig.. and 16+4*tig.. of each of this warp's blocks
+    uint32_t bf[NBW][2];
+#pragma unroll
+    for (int i = 0; i < NBW; i++) {
+        const int b = b0 + i;
+        bf[i][0] = bf[i][1] = 0u;
+        if (b < nb && g < p.T) {
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(p.act + ((size_t)g * nb + b) * kQ81Bytes);
+            bf[i][0] = __ldg(q + 1 + tig);
+            bf[i][1] = __ldg(q + 5 + tig);
+        }
+    }
+    // activation scales of all blocks, all 8 token slots: [b][token] (d_a, c_a)
+    for (int i = tid; i < nb * 8; i += kMmaWarps * 32) {
+        const int b = i >> 3, t = i & 7;
+        ActScale sc{0.f, 0.f};
+        if (t < p.T) {
+            const uint32_t ds = __ldg(reinterpret_cast<const uint32_t*>(p.act + ((size_t)t * nb + b) * kQ81Bytes));
+            sc = prep_act_scale<WT, kMsExact>(half_bits_to_float(ds), half_bits_to_float(ds >> 16));
+        }
+        a_sc[i] = make_float2(sc.d, sc.s);
+    }
+    ptx::bar_sync(1, kMmaWarps * 32);
+
+    int s = 0, par = 0;
+    uint32_t ph = 0;
+    for (int t = t_begin; t < t_end; t++, par ^= 1) {
+        ptx::mbar_wait(&full[s], ph);
+        const uint8_t* r0 = stage0 + (size_t)s * stage_bytes + (size_t)g * p.pitch;
+        const uint8_t* r1 = r0 + (size_t)8 * p.pitch;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};  // (row g, tok 2tig), (row g, tok 2tig+1), (row g+8, ...)
+#pragma unroll
+        for (int i = 0; i < NBW; i++) {
+            const int b = b0 + i;
+            if (b < nb) {
+                uint32_t a[4];
+                WScale w0, w1;
+                row_frag<WT>(r0 + (size_t)b * Fm::bytes, tig, a[0], a[2], w0);
+                row_frag<WT>(r1 + (size_t)b * Fm::bytes, tig, a[1], a[3], w1);
+                int c[4] = {0, 0, 0, 0};
+                if constexpr (Fm::bits == 8) mma_s8s8(c, a, bf[i][0], bf[i][1]);
+                else mma_u8s8(c, a, bf[i][0], bf[i][1]);
+                const float4 sc = *reinterpret_cast<const float4*>(&a_sc[b * 8 + 2 * tig]);  // tokens 2tig, 2tig+1
+                acc[0] = fold_block_pre<WT>(acc[0], c[0], w0, ActScale{sc.x, sc.y});
+                acc[1] = fold_block_pre<WT>(acc[1], c[1], w0, ActScale{sc.z, sc.w});
+                acc[2] = fold_block_pre<WT>(acc[2], c[2], w1, ActScale{sc.x, sc.y});
+                acc[3] = fold_block_pre<WT>(acc[3], c[3], w1, ActScale{sc.z, sc.w});
+            }
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&empty[s]);
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+
+        // combine the 8 K-slices in warp order
+        float* rb = red + par * (kMmaWarps * 128);
+        rb[warp * 128 + g * 8 + 2 * tig] = acc[0];
+        rb[warp * 128 + g * 8 + 2 * tig + 1] = acc[1];
+        rb[warp * 128 + (g + 8) * 8 + 2 * tig] = acc[2];
+        rb[warp * 128 + (g + 8) * 8 + 2 * tig + 1] = acc[3];
+        ptx::bar_sync(1, kMmaWarps * 32);
+        if (tid < 128) {
+            const int r = tid >> 3, tok = tid & 7;
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < kMmaWarps; w++) v += rb[w * 128 + tid];
+            const int f = t * kMmaRows + r;
+            if (f < p.F && tok < p.T) p.C[(int64_t)tok * p.ldc_t + (int64_t)f * p.ldc_f] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+bool gemv_mma_supported(int wtype, const void* act, const void* wgt, int T, int F, int K) {
+    const int nb = K / 32;
+    const size_t rowbytes = (size_t)nb * block_bytes(wtype);
+    if (T < 1 || F < 1 || nb < 8 || nb > kMmaWarps * 32) return false;     // <= 32 blocks per warp in registers
+    if (rowbytes % 16 != 0) return false;
+    if (reinterpret_cast<uintptr_t>(wgt) % 16 != 0 || reinterpret_cast<uintptr_t>(act) % 4 != 0) return false;
+    const size_t pitch = rowbytes + 16 + ((128 - (rowbytes % 128)) % 128);
+    const size_t fixed = 128 + 2 * kMmaWarps * 128 * 4 + (size_t)nb * 64 + 128;
+    return fixed + 2 * kMmaRows * pitch <= (size_t)kMmaSmemMax;
+}
+
+template <int WT, int NBW>
+static cudaError_t launch_mma_inst(const GemvMmaParams& p, size_t smem, int grid, bool ms_exact, cudaStream_t st) {
+    auto launch = [&](auto kernel, int variant) -> cudaError_t {
+        static size_t attr_set[2] = {0, 0};
+        if (smem > attr_set[variant]) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            attr_set[variant] = smem;
+        }
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kMmaThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = p.pdl ? 1 : 0;
+        return cudaLaunchKernelEx(&cfg, kernel, p);
+    };
+    cudaError_t e;
+    if constexpr (Fmt<WT>::m >= 0) {
+        e = ms_exact ? launch(gemv_mma_kernel<WT, NBW, true>, 1) : launch(gemv_mma_kernel<WT, NBW, false>, 0);
+    } else {
+        e = launch(gemv_mma_kernel<WT, NBW, false>, 0);
+    }
+    note_launch();
+    return e;
+}
+
+template <int WT>
+static cudaError_t launch_mma_wt(const GemvMmaParams& p, size_t smem, int grid, bool ms, cudaStream_t st) {
+    const int nbw = (p.nb + kMmaWarps - 1) / kMmaWarps;
+    if (nbw <= 8) return launch_mma_inst<WT, 8>(p, smem, grid, ms, st);
+    if (nbw <= 16) return launch_mma_inst<WT, 16>(p, smem, grid, ms, st);
+    return launch_mma_inst<WT, 32>(p, smem, grid, ms, st);
+}
+
+// T tokens in passes of 8
+cudaError_t launch_gemv_mma(int wtype, const void* act, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
+                            int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t st) {
+    const int nb = K / 32;
+    const size_t rowbytes = (size_t)nb * block_bytes(wtype);
+    const int pitch = (int)(rowbytes + 16 + ((128 - (rowbytes % 128)) % 128));
+    const size_t fixed = 128 + 2 * kMmaWarps * 128 * 4 + (size_t)nb * 64 + 128;
+    const size_t budget = (fixed + 2 * (size_t)kMmaRows * pitch <= (size_t)kMmaSmemBudget) ? kMmaSmemBudget : kMmaSmemMax;
+    int stages = (int)((budget - fixed) / ((size_t)kMmaRows * pitch));
+    stages = max(2, min(kMmaStagesMax, stages));
+    const int ntiles = (F + kMmaRows - 1) / kMmaRows;
+    const int grid = min(ntiles, 2 * num_sms);
+    stages = max(2, min(stages, (ntiles + grid - 1) / grid));
+    const size_t smem = fixed + (size_t)stages * kMmaRows * pitch;
+    for (int t0 = 0; t0 < T; t0 += 8) {
+        GemvMmaParams p;
+        p.act = (const uint8_t*)act + (size_t)t0 * nb * kQ81Bytes;
+        p.wgt = (const uint8_t*)wgt;
+        p.C = C + (int64_t)t0 * ldc_t;
+        p.T = min(8, T - t0); p.F = F; p.nb = nb; p.ldc_t = ldc_t; p.ldc_f = ldc_f;
+        p.pitch = pitch; p.stages = stages; p.pdl = (flags & QGEMM_WEIGHTS_STATIC) ? 1 : 0;
+        const bool ms = flags & QGEMM_MS_EXACT;
+        cudaError_t e;
+        switch (wtype) {
+        case QGEMM_TYPE_Q4_0: e = launch_mma_wt<QGEMM_TYPE_Q4_0>(p, smem, grid, ms, st); break;
+        case QGEMM_TYPE_Q4_1: e = launch_mma_wt<QGEMM_TYPE_Q4_1>(p, smem, grid, ms, st); break;
+        case QGEMM_TYPE_Q5_0: e = launch_mma_wt<QGEMM_TYPE_Q5_0>(p, smem, grid, ms, st); break;
+        case QGEMM_TYPE_Q5_1: e = launch_mma_wt<QGEMM_TYPE_Q5_1>(p, smem, grid, ms, st); break;
+        case QGEMM_TYPE_Q8_0: e = launch_mma_wt<QGEMM_TYPE_Q8_0>(p, smem, grid, ms, st); break;
+        default: e = cudaErrorInvalidValue;
+        }
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+}  // namespace qgemm

@@ -19,12 +19,16 @@ cudaError_t launch_sumi_generic(int wtype, const void* act, const void* wgt, int
 bool gemv_supported(int wtype, const void* act, const void* wgt, int F, int K);
 cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
                         int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t);
+bool gemv_mma_supported(int wtype, const void* act, const void* wgt, int T, int F, int K);
+cudaError_t launch_gemv_mma(int wtype, const void* act, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
+                            int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t);
 bool mmq_supported(int wtype, const void* act, const void* wgt, int T, int F, int K);
 size_t mmq_workspace_bytes(int wtype, int T, int F, int K);
 cudaError_t launch_mmq(int wtype, const void* act, const void* wgt, float* C, int32_t* sumi_out, int T, int F, int K,
                        int64_t ldc_t, int64_t ldc_f, uint32_t flags, void* ws, size_t ws_bytes, int num_sms,
                        cudaStream_t);
 
+constexpr int kMmaMinTokens = 3;   // dp4a GEMV below, mma.sync skinny path from here
 constexpr int kMmqMinTokens = 64;  // AUTO switches from the weight-streaming path to tensor cores here
 
 static std::atomic<int64_t> g_launches{0};
@@ -112,6 +116,8 @@ static int run_gemm(int wtype, const void* act, const void* wgt, float* C, int T
     if (path == QGEMM_PATH_AUTO) {
         if (T >= kMmqMinTokens && mmq_supported(wtype, act, wgt, T, F, K) && ws && ws_bytes >= mmq_workspace_bytes(wtype, T, F, K))
             path = QGEMM_PATH_TCGEN05;
+        else if (T >= kMmaMinTokens && gemv_mma_supported(wtype, act, wgt, T, F, K))
+            path = QGEMM_PATH_MMA;
         else if (gemv_supported(wtype, act, wgt, F, K))
             path = QGEMM_PATH_GEMV;
         else
@@ -123,12 +129,14 @@ static int run_gemm(int wtype, const void* act, const void* wgt, float* C, int T
         if (!gemv_supported(wtype, act, wgt, F, K)) return QGEMM_E_ALIGN;
         e = launch_gemv(wtype, act, wgt, C, T, F, K, ldc_t, ldc_f, flags, dev.sms, st);
         break;
-    case QGEMM_PATH_TCGEN05:
     case QGEMM_PATH_MMA:
+        if (!gemv_mma_supported(wtype, act, wgt, T, F, K)) return QGEMM_E_ALIGN;
+        e = launch_gemv_mma(wtype, act, wgt, C, T, F, K, ldc_t, ldc_f, flags, dev.sms, st);
+        break;
+    case QGEMM_PATH_TCGEN05:
         if (!mmq_supported(wtype, act, wgt, T, F, K)) return QGEMM_E_ALIGN;
         if (!ws || ws_bytes < mmq_workspace_bytes(wtype, T, F, K)) return QGEMM_E_WORKSPACE;
         e = launch_mmq(wtype, act, wgt, C, nullptr, T, F, K, ldc_t, ldc_f, flags, ws, ws_bytes, dev.sms, st);
-        path = QGEMM_PATH_TCGEN05;
         break;
     case QGEMM_PATH_GENERIC:
         e = launch_gemm_sequential(wtype, act, wgt, C, T, F, K, ldc_t, ldc_f, flags, st);
@@ -206,7 +214,7 @@ size_t qgemm_workspace_bytes(int wtype, int T, int F, int K, uint32_t flags) {
     // [ q8_1 copy of A for qgemm_gemm_f32act | tensor-core path scratch (only where that path can run) ]
     const size_t a_q = align_up((size_t)T * (K / kQK) * kQ81Bytes, 256);
     const uint32_t path = flags & QGEMM_PATH_MASK;
-    const bool mmq = (path == QGEMM_PATH_TCGEN05 || path == QGEMM_PATH_MMA || (path == QGEMM_PATH_AUTO && T >= kMmqMinTokens)) &&
+    const bool mmq = (path == QGEMM_PATH_TCGEN05 || (path == QGEMM_PATH_AUTO && T >= kMmqMinTokens)) &&
                      !(flags & QGEMM_SEQUENTIAL);
     return a_q + (mmq ? align_up(mmq_workspace_bytes(wtype, T, F, K), 256) : 0);
 }
@@ -257,7 +265,7 @@ int qgemm_sumi(int wtype, const void* act_q8_1, const void* weight, int32_t* sum
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t path = flags & QGEMM_PATH_MASK;
     cudaError_t e;
-    if (path == QGEMM_PATH_TCGEN05 || path == QGEMM_PATH_MMA) {
+    if (path == QGEMM_PATH_TCGEN05) {
         if (!mmq_supported(wtype, act_q8_1, weight, T, F, K)) return QGEMM_E_ALIGN;
         if (!workspace || workspace_bytes < mmq_workspace_bytes(wtype, T, F, K)) return QGEMM_E_WORKSPACE;
         e = launch_mmq(wtype, act_q8_1, weight, nullptr, sumi, T, F, K, 0, 0, flags, workspace, workspace_bytes,

@@ -131,7 +131,7 @@ def test_sumi_bit_exact_fuzz(qg, O, wt):
 # ------------------------------------------------------------------------------------------
 # GEMM parity
 # ------------------------------------------------------------------------------------------
-PATHS = {"auto": 0, "gemv": 0x200, "generic": 0x100}
+PATHS = {"auto": 0, "gemv": 0x200, "generic": 0x100, "mma": 0x300}
 
 
 def run_gemm(qg, wt, aq, wq, path, flags=0):
@@ -368,3 +368,34 @@ def test_mmq_full_size_prefill_properties(qg, O):
     perm = np.random.default_rng(1).permutation(T)
     c2 = host(qg.gemm(dwq, dev(aq[perm]), F, T, K, qo.Q4_0))
     assert (bits(c2) == bits(c[:, perm])).all()
+
+
+# ------------------------------------------------------------------------------------------
+# skinny path: mma.sync m16n8k32 with tokens on N (QGEMM_PATH_MMA), 3 <= T < 64
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("wt", qo.WEIGHT_TYPES)
+@pytest.mark.parametrize("T,F,K", [(3, 256, 4096), (8, 130, 2048), (5, 33, 256), (8, 512, 8192), (20, 96, 1024), (1, 64, 512)])
+def test_mma_skinny_vs_oracle(qg, O, wt, T, F, K):
+    x, w = datagen.model_like(T, F, K, seed=T * 3 + F)
+    aq, wq = O.quantize_q8_1(x), O.quantize_weight(wt, w)
+    try:
+        c = run_gemm(qg, wt, aq, wq, "mma")
+    except RuntimeError as e:  # a forced path refuses shapes whose 16-row tile does not fit in shared memory
+        if K >= 8192 and "cannot take this layout" in str(e):
+            pytest.skip("tile too large for the skinny path at this K / format")
+        raise
+    assert qg.last_path() == 0x300
+    check_c(c, O.gemm(wt, aq, wq, layout="FT"), f"mma {qo.TYPE_NAMES[wt]} {T}x{F}x{K}")
+
+
+@pytest.mark.parametrize("wt", [qo.Q4_0, qo.Q5_1, qo.Q8_0])
+def test_mma_skinny_fuzz_and_auto(qg, O, wt):
+    T, F, nb = 7, 200, 64
+    wq = datagen.fuzz_weight_blocks(wt, F, nb, seed=31 + wt)
+    aq = datagen.fuzz_act_blocks(T, nb, seed=31 + wt, const_ds=False)
+    for fl in (0, qo.GEMM_MS_EXACT):
+        check_c(run_gemm(qg, wt, aq, wq, "mma", flags=fl), O.gemm(wt, aq, wq, layout="FT", flags=fl), "mma fuzz")
+    run_gemm(qg, wt, aq, wq, "auto")
+    assert qg.last_path() == 0x300        # AUTO: dp4a GEMV for T <= 2, mma.sync from 3, tcgen05 from 64
+    run_gemm(qg, wt, aq[:2], wq, "auto")
+    assert qg.last_path() == 0x200
