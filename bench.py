@@ -181,7 +181,7 @@ def workload_config(n_gpus):
                         "Q4_0 weights x Q8_1 activations (BASELINE configs[1])",
             "launches_per_step": 224, "weight_bytes_per_gpu": 32 * sum(F * (K // 32) * 18 for _, F, K in LLAMA7B),
             "l2_defeat": "inputs larger than L2: 3.64 GB of distinct weights per step vs 126 MB L2",
-            "parallelism": f"weight rows (N) sharded x{n_gpus}, all-gather of C" if n_gpus > 1 else "1 GPU",
+            "parallelism": f"weight rows (N) sharded x{n_gpus}, all-gather of C fused into the GEMV kernel (NVLink peer stores)" if n_gpus > 1 else "1 GPU",
             "timing": "CUDA events on the launch stream around K graph replays, max over ranks"}
 
 
@@ -196,6 +196,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layers", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: all-gather fused into the kernel (peer stores over NVLink) or NCCL per GEMV")
     ap.add_argument("--detail", default=None, help="write a per-shape sweep (all formats, M=1..8, prefill) to this JSON file")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -243,12 +245,25 @@ def main():
     step_bytes = sum(algorithmic_bytes(WTYPE, 1, F, K) for F, K, _ in mats)
 
     from quant_gemm import sharded
-    # every rank owns rows [rank*F, (rank+1)*F) of an (N*F)-row matrix; C is all-gathered in place
-    ops = [sharded.ShardedGemm(w, F * world, K, WTYPE, flags=GEMV_FLAGS) for F, K, w in mats]
+    # every rank owns rows [rank*F, (rank+1)*F) of an (N*F)-row matrix
+    plan = None
+    if world > 1 and args.gather == "fused":
+        # all-gather fused into the GEMV: the kernel stores its slice of C into every rank's gathered
+        # buffer over NVLink (symmetric memory) and signals with device-side counters
+        plan = sharded.PeerPlan(sum(F * world for F, K, _ in mats), len(mats), dev, ctl_group=ctl)
+        ops = [sharded.ShardedGemvP2P(w, F * world, K, WTYPE, 1, plan, flags=GEMV_FLAGS) for F, K, w in mats]
+        outs = [op.out for op in ops]
+    else:  # baseline: in-place NCCL all-gather after every GEMV
+        ops = [sharded.ShardedGemm(w, F * world, K, WTYPE, flags=GEMV_FLAGS) for F, K, w in mats]
 
     def gemv_all():
-        for op, (F, K, w), o in zip(ops, mats, outs):
-            op(acts_q[K], out=o)
+        if plan is not None:
+            for op, (F, K, w) in zip(ops, mats):
+                op(acts_q[K])
+            plan.end_step()
+        else:
+            for op, (F, K, w), o in zip(ops, mats, outs):
+                op(acts_q[K], out=o)
 
     def e2e_step():
         for K in acts_host:

@@ -171,6 +171,35 @@ QGEMM_API int qgemm_gemm_f32act(int wtype, const float *act_f32, const void *wei
 QGEMM_API int qgemm_sumi(int wtype, const void *act_q8_1, const void *weight, int32_t *sumi, int T, int F, int K,
                uint32_t flags, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- multi-GPU: N-sharded decode with the all-gather fused into the kernel --------
+ *
+ * New functionality (the reference has no multi-GPU code).  Weight rows
+ * are sharded across `world` GPUs of one NVLink/NVSwitch domain; every rank calls
+ * qgemm_gemm_peers() with ITS rows and the kernel stores its slice of C directly into every
+ * rank's copy of the gathered buffer (peer stores over NVLink) -- no separate all-gather.
+ * Completion is tracked by device-side counters in peer-accessible memory:
+ *   - all ranks issue the same sequence of launches; a "step" is `launches_per_step` launches
+ *     followed by qgemm_peer_step_advance(step) (so the sequence can sit in a CUDA graph);
+ *   - launch q waits, before reading its activations, until every rank's launches < q have
+ *     landed locally; qgemm_peer_wait() does the same for the end of the current step.
+ * C[r] / flag[r] are peer-mapped device pointers (e.g. torch symmetric memory, cudaIpc, or
+ * cuMem fabric handles); flag words and `done`/`step` must start at zero.  T <= 8 only.
+ */
+#define QGEMM_MAX_PEERS 8
+typedef struct qgemm_peers {
+    int world, rank;
+    float *C[QGEMM_MAX_PEERS];        /* rank r's destination of this launch's slice (same logical offset everywhere) */
+    uint32_t *flag[QGEMM_MAX_PEERS];  /* rank r's arrival counter */
+    uint32_t *done;                   /* local scratch counter */
+    const uint32_t *step;             /* local step counter */
+    uint32_t launches_per_step, launch_index;
+} qgemm_peers;
+
+QGEMM_API int qgemm_gemm_peers(int wtype, const void *act_q8_1, const void *weight, const qgemm_peers *peers, int T,
+                               int F, int K, int64_t ldc_t, int64_t ldc_f, uint32_t flags, void *stream);
+QGEMM_API int qgemm_peer_step_advance(uint32_t *step, void *stream);
+QGEMM_API int qgemm_peer_wait(const qgemm_peers *peers, void *stream);
+
 /* ---- multi-GPU sharding helper (host arithmetic only) ------------------------ */
 /*
  * Weight rows [0,F) split into `world` contiguous ranges whose sizes are

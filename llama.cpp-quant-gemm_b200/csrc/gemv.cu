@@ -156,6 +156,7 @@ struct GemvParams {
     int stage_bytes;      // 128-byte multiple
     int pdl;              // programmatic dependent launch in use
     int nocompute;        // tuning aid: stream the tiles, skip the math (memory-system ceiling)
+    PeerOut peer;         // fused all-gather (world <= 1: plain store to C)
 };
 
 // PPL > 0: activations in registers, PPL pairs per lane.  PPL == 0: activations in smem.
@@ -215,6 +216,10 @@ __global__ void __launch_bounds__(kGemvThreads, kGemvCtasPerSm) gemv_kernel(cons
 
     // ================= consumer warps =================
     if (p.pdl) ptx::griddep_wait();  // activations / C may belong to the previous launch
+    if (p.peer.world > 1) {          // ... or to an earlier launch of a peer GPU
+        if (tid == 0) peer_wait_prior(p.peer);
+        ptx::bar_sync(1, kGemvWarps * 32);
+    }
     const int WPR = p.WPR;
     const int rpp = kGemvWarps / WPR;            // rows per pass
     const int rslot = warp / WPR, sub = warp - rslot * WPR;
@@ -335,7 +340,7 @@ __global__ void __launch_bounds__(kGemvThreads, kGemvCtasPerSm) gemv_kernel(cons
                     float v = acc[0];
 #pragma unroll
                     for (int tt = 1; tt < TT; tt++) v = (lane == tt) ? acc[tt] : v;
-                    p.C[(int64_t)lane * p.ldc_t + (int64_t)(r0 + r) * p.ldc_f] = v;
+                    peer_store(p.peer, p.C, (int64_t)lane * p.ldc_t + (int64_t)(r0 + r) * p.ldc_f, v);
                 }
             } else {
                 float* sl = slots + spar * (kGemvWarps * 8);
@@ -350,7 +355,7 @@ __global__ void __launch_bounds__(kGemvThreads, kGemvCtasPerSm) gemv_kernel(cons
                     if (rr < rows) {
                         float v = 0.f;
                         for (int k = 0; k < WPR; k++) v += sl[(rs * WPR + k) * 8 + tt];
-                        p.C[(int64_t)tt * p.ldc_t + (int64_t)(r0 + rr) * p.ldc_f] = v;
+                        peer_store(p.peer, p.C, (int64_t)tt * p.ldc_t + (int64_t)(r0 + rr) * p.ldc_f, v);
                     }
                 }
                 spar ^= 1;
@@ -359,6 +364,11 @@ __global__ void __launch_bounds__(kGemvThreads, kGemvCtasPerSm) gemv_kernel(cons
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&empty[s]);
         if (++s == p.stages) { s = 0; ph ^= 1; }
+    }
+    if (p.peer.world > 1) {
+        if (!(p.peer.dbg & 4)) __threadfence();  // this thread's peer stores are ordered before the CTA barrier                  // this thread's peer stores are out
+        ptx::bar_sync(1, kGemvWarps * 32);
+        if (tid == 0) peer_signal_done(p.peer, gridDim.x);
     }
 }
 
@@ -466,7 +476,7 @@ static cudaError_t launch_gemv_wt(const GemvPlan& pl, const GemvParams& p, int g
 }
 
 cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
-                        int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t st) {
+                        int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t st, const PeerOut* peer) {
     const int nb = K / 32;
     const bool ms = flags & QGEMM_MS_EXACT;
     GemvPlan pl;
@@ -484,6 +494,11 @@ cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, i
         p.RT = cur.rt; p.WPR = cur.wpr; p.stages = cur.stages; p.stage_bytes = cur.stage_bytes;
         p.pdl = pdl ? 1 : 0;
         p.nocompute = getenv("QGEMM_GEMV_NOCOMPUTE") ? 1 : 0;
+        p.peer = PeerOut{};
+        if (peer) {
+            if (T > pl.tt) return cudaErrorInvalidValue;  // peer mode: one pass per launch (flag accounting)
+            p.peer = *peer;
+        }
         cudaError_t e;
         switch (wtype) {
         case QGEMM_TYPE_Q4_0: e = launch_gemv_wt<QGEMM_TYPE_Q4_0>(cur, p, grid, ms, st); break;

@@ -33,6 +33,7 @@ struct GemvMmaParams {
     int pitch;        // smem bytes per weight row (row bytes + 16: pitch % 128 == 16)
     int stages;
     int pdl;
+    PeerOut peer;
 };
 
 __device__ __forceinline__ void mma_u8s8(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -120,6 +121,10 @@ __global__ void __launch_bounds__(kMmaThreads, 2) gemv_mma_kernel(const GemvMmaP
 
     // ===== consumers
     if (p.pdl) ptx::griddep_wait();
+    if (p.peer.world > 1) {
+        if (tid == 0) peer_wait_prior(p.peer);
+        ptx::bar_sync(1, kMmaWarps * 32);
+    }
     const int b0 = warp * NBW;
     // B fragments: token g (zero beyond T), elements 4*tig.. and 16+4*tig.. of each of this warp's blocks
     uint32_t bf[NBW][2];
@@ -187,8 +192,13 @@ __global__ void __launch_bounds__(kMmaThreads, 2) gemv_mma_kernel(const GemvMmaP
 #pragma unroll
             for (int w = 0; w < kMmaWarps; w++) v += rb[w * 128 + tid];
             const int f = t * kMmaRows + r;
-            if (f < p.F && tok < p.T) p.C[(int64_t)tok * p.ldc_t + (int64_t)f * p.ldc_f] = v;
+            if (f < p.F && tok < p.T) peer_store(p.peer, p.C, (int64_t)tok * p.ldc_t + (int64_t)f * p.ldc_f, v);
         }
+    }
+    if (p.peer.world > 1) {
+        if (!(p.peer.dbg & 4)) __threadfence();  // this thread's peer stores are ordered before the CTA barrier
+        ptx::bar_sync(1, kMmaWarps * 32);
+        if (tid == 0) peer_signal_done(p.peer, gridDim.x);
     }
 }
 
@@ -247,7 +257,8 @@ static cudaError_t launch_mma_wt(const GemvMmaParams& p, size_t smem, int grid, 
 
 // T tokens in passes of 8
 cudaError_t launch_gemv_mma(int wtype, const void* act, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
-                            int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t st) {
+                            int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t st, const PeerOut* peer) {
+    if (peer && T > 8) return cudaErrorInvalidValue;  // peer mode: one pass per launch
     const int nb = K / 32;
     const size_t rowbytes = (size_t)nb * block_bytes(wtype);
     const int pitch = (int)(rowbytes + 16 + ((128 - (rowbytes % 128)) % 128));
@@ -266,6 +277,7 @@ cudaError_t launch_gemv_mma(int wtype, const void* act, const void* wgt, float* 
         p.C = C + (int64_t)t0 * ldc_t;
         p.T = min(8, T - t0); p.F = F; p.nb = nb; p.ldc_t = ldc_t; p.ldc_f = ldc_f;
         p.pitch = pitch; p.stages = stages; p.pdl = (flags & QGEMM_WEIGHTS_STATIC) ? 1 : 0;
+        p.peer = peer ? *peer : PeerOut{};
         const bool ms = flags & QGEMM_MS_EXACT;
         cudaError_t e;
         switch (wtype) {

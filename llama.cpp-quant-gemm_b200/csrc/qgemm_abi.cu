@@ -2,6 +2,7 @@
 // argument validation, device check, path selection, launch bookkeeping.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "qgemm_common.cuh"
@@ -18,10 +19,10 @@ cudaError_t launch_sumi_generic(int wtype, const void* act, const void* wgt, int
                                 cudaStream_t);
 bool gemv_supported(int wtype, const void* act, const void* wgt, int F, int K);
 cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
-                        int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t);
+                        int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t, const PeerOut* peer = nullptr);
 bool gemv_mma_supported(int wtype, const void* act, const void* wgt, int T, int F, int K);
 cudaError_t launch_gemv_mma(int wtype, const void* act, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
-                            int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t);
+                            int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t, const PeerOut* peer = nullptr);
 bool mmq_supported(int wtype, const void* act, const void* wgt, int T, int F, int K);
 size_t mmq_workspace_bytes(int wtype, int T, int F, int K);
 cudaError_t launch_mmq(int wtype, const void* act, const void* wgt, float* C, int32_t* sumi_out, int T, int F, int K,
@@ -85,6 +86,12 @@ static int check_gemm_args(int wtype, const void* act, const void* wgt, const vo
     if (!act || !wgt || !out) return QGEMM_E_BADARG;
     if (!aligned(act, 4) || !aligned(wgt, 2) || !aligned(out, 4)) return QGEMM_E_ALIGN;
     return QGEMM_OK;
+}
+
+__global__ void peer_step_advance_kernel(uint32_t* step) { *step = *step + 1u; }
+__global__ void peer_wait_kernel(const uint32_t* flag, const uint32_t* step, uint32_t lps, uint32_t world) {
+    const uint32_t target = (*step) * lps * world + lps * world;  // every launch of the current step, every rank
+    while ((int32_t)(ld_acquire_sys(flag) - target) < 0) __nanosleep(64);
 }
 
 __global__ void fill_zero_strided(float* C, int T, int F, int64_t ldc_t, int64_t ldc_f) {
@@ -274,6 +281,53 @@ int qgemm_sumi(int wtype, const void* act_q8_1, const void* weight, int32_t* sum
         e = launch_sumi_generic(wtype, act_q8_1, weight, sumi, T, F, K, st);
     }
     return e == cudaSuccess ? QGEMM_OK : QGEMM_E_CUDA;
+}
+
+int qgemm_gemm_peers(int wtype, const void* act_q8_1, const void* weight, const qgemm_peers* peers, int T, int F, int K,
+                     int64_t ldc_t, int64_t ldc_f, uint32_t flags, void* stream) {
+    if (!peers || peers->world < 1 || peers->world > kMaxPeers || peers->rank < 0 || peers->rank >= peers->world ||
+        !peers->done || !peers->step || peers->launches_per_step == 0 || peers->launch_index >= peers->launches_per_step)
+        return QGEMM_E_BADARG;
+    for (int r = 0; r < peers->world; r++)
+        if (!peers->C[r] || !peers->flag[r]) return QGEMM_E_BADARG;
+    float* C = peers->C[peers->rank];
+    if (int rc = check_gemm_args(wtype, act_q8_1, weight, C, T, F, K)) return rc;
+    if (T == 0 || F == 0 || K == 0) return QGEMM_E_BADARG;  // every rank must launch: no empty shards in peer mode
+    DeviceInfo dev;
+    if (int rc = device_check(&dev)) return rc;
+    PeerOut po{};
+    po.world = peers->world; po.rank = peers->rank;
+    for (int r = 0; r < peers->world; r++) { po.C[r] = peers->C[r]; po.flag[r] = peers->flag[r]; }
+    po.done = peers->done; po.step = peers->step; po.lps = peers->launches_per_step; po.li = peers->launch_index;
+    po.dbg = getenv("QGEMM_PEER_DBG") ? atoi(getenv("QGEMM_PEER_DBG")) : 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    if (T >= kMmaMinTokens && T <= 8 && gemv_mma_supported(wtype, act_q8_1, weight, T, F, K)) {
+        e = launch_gemv_mma(wtype, act_q8_1, weight, C, T, F, K, ldc_t, ldc_f, flags, dev.sms, st, &po);
+        t_last_path = QGEMM_PATH_MMA;
+    } else if (T <= 8 && gemv_supported(wtype, act_q8_1, weight, F, K)) {
+        e = launch_gemv(wtype, act_q8_1, weight, C, T, F, K, ldc_t, ldc_f, flags, dev.sms, st, &po);
+        t_last_path = QGEMM_PATH_GEMV;
+    } else {
+        return QGEMM_E_ALIGN;  // peer stores are fused into the decode kernels only (T <= 8, bulk-copyable rows)
+    }
+    return e == cudaSuccess ? QGEMM_OK : cuda_fail(e, "gemm_peers launch");
+}
+
+int qgemm_peer_step_advance(uint32_t* step, void* stream) {
+    if (!step) return QGEMM_E_BADARG;
+    peer_step_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step);
+    note_launch();
+    return cudaGetLastError() == cudaSuccess ? QGEMM_OK : QGEMM_E_CUDA;
+}
+
+int qgemm_peer_wait(const qgemm_peers* peers, void* stream) {
+    if (!peers || peers->world < 1 || peers->world > kMaxPeers || !peers->step) return QGEMM_E_BADARG;
+    if (peers->world == 1) return QGEMM_OK;
+    peer_wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(peers->flag[peers->rank], peers->step, peers->launches_per_step,
+                                                        (uint32_t)peers->world);
+    note_launch();
+    return cudaGetLastError() == cudaSuccess ? QGEMM_OK : QGEMM_E_CUDA;
 }
 
 int qgemm_shard_range(int F, int world, int rank, int align, int* f0, int* f1) {

@@ -168,6 +168,69 @@ __device__ __forceinline__ WScale load_wscale(const uint8_t* blk) {
 }
 
 // ---------------------------------------------------------------------------
+// Fused all-gather: the decode kernels can store their slice of C straight into every
+// peer GPU's copy of the gathered buffer (NVLink peer stores) and signal completion with
+// system-scope counters, instead of a separate NCCL all-gather per GEMV.
+//   * launch q = step * launches_per_step + launch_index (same sequence on every rank)
+//   * before touching its activations, launch q waits until flag[rank] >= q * world:
+//     every rank's launches < q have landed here (the activations may derive from them)
+//   * the last CTA of a launch adds 1 to flag[r] on every rank r (release, system scope)
+// ---------------------------------------------------------------------------
+constexpr int kMaxPeers = 8;
+struct PeerOut {
+    int world;                    // 0 or 1: plain store to C
+    int rank;
+    float* C[kMaxPeers];          // rank r's destination for this launch's slice (same logical offset)
+    uint32_t* flag[kMaxPeers];    // rank r's arrival counter
+    uint32_t* done;               // local CTA-completion counter (returns to 0 after each launch)
+    const uint32_t* step;         // local step counter (qgemm_peer_step_advance)
+    uint32_t lps, li;             // launches per step, index of this launch inside the step
+    int dbg;                      // tuning aid: 1 skip wait, 2 local store only, 4 skip per-thread fence
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_sys_add(uint32_t* p, uint32_t v) {
+    asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// one thread: block until every earlier launch of every rank has landed in local memory
+__device__ __forceinline__ void peer_wait_prior(const PeerOut& po) {
+    if (po.world > 1 && !(po.dbg & 1)) {
+        const uint32_t target = ((*po.step) * po.lps + po.li) * (uint32_t)po.world;
+        while ((int32_t)(ld_acquire_sys(po.flag[po.rank]) - target) < 0) __nanosleep(64);
+    }
+}
+// every storing thread calls this after its last store; then, after a CTA-wide barrier, one
+// thread calls peer_signal_done()
+__device__ __forceinline__ void peer_store(const PeerOut& po, float* C, int64_t idx, float v) {
+    if (po.world > 1) {
+#pragma unroll 1
+        if (po.dbg & 2) { po.C[po.rank][idx] = v; return; }
+        for (int r = 0; r < po.world; r++) po.C[r][idx] = v;
+    } else {
+        C[idx] = v;
+    }
+}
+__device__ __forceinline__ void peer_signal_done(const PeerOut& po, unsigned grid) {
+    if (po.world > 1) {
+        // CTA-local barrier already ordered this CTA's peer stores before this thread.  A device-scope
+        // fence per CTA + one system-scope fence by the last CTA (release cumulativity) replaces a
+        // system-scope fence per CTA, which serialises chip-wide (measured: +12 us per launch).
+        if (!(po.dbg & 8)) __threadfence();
+        if (atomicAdd(po.done, 1u) == grid - 1) {   // last CTA of this launch on this GPU
+            *po.done = 0u;
+            if (!(po.dbg & 16)) __threadfence_system();
+            // fence.sys + relaxed system-scope atomics = one release pattern for all peers
+            // (a red.release.sys per peer costs a system fence each: measured +1.6 us per peer)
+            for (int r = 0; r < po.world; r++) atomicAdd_system(po.flag[r], 1u);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Host-side launch bookkeeping (defined in qgemm_abi.cu)
 // ---------------------------------------------------------------------------
 void note_launch(int n = 1);

@@ -34,6 +34,20 @@ SYMBOLS = {
     "qgemm_shard_range": (_i, [_i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
 }
 
+
+
+class QgemmPeers(C.Structure):
+    """struct qgemm_peers of include/qgemm.h"""
+    _fields_ = [("world", _i), ("rank", _i), ("C", _p * 8), ("flag", _p * 8), ("done", _p), ("step", _p),
+                ("launches_per_step", _u32), ("launch_index", _u32)]
+
+
+SYMBOLS.update({
+    "qgemm_gemm_peers": (_i, [_i, _p, _p, C.POINTER(QgemmPeers), _i, _i, _i, _i64, _i64, _u32, _p]),
+    "qgemm_peer_step_advance": (_i, [_p, _p]),
+    "qgemm_peer_wait": (_i, [C.POINTER(QgemmPeers), _p]),
+})
+
 _lib = None
 
 

@@ -86,3 +86,91 @@ class ShardedGemm:
             out = torch.empty((self.F_total, T), dtype=torch.float32, device=activation_q.device)
         self.local(activation_q, out)
         return self.gather(out)
+
+
+# ------------------------------------------------------------------------------------------
+# Decode: all-gather fused into the GEMV kernel (peer stores over NVLink, device-side flags)
+# ------------------------------------------------------------------------------------------
+class PeerPlan:
+    """Symmetric (peer-mapped) memory shared by the sharded decode GEMVs of one step.
+
+    Holds one gathered-output pool and the arrival counters; every ShardedGemvP2P of the step takes
+    a slice of the pool and a launch index.  torch symmetric memory provides the peer pointers; the
+    kernels do the rest (include/qgemm.h, qgemm_gemm_peers)."""
+
+    def __init__(self, pool_floats: int, launches_per_step: int, device: torch.device,
+                 group: Optional[dist.ProcessGroup] = None, ctl_group: Optional[dist.ProcessGroup] = None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        assert self.world <= 8
+        self.lps = launches_per_step
+        self.pool = symm_mem.empty(max(pool_floats, 1024), dtype=torch.float32, device=device)
+        self.flags = symm_mem.empty(1024, dtype=torch.int32, device=device)
+        self.pool.zero_()
+        self.flags.zero_()
+        self.pool_hdl = symm_mem.rendezvous(self.pool, self.group)
+        self.flag_hdl = symm_mem.rendezvous(self.flags, self.group)
+        self.pool_ptrs = list(self.pool_hdl.buffer_ptrs)
+        self.flag_ptrs = list(self.flag_hdl.buffer_ptrs)
+        self.done = torch.zeros(1, dtype=torch.int32, device=device)
+        self.step = torch.zeros(1, dtype=torch.int32, device=device)
+        self.cursor = 0
+        self.next_index = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(group=ctl_group if ctl_group is not None else self.group)  # zeroed everywhere before any signal
+
+    def alloc(self, numel: int) -> int:
+        off = self.cursor
+        self.cursor += (numel + 63) // 64 * 64
+        assert self.cursor <= self.pool.numel(), "PeerPlan pool too small"
+        return off
+
+    def peers_struct(self, elem_offset: int, launch_index: int) -> "_lib.QgemmPeers":
+        ps = _lib.QgemmPeers()
+        ps.world, ps.rank = self.world, self.rank
+        for r in range(self.world):
+            ps.C[r] = self.pool_ptrs[r] + 4 * elem_offset
+            ps.flag[r] = self.flag_ptrs[r]
+        ps.done, ps.step = self.done.data_ptr(), self.step.data_ptr()
+        ps.launches_per_step, ps.launch_index = self.lps, launch_index
+        return ps
+
+    def end_step(self) -> None:
+        """Wait until every launch of the step has landed from every rank, then advance the step."""
+        assert self.next_index == self.lps or self.next_index == 0
+        L = _lib.lib()
+        st = torch.cuda.current_stream(self.pool.device).cuda_stream
+        ps = self.peers_struct(0, 0)
+        _lib.raise_on_error(L.qgemm_peer_wait(ps, st), "peer_wait")
+        _lib.raise_on_error(L.qgemm_peer_step_advance(self.step.data_ptr(), st), "peer_step_advance")
+
+
+class ShardedGemvP2P:
+    """Decode GEMV (T <= 8) over row-sharded weights whose kernel writes its slice of C[F_total, T]
+    into every rank's gathered buffer.  `out` is this rank's full gathered view (valid after the
+    next launch's prologue or PeerPlan.end_step())."""
+
+    def __init__(self, weight_shard: torch.Tensor, F_total: int, K: int, wtype: int, T: int, plan: PeerPlan,
+                 align: int = DEFAULT_ALIGN, flags: int = 0):
+        self.plan, self.K, self.wtype, self.T, self.flags = plan, K, wtype, T, flags
+        self.ranges = [shard_rows(F_total, plan.world, r, align) for r in range(plan.world)]
+        self.f0, self.f1 = self.ranges[plan.rank]
+        assert weight_shard.shape[0] == self.f1 - self.f0 > 0, "every rank needs a non-empty shard in peer mode"
+        self.weight = weight_shard.contiguous()
+        self.offset = plan.alloc(F_total * T)
+        self.out = plan.pool[self.offset:self.offset + F_total * T].view(F_total, T)
+        self.launch_index = plan.next_index
+        plan.next_index += 1
+        assert plan.next_index <= plan.lps
+        # this rank's rows start at element f0 * T of the [F_total, T] buffer on every rank
+        self.ps = plan.peers_struct(self.offset + self.f0 * T, self.launch_index)
+
+    def __call__(self, activation_q: torch.Tensor) -> torch.Tensor:
+        L = _lib.lib()
+        rc = L.qgemm_gemm_peers(self.wtype, activation_q.data_ptr(), self.weight.data_ptr(), self.ps, self.T,
+                                self.f1 - self.f0, self.K, 1, self.T, self.flags,
+                                torch.cuda.current_stream(self.weight.device).cuda_stream)
+        _lib.raise_on_error(rc, "gemm_peers")
+        return self.out
