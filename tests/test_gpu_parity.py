@@ -399,3 +399,44 @@ def test_mma_skinny_fuzz_and_auto(qg, O, wt):
     assert qg.last_path() == 0x300        # AUTO: dp4a GEMV for T <= 2, mma.sync from 3, tcgen05 from 64
     run_gemm(qg, wt, aq[:2], wq, "auto")
     assert qg.last_path() == 0x200
+
+
+# ------------------------------------------------------------------------------------------
+# fused all-gather (qgemm_gemm_peers): one GPU stands in for two ranks' memory
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("wt,T", [(qo.Q4_0, 1), (qo.Q5_1, 2), (qo.Q8_0, 6)])
+def test_peer_store_protocol_single_gpu(qg, O, wt, T):
+    """Both 'peers' are buffers on this GPU and both arrival counters are the same word, so every
+    launch delivers the `world` arrivals the next launch waits for: exercises the peer stores, the
+    done/step/flag accounting and the prologue wait without a second device."""
+    from quant_gemm import _lib
+    L = _lib.lib()
+    F, K, world, steps = 300, 1024, 2, 5
+    x, w = datagen.model_like(T, F, K, seed=70 + wt)
+    aq, wq = O.quantize_q8_1(x), O.quantize_weight(wt, w)
+    da, dw = dev(aq), dev(wq)
+    bufs = [torch.full((F, T), -1.0, device="cuda") for _ in range(world)]
+    flag = torch.zeros(32, dtype=torch.int32, device="cuda")
+    done = torch.zeros(1, dtype=torch.int32, device="cuda")
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ps = _lib.QgemmPeers()
+    ps.world, ps.rank = world, 0
+    for r in range(world):
+        ps.C[r] = bufs[r].data_ptr()
+        ps.flag[r] = flag.data_ptr()
+    ps.done, ps.step, ps.launches_per_step, ps.launch_index = done.data_ptr(), step.data_ptr(), 1, 0
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(steps):
+        assert L.qgemm_gemm_peers(wt, da.data_ptr(), dw.data_ptr(), ps, T, F, K, 1, T, 0, st) == 0
+        assert L.qgemm_peer_wait(ps, st) == 0
+        assert L.qgemm_peer_step_advance(step.data_ptr(), st) == 0
+    ref = O.gemm(wt, aq, wq, layout="FT")
+    for b in bufs:
+        check_c(host(b), ref, "peer store")
+    assert (bits(host(bufs[0])) == bits(host(bufs[1]))).all()
+    assert int(flag[0]) == steps * world and int(done[0]) == 0 and int(step[0]) == steps
+    # argument checks
+    ps.launch_index = 1
+    assert L.qgemm_gemm_peers(wt, da.data_ptr(), dw.data_ptr(), ps, T, F, K, 1, T, 0, st) == -1
+    ps.launch_index = 0
+    assert L.qgemm_gemm_peers(wt, da.data_ptr(), dw.data_ptr(), ps, 64, F, K, 1, 64, 0, st) in (-1, -2)
