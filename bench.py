@@ -47,6 +47,15 @@ def algorithmic_bytes(wtype, T, F, K):
     return F * nb * BS[wtype] + T * nb * 36 + 4 * T * F
 
 
+def load_traffic():
+    """Per-launch DRAM bytes of the dominant kernel from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["dram_bytes_per_launch_bench_average"], d["source"]
+    return None, None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -64,7 +73,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             pass
@@ -239,8 +248,14 @@ def main():
     acts_host = {K: torch.randn((1, K), generator=torch.Generator().manual_seed(7 + K)).pin_memory() for K in (4096, 11008)}
     acts_dev = {K: v.to(dev) for K, v in acts_host.items()}
     acts_q = {K: quant_gemm.quantize_q8_1(v) for K, v in acts_dev.items()}
-    outs = [torch.empty((F * world, 1), device=dev) for F, K, _ in mats]  # gathered C, [F_total, T=1]
-    total_out = sum(o.numel() for o in outs)
+    # gathered C of every GEMV, [F_total, T=1] each, carved out of one buffer so the step's result
+    # goes back to the host in one copy
+    total_out = sum(F * world for F, K, _ in mats)
+    out_all = torch.empty(total_out, device=dev)
+    outs, off = [], 0
+    for F, K, _ in mats:
+        outs.append(out_all[off:off + F * world].view(F * world, 1))
+        off += F * world
     out_host = torch.empty(total_out, dtype=torch.float32).pin_memory()
     step_bytes = sum(algorithmic_bytes(WTYPE, 1, F, K) for F, K, _ in mats)
 
@@ -251,7 +266,12 @@ def main():
         # all-gather fused into the GEMV: the kernel stores its slice of C into every rank's gathered
         # buffer over NVLink (symmetric memory) and signals with device-side counters
         plan = sharded.PeerPlan(sum(F * world for F, K, _ in mats), len(mats), dev, ctl_group=ctl)
-        ops = [sharded.ShardedGemvP2P(w, F * world, K, WTYPE, 1, plan, flags=GEMV_FLAGS) for F, K, w in mats]
+        # Llama dataflow: [wq wk wv] <- previous layer's down, wo <- wv, [gate up] <- wo, down <- up
+        ops = []
+        for i, (F, K, w) in enumerate(mats):
+            j = i % 7
+            wait = i - j if j < 3 else (i if j in (3, 4, 6) else i - 1)
+            ops.append(sharded.ShardedGemvP2P(w, F * world, K, WTYPE, 1, plan, flags=GEMV_FLAGS, wait_index=wait))
         outs = [op.out for op in ops]
     else:  # baseline: in-place NCCL all-gather after every GEMV
         ops = [sharded.ShardedGemm(w, F * world, K, WTYPE, flags=GEMV_FLAGS) for F, K, w in mats]
@@ -270,10 +290,13 @@ def main():
             acts_dev[K].copy_(acts_host[K], non_blocking=True)
             acts_q[K] = quant_gemm.quantize_q8_1(acts_dev[K])
         gemv_all()
-        off = 0
-        for o in outs:
-            out_host[off:off + o.numel()].copy_(o.view(-1), non_blocking=True)
-            off += o.numel()
+        if plan is not None:   # fused all-gather: the gathered outputs live in the symmetric pool
+            off = 0
+            for op in ops:
+                out_host[off:off + op.out.numel()].copy_(op.out.view(-1), non_blocking=True)
+                off += op.out.numel()
+        else:
+            out_host.copy_(out_all, non_blocking=True)
 
     stream = torch.cuda.Stream(device=dev)
     with torch.cuda.stream(stream):
@@ -314,10 +337,10 @@ def main():
             ms = float(t.item())
         return ms
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # samples through both timed regions
     ms_dev = timed(g_dev, args.steps, args.warmup)
-    clocks = sampler.stop() if sampler else None
     ms_e2e = timed(g_e2e, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
 
     # correctness spot check of the timed path against the oracle (rank 0, a few rows)
     check = None
@@ -337,6 +360,16 @@ def main():
     per_launch_bytes = step_bytes / len(mats)
     per_launch_us = ms_dev * 1e3 / (args.steps * len(mats))
     achieved = per_launch_bytes / (per_launch_us * 1e-6) / 1e9
+    traffic, traffic_src = load_traffic()
+
+    # prefill side of the metric ("Q4_0 x Q8_1 GEMM TOPS"): BASELINE configs[2], whole call, rank 0 only
+    extra = None
+    if rank == 0 and world == 1:
+        import bench_detail
+        r = bench_detail.time_prefill(torch, quant_gemm, WTYPE, 512, 4096, 4096, reps=5)
+        extra = {"prefill_q4_0_M512_N4096_K4096": {"us": r["us"], "tops": r["tops"], "path": r["path"],
+                                                   "frac_of_nominal_int8_4500_tops": r["tops"] / 4500.0,
+                                                   "note": "whole qgemm_gemm call incl. operand prepass, L2 flushed between reps"}}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -352,10 +385,11 @@ def main():
         "gpu_launches": int(launches_per_step * args.steps),
         "gpu_launches_e2e": int(launches_per_e2e * args.steps),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "gemv_kernel<Q4_0,1>", "peak_source": peak_src,
+                     "traffic": traffic, "traffic_source": traffic_src, "kernel": "gemv_kernel<Q4_0,1>", "peak_source": peak_src,
                      "avg_launch_us": per_launch_us, "algorithmic_bytes_per_launch": per_launch_bytes,
                      "frac_of_nominal_8000": achieved / 8000.0},
         "oracle_check_max_norm_err": check,
+        "extra": extra,
     }
     if world > 1:
         dist.barrier(group=ctl)

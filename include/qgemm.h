@@ -180,8 +180,9 @@ QGEMM_API int qgemm_sumi(int wtype, const void *act_q8_1, const void *weight, in
  * Completion is tracked by device-side counters in peer-accessible memory:
  *   - all ranks issue the same sequence of launches; a "step" is `launches_per_step` launches
  *     followed by qgemm_peer_step_advance(step) (so the sequence can sit in a CUDA graph);
- *   - launch q waits, before reading its activations, until every rank's launches < q have
- *     landed locally; qgemm_peer_wait() does the same for the end of the current step.
+ *   - a launch waits, before reading its activations, until every rank's launches [0, wait_index)
+ *     of the step have landed locally (wait_index = launch_index: everything before it);
+ *     qgemm_peer_wait() does the same for the end of the current step.
  * C[r] / flag[r] are peer-mapped device pointers (e.g. torch symmetric memory, cudaIpc, or
  * cuMem fabric handles); flag words and `done`/`step` must start at zero.  T <= 8 only.
  */
@@ -193,6 +194,9 @@ typedef struct qgemm_peers {
     uint32_t *done;                   /* local scratch counter */
     const uint32_t *step;             /* local step counter */
     uint32_t launches_per_step, launch_index;
+    uint32_t wait_index;              /* launches [0, wait_index) of this step (and all earlier steps) must have
+                                         landed before this launch reads its activations; launch_index = strict
+                                         chain, smaller = the producer of this launch's input finished earlier   */
 } qgemm_peers;
 
 QGEMM_API int qgemm_gemm_peers(int wtype, const void *act_q8_1, const void *weight, const qgemm_peers *peers, int T,

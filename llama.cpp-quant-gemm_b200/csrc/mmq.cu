@@ -87,7 +87,10 @@ mmq_repack_act_kernel(const uint8_t* __restrict__ act, uint8_t* __restrict__ a8,
                       int Tpad, int nb, int nbp, float coef) {
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (int64_t)Tpad * nbp) return;
-    const int t = (int)(gid % Tpad), b = (int)(gid / Tpad);
+    // 4 consecutive lanes = the 4 blocks of one 128-byte operand row: contiguous reads (4 x 36 B) and
+    // a contiguous 128-byte write per row, 8 rows per warp
+    const int j4 = (int)(gid & 3);
+    const int t = (int)((gid >> 2) % Tpad), b = (int)((gid >> 2) / Tpad) * 4 + j4;
     uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
     float2 sc = make_float2(0.f, 0.f);
     if (t < T && b < nb) {
@@ -116,7 +119,8 @@ mmq_unpack_weight_kernel(const uint8_t* __restrict__ wgt, uint8_t* __restrict__ 
     using Fm = Fmt<WT>;
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (int64_t)Fpad * nbp) return;
-    const int f = (int)(gid % Fpad), b = (int)(gid / Fpad);
+    const int j4 = (int)(gid & 3);  // lanes 4i..4i+3 = the 4 blocks of one operand row (see the activation prepass)
+    const int f = (int)((gid >> 2) % Fpad), b = (int)((gid >> 2) / Fpad) * 4 + j4;
     uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     WScale sc{0.f, 0.f};
     if (f < F && b < nb) {

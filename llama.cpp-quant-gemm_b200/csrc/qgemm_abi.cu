@@ -30,7 +30,7 @@ cudaError_t launch_mmq(int wtype, const void* act, const void* wgt, float* C, in
                        cudaStream_t);
 
 constexpr int kMmaMinTokens = 3;   // dp4a GEMV below, mma.sync skinny path from here
-constexpr int kMmqMinTokens = 64;  // AUTO switches from the weight-streaming path to tensor cores here
+constexpr int kMmqMinTokens = 96;  // AUTO switches to the tcgen05 path here (below it the skinny passes are faster)
 
 static std::atomic<int64_t> g_launches{0};
 void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
@@ -286,7 +286,8 @@ int qgemm_sumi(int wtype, const void* act_q8_1, const void* weight, int32_t* sum
 int qgemm_gemm_peers(int wtype, const void* act_q8_1, const void* weight, const qgemm_peers* peers, int T, int F, int K,
                      int64_t ldc_t, int64_t ldc_f, uint32_t flags, void* stream) {
     if (!peers || peers->world < 1 || peers->world > kMaxPeers || peers->rank < 0 || peers->rank >= peers->world ||
-        !peers->done || !peers->step || peers->launches_per_step == 0 || peers->launch_index >= peers->launches_per_step)
+        !peers->done || !peers->step || peers->launches_per_step == 0 || peers->launch_index >= peers->launches_per_step ||
+        peers->wait_index > peers->launch_index)
         return QGEMM_E_BADARG;
     for (int r = 0; r < peers->world; r++)
         if (!peers->C[r] || !peers->flag[r]) return QGEMM_E_BADARG;
@@ -298,7 +299,7 @@ int qgemm_gemm_peers(int wtype, const void* act_q8_1, const void* weight, const 
     PeerOut po{};
     po.world = peers->world; po.rank = peers->rank;
     for (int r = 0; r < peers->world; r++) { po.C[r] = peers->C[r]; po.flag[r] = peers->flag[r]; }
-    po.done = peers->done; po.step = peers->step; po.lps = peers->launches_per_step; po.li = peers->launch_index;
+    po.done = peers->done; po.step = peers->step; po.lps = peers->launches_per_step; po.li = peers->wait_index;
     po.dbg = getenv("QGEMM_PEER_DBG") ? atoi(getenv("QGEMM_PEER_DBG")) : 0;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;

@@ -184,7 +184,7 @@ struct PeerOut {
     uint32_t* flag[kMaxPeers];    // rank r's arrival counter
     uint32_t* done;               // local CTA-completion counter (returns to 0 after each launch)
     const uint32_t* step;         // local step counter (qgemm_peer_step_advance)
-    uint32_t lps, li;             // launches per step, index of this launch inside the step
+    uint32_t lps, li;             // launches per step, launches of this step that must have landed first
     int dbg;                      // tuning aid: 1 skip wait, 2 local store only, 4 skip per-thread fence
 };
 

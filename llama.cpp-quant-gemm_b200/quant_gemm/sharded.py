@@ -127,7 +127,7 @@ class PeerPlan:
         assert self.cursor <= self.pool.numel(), "PeerPlan pool too small"
         return off
 
-    def peers_struct(self, elem_offset: int, launch_index: int) -> "_lib.QgemmPeers":
+    def peers_struct(self, elem_offset: int, launch_index: int, wait_index: Optional[int] = None) -> "_lib.QgemmPeers":
         ps = _lib.QgemmPeers()
         ps.world, ps.rank = self.world, self.rank
         for r in range(self.world):
@@ -135,6 +135,7 @@ class PeerPlan:
             ps.flag[r] = self.flag_ptrs[r]
         ps.done, ps.step = self.done.data_ptr(), self.step.data_ptr()
         ps.launches_per_step, ps.launch_index = self.lps, launch_index
+        ps.wait_index = launch_index if wait_index is None else wait_index
         return ps
 
     def end_step(self) -> None:
@@ -153,7 +154,10 @@ class ShardedGemvP2P:
     next launch's prologue or PeerPlan.end_step())."""
 
     def __init__(self, weight_shard: torch.Tensor, F_total: int, K: int, wtype: int, T: int, plan: PeerPlan,
-                 align: int = DEFAULT_ALIGN, flags: int = 0):
+                 align: int = DEFAULT_ALIGN, flags: int = 0, wait_index: Optional[int] = None):
+        """wait_index: how many launches of the step must have landed everywhere before this one reads
+        its activations (default: all earlier ones).  A model passes the index after the launch that
+        produced this GEMV's input, so independent projections (q/k/v, gate/up) do not re-synchronise."""
         self.plan, self.K, self.wtype, self.T, self.flags = plan, K, wtype, T, flags
         self.ranges = [shard_rows(F_total, plan.world, r, align) for r in range(plan.world)]
         self.f0, self.f1 = self.ranges[plan.rank]
@@ -165,7 +169,7 @@ class ShardedGemvP2P:
         plan.next_index += 1
         assert plan.next_index <= plan.lps
         # this rank's rows start at element f0 * T of the [F_total, T] buffer on every rank
-        self.ps = plan.peers_struct(self.offset + self.f0 * T, self.launch_index)
+        self.ps = plan.peers_struct(self.offset + self.f0 * T, self.launch_index, wait_index)
 
     def __call__(self, activation_q: torch.Tensor) -> torch.Tensor:
         L = _lib.lib()

@@ -332,7 +332,7 @@ def test_mmq_fuzz_ms_exact_and_layouts(qg, O, wt):
     for fl in (0, qo.GEMM_MS_EXACT):
         c = run_gemm(qg, wt, aq, wq, "tcgen05", flags=fl)
         check_c(c, O.gemm(wt, aq, wq, layout="FT", flags=fl), "mmq fuzz")
-    # AUTO takes the tensor-core path from 64 tokens up, and the include/ [T,F] layout works too
+    # AUTO takes the tensor-core path from 96 tokens up, and the include/ [T,F] layout works too
     c = run_gemm(qg, wt, aq, wq, "auto")
     assert qg.last_path() == 0x400
     da, dw = dev(aq), dev(wq)
@@ -425,6 +425,7 @@ def test_peer_store_protocol_single_gpu(qg, O, wt, T):
         ps.C[r] = bufs[r].data_ptr()
         ps.flag[r] = flag.data_ptr()
     ps.done, ps.step, ps.launches_per_step, ps.launch_index = done.data_ptr(), step.data_ptr(), 1, 0
+    ps.wait_index = 0
     st = torch.cuda.current_stream().cuda_stream
     for _ in range(steps):
         assert L.qgemm_gemm_peers(wt, da.data_ptr(), dw.data_ptr(), ps, T, F, K, 1, T, 0, st) == 0
@@ -436,7 +437,7 @@ def test_peer_store_protocol_single_gpu(qg, O, wt, T):
     assert (bits(host(bufs[0])) == bits(host(bufs[1]))).all()
     assert int(flag[0]) == steps * world and int(done[0]) == 0 and int(step[0]) == steps
     # argument checks
-    ps.launch_index = 1
+    ps.launch_index = 1   # outside launches_per_step
     assert L.qgemm_gemm_peers(wt, da.data_ptr(), dw.data_ptr(), ps, T, F, K, 1, T, 0, st) == -1
     ps.launch_index = 0
     assert L.qgemm_gemm_peers(wt, da.data_ptr(), dw.data_ptr(), ps, 64, F, K, 1, 64, 0, st) in (-1, -2)
