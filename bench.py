@@ -39,6 +39,7 @@ LLAMA7B = [("wq", 4096, 4096), ("wk", 4096, 4096), ("wv", 4096, 4096), ("wo", 40
            ("gate", 11008, 4096), ("up", 11008, 4096), ("down", 4096, 11008)]
 WTYPE = 2  # Q4_0
 GEMV_FLAGS = 0x10  # QGEMM_WEIGHTS_STATIC: model weights are never written while decoding
+READY_FLAGS = 0x30  # + QGEMM_INPUTS_READY: wk/wv after wq and `up` after `gate` share an input that is already there
 BS = {2: 18, 3: 20, 6: 22, 7: 24, 8: 34}
 
 
@@ -205,6 +206,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layers", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--prefetch", type=int, default=1, help="1: hint each GEMV with the next one's weights (L2 prefetch)")
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
                     help="N > 1: all-gather fused into the kernel (peer stores over NVLink) or NCCL per GEMV")
     ap.add_argument("--detail", default=None, help="write a per-shape sweep (all formats, M=1..8, prefill) to this JSON file")
@@ -271,19 +273,26 @@ def main():
         for i, (F, K, w) in enumerate(mats):
             j = i % 7
             wait = i - j if j < 3 else (i if j in (3, 4, 6) else i - 1)
-            ops.append(sharded.ShardedGemvP2P(w, F * world, K, WTYPE, 1, plan, flags=GEMV_FLAGS, wait_index=wait))
+            ops.append(sharded.ShardedGemvP2P(w, F * world, K, WTYPE, 1, plan, wait_index=wait,
+                                              flags=READY_FLAGS if j in (1, 2, 5) else GEMV_FLAGS))
         outs = [op.out for op in ops]
     else:  # baseline: in-place NCCL all-gather after every GEMV
-        ops = [sharded.ShardedGemm(w, F * world, K, WTYPE, flags=GEMV_FLAGS) for F, K, w in mats]
+        # Llama dataflow: wk, wv read the same (already complete) input as wq, `up` the same as `gate`
+        ops = [sharded.ShardedGemm(w, F * world, K, WTYPE, flags=READY_FLAGS if (i % 7) in (1, 2, 5) else GEMV_FLAGS)
+               for i, (F, K, w) in enumerate(mats)]
 
     def gemv_all():
-        if plan is not None:
-            for op, (F, K, w) in zip(ops, mats):
+        # a decode runtime knows its layer order: each launch pulls the next GEMV's weights into L2
+        n = len(mats)
+        for i, (op, (F, K, w)) in enumerate(zip(ops, mats)):
+            if args.prefetch:
+                quant_gemm.hint_next_weights(mats[(i + 1) % n][2])
+            if plan is not None:
                 op(acts_q[K])
+            else:
+                op(acts_q[K], out=outs[i])
+        if plan is not None:
             plan.end_step()
-        else:
-            for op, (F, K, w), o in zip(ops, mats, outs):
-                op(acts_q[K], out=o)
 
     def e2e_step():
         for K in acts_host:

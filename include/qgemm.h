@@ -72,6 +72,12 @@ extern "C" {
                                    weight buffer: the decode path then launches with programmatic
                                    dependent launch and prefetches weights under the previous
                                    kernel's tail (activations / C are still ordered normally)       */
+#define QGEMM_INPUTS_READY 0x20u  /* with QGEMM_WEIGHTS_STATIC: the caller also promises that this call's
+                                   activations and output are not written or read by earlier work still
+                                   in flight on `stream` (e.g. the k/v projections after q, `up` after
+                                   `gate`: same input, different outputs).  The decode kernel then computes
+                                   without waiting for its predecessor and only waits before it exits, so
+                                   stream-order completion is preserved for everything launched after it */
 #define QGEMM_PATH_MASK 0xF00u
 #define QGEMM_PATH_AUTO 0x000u
 #define QGEMM_PATH_GENERIC 0x100u /* same kernel as QGEMM_SEQUENTIAL                         */
@@ -152,6 +158,16 @@ QGEMM_API int qgemm_gemm(int wtype, const void *act_q8_1, const void *weight, fl
  * keep it alive and un-shared between concurrently running streams.  (NULL, 0) unregisters.
  */
 QGEMM_API int qgemm_set_default_workspace(void *workspace, size_t workspace_bytes);
+
+/*
+ * One-shot hint for the calling thread's NEXT decode-path qgemm_gemm*() call: once that launch
+ * has issued its own weight stream it also pulls [next_weights, next_weights + bytes) into L2
+ * (cp.async.bulk.prefetch.L2), i.e. the weights of the GEMV that will follow it.  Back-to-back
+ * decode GEMVs are separated by a dependency bubble in which HBM would otherwise idle; a runtime
+ * that knows its layer order (llama.cpp does) hides it this way.  Pure performance hint: no effect
+ * on results, ignored by the other paths.  (NULL, 0) clears it.
+ */
+QGEMM_API int qgemm_hint_next_weights(const void *next_weights, size_t bytes);
 
 /*
  * Same, with fp32 activations act_f32[T][K]: quantize_q8_1 (flags' QGEMM_Q81_*

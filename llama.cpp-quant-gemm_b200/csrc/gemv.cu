@@ -154,9 +154,11 @@ struct GemvParams {
     int WPR;              // warps sharing one row: 1, 2, 4 or 8
     int stages;
     int stage_bytes;      // 128-byte multiple
-    int pdl;              // programmatic dependent launch in use
+    int pdl;              // programmatic dependent launch: 1 wait before the activations, 2 wait before exit
     int nocompute;        // tuning aid: stream the tiles, skip the math (memory-system ceiling)
     PeerOut peer;         // fused all-gather (world <= 1: plain store to C)
+    const uint8_t* pf_ptr; // next launch's weights to pull into L2 (or null)
+    unsigned long long pf_bytes;
 };
 
 // PPL > 0: activations in registers, PPL pairs per lane.  PPL == 0: activations in smem.
@@ -210,12 +212,20 @@ __global__ void __launch_bounds__(kGemvThreads, kGemvCtasPerSm) gemv_kernel(cons
                 ptx::bulk_g2s(stage0 + (size_t)s * p.stage_bytes, p.wgt + (size_t)r0 * rowbytes, bytes, &full[s]);
                 if (++s == p.stages) { s = 0; ph ^= 1; }
             }
+            // own stream issued: now pull this CTA's share of the NEXT launch's weights into L2
+            if (p.pf_ptr) {
+                const unsigned long long chunk = ((p.pf_bytes / gridDim.x) + 15ull) & ~15ull;
+                unsigned long long off = chunk * blockIdx.x;
+                const unsigned long long end = min(off + chunk, p.pf_bytes & ~15ull);
+                for (; off < end; off += 16384ull)
+                    ptx::bulk_prefetch_l2(p.pf_ptr + off, (uint32_t)min(16384ull, end - off));
+            }
         }
         return;
     }
 
     // ================= consumer warps =================
-    if (p.pdl) ptx::griddep_wait();  // activations / C may belong to the previous launch
+    if (p.pdl == 1) ptx::griddep_wait();  // activations / C may belong to the previous launch
     if (p.peer.world > 1) {          // ... or to an earlier launch of a peer GPU
         if (tid == 0) peer_wait_prior(p.peer);
         ptx::bar_sync(1, kGemvWarps * 32);
@@ -366,10 +376,11 @@ __global__ void __launch_bounds__(kGemvThreads, kGemvCtasPerSm) gemv_kernel(cons
         if (++s == p.stages) { s = 0; ph ^= 1; }
     }
     if (p.peer.world > 1) {
-        if (!(p.peer.dbg & 4)) __threadfence();  // this thread's peer stores are ordered before the CTA barrier                  // this thread's peer stores are out
+        if (!(p.peer.dbg & 4)) __threadfence();  // this thread's peer stores are ordered before the CTA barrier
         ptx::bar_sync(1, kGemvWarps * 32);
         if (tid == 0) peer_signal_done(p.peer, gridDim.x);
     }
+    if (p.pdl == 2) ptx::griddep_wait();  // QGEMM_INPUTS_READY: ran ahead, but do not complete before the predecessor
 }
 
 // ---------------------------------------------------------------------------
@@ -476,7 +487,8 @@ static cudaError_t launch_gemv_wt(const GemvPlan& pl, const GemvParams& p, int g
 }
 
 cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
-                        int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t st, const PeerOut* peer) {
+                        int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t st, const PeerOut* peer,
+                        const void* pf_ptr, size_t pf_bytes) {
     const int nb = K / 32;
     const bool ms = flags & QGEMM_MS_EXACT;
     GemvPlan pl;
@@ -492,8 +504,10 @@ cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, i
         p.C = C + (int64_t)t0 * ldc_t;
         p.F = F; p.nb = nb; p.ldc_t = ldc_t; p.ldc_f = ldc_f;
         p.RT = cur.rt; p.WPR = cur.wpr; p.stages = cur.stages; p.stage_bytes = cur.stage_bytes;
-        p.pdl = pdl ? 1 : 0;
+        p.pdl = pdl ? ((flags & QGEMM_INPUTS_READY) ? 2 : 1) : 0;
         p.nocompute = getenv("QGEMM_GEMV_NOCOMPUTE") ? 1 : 0;
+        p.pf_ptr = (t0 + pl.tt >= T && reinterpret_cast<uintptr_t>(pf_ptr) % 16 == 0) ? (const uint8_t*)pf_ptr : nullptr;
+        p.pf_bytes = pf_bytes;
         p.peer = PeerOut{};
         if (peer) {
             if (T > pl.tt) return cudaErrorInvalidValue;  // peer mode: one pass per launch (flag accounting)

@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) gemv_mma_kernel(const GemvMmaP
     }
 
     // ===== consumers
-    if (p.pdl) ptx::griddep_wait();
+    if (p.pdl == 1) ptx::griddep_wait();
     if (p.peer.world > 1) {
         if (tid == 0) peer_wait_prior(p.peer);
         ptx::bar_sync(1, kMmaWarps * 32);
@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) gemv_mma_kernel(const GemvMmaP
         ptx::bar_sync(1, kMmaWarps * 32);
         if (tid == 0) peer_signal_done(p.peer, gridDim.x);
     }
+    if (p.pdl == 2) ptx::griddep_wait();
 }
 
 // ---------------------------------------------------------------------------
@@ -276,7 +277,7 @@ cudaError_t launch_gemv_mma(int wtype, const void* act, const void* wgt, float* 
         p.wgt = (const uint8_t*)wgt;
         p.C = C + (int64_t)t0 * ldc_t;
         p.T = min(8, T - t0); p.F = F; p.nb = nb; p.ldc_t = ldc_t; p.ldc_f = ldc_f;
-        p.pitch = pitch; p.stages = stages; p.pdl = (flags & QGEMM_WEIGHTS_STATIC) ? 1 : 0;
+        p.pitch = pitch; p.stages = stages; p.pdl = (flags & QGEMM_WEIGHTS_STATIC) ? ((flags & QGEMM_INPUTS_READY) ? 2 : 1) : 0;
         p.peer = peer ? *peer : PeerOut{};
         const bool ms = flags & QGEMM_MS_EXACT;
         cudaError_t e;

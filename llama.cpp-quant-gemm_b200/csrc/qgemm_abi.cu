@@ -19,7 +19,8 @@ cudaError_t launch_sumi_generic(int wtype, const void* act, const void* wgt, int
                                 cudaStream_t);
 bool gemv_supported(int wtype, const void* act, const void* wgt, int F, int K);
 cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
-                        int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t, const PeerOut* peer = nullptr);
+                        int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t, const PeerOut* peer = nullptr,
+                        const void* pf_ptr = nullptr, size_t pf_bytes = 0);
 bool gemv_mma_supported(int wtype, const void* act, const void* wgt, int T, int F, int K);
 cudaError_t launch_gemv_mma(int wtype, const void* act, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
                             int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t, const PeerOut* peer = nullptr);
@@ -36,6 +37,8 @@ static std::atomic<int64_t> g_launches{0};
 void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 static thread_local uint32_t t_last_path = 0;
+static thread_local const void* t_pf_ptr = nullptr;  // qgemm_hint_next_weights (one-shot)
+static thread_local size_t t_pf_bytes = 0;
 static thread_local char t_detail[256] = "";
 
 static int cuda_fail(cudaError_t e, const char* where) {
@@ -134,7 +137,9 @@ static int run_gemm(int wtype, const void* act, const void* wgt, float* C, int T
     switch (path) {
     case QGEMM_PATH_GEMV:
         if (!gemv_supported(wtype, act, wgt, F, K)) return QGEMM_E_ALIGN;
-        e = launch_gemv(wtype, act, wgt, C, T, F, K, ldc_t, ldc_f, flags, dev.sms, st);
+        e = launch_gemv(wtype, act, wgt, C, T, F, K, ldc_t, ldc_f, flags, dev.sms, st, nullptr, t_pf_ptr, t_pf_bytes);
+        t_pf_ptr = nullptr;
+        t_pf_bytes = 0;
         break;
     case QGEMM_PATH_MMA:
         if (!gemv_mma_supported(wtype, act, wgt, T, F, K)) return QGEMM_E_ALIGN;
@@ -236,6 +241,12 @@ int qgemm_set_default_workspace(void* workspace, size_t workspace_bytes) {
     return QGEMM_OK;
 }
 
+int qgemm_hint_next_weights(const void* next_weights, size_t bytes) {
+    t_pf_ptr = bytes ? next_weights : nullptr;
+    t_pf_bytes = next_weights ? bytes : 0;
+    return QGEMM_OK;
+}
+
 int qgemm_gemm(int wtype, const void* act_q8_1, const void* weight, float* C, int T, int F, int K, int64_t ldc_t,
                int64_t ldc_f, uint32_t flags, void* workspace, size_t workspace_bytes, void* stream) {
     if (int rc = check_gemm_args(wtype, act_q8_1, weight, C, T, F, K)) return rc;
@@ -307,7 +318,9 @@ int qgemm_gemm_peers(int wtype, const void* act_q8_1, const void* weight, const 
         e = launch_gemv_mma(wtype, act_q8_1, weight, C, T, F, K, ldc_t, ldc_f, flags, dev.sms, st, &po);
         t_last_path = QGEMM_PATH_MMA;
     } else if (T <= 8 && gemv_supported(wtype, act_q8_1, weight, F, K)) {
-        e = launch_gemv(wtype, act_q8_1, weight, C, T, F, K, ldc_t, ldc_f, flags, dev.sms, st, &po);
+        e = launch_gemv(wtype, act_q8_1, weight, C, T, F, K, ldc_t, ldc_f, flags, dev.sms, st, &po, t_pf_ptr, t_pf_bytes);
+        t_pf_ptr = nullptr;
+        t_pf_bytes = 0;
         t_last_path = QGEMM_PATH_GEMV;
     } else {
         return QGEMM_E_ALIGN;  // peer stores are fused into the decode kernels only (T <= 8, bulk-copyable rows)

@@ -23,7 +23,7 @@ import torch
 
 from . import _lib
 from ._lib import (  # noqa: F401  (re-exported constants)
-    GEMM_MS_EXACT, GEMM_SEQUENTIAL, GEMM_WEIGHTS_STATIC, PATH_AUTO, PATH_GEMV, PATH_GENERIC, PATH_MMA, PATH_TCGEN05,
+    GEMM_INPUTS_READY, GEMM_MS_EXACT, GEMM_SEQUENTIAL, GEMM_WEIGHTS_STATIC, PATH_AUTO, PATH_GEMV, PATH_GENERIC, PATH_MMA, PATH_TCGEN05,
     Q81_CLAMP127, Q81_ROUND_AWAY, Q81_ROUND_EVEN, Q81_S_FROM_QSUM,
     TYPE_Q4_0, TYPE_Q4_1, TYPE_Q5_0, TYPE_Q5_1, TYPE_Q8_0, TYPE_Q8_1,
 )
@@ -130,6 +130,15 @@ def dequantize(x_q: torch.Tensor, K: int, qtype: int) -> torch.Tensor:
 def dequantize_q4_0(x_q: torch.Tensor, K: int) -> torch.Tensor:
     """Q4_0 bytes [..., K//32, 18] -> FP32 [..., K] (python/quant_gemm/__init__.py:78-89)."""
     return dequantize(x_q, K, TYPE_Q4_0)
+
+
+def hint_next_weights(next_weight_q: torch.Tensor | None) -> None:
+    """Decode hint: the next gemm() call also prefetches `next_weight_q` (the weights of the GEMV after
+    it) into L2 while it runs.  No effect on results."""
+    if next_weight_q is None:
+        _lib.lib().qgemm_hint_next_weights(None, 0)
+    else:
+        _lib.lib().qgemm_hint_next_weights(next_weight_q.data_ptr(), next_weight_q.numel() * next_weight_q.element_size())
 
 
 def gemm(weight_q: torch.Tensor, activation_q: torch.Tensor, M: int, N: int, K: int, wtype: int,
@@ -252,5 +261,5 @@ __all__ = [
     # supersets
     "quantize_q4_1", "quantize_q5_0", "quantize_q5_1", "quantize_q8_0", "dequantize",
     "gemm", "gemm_q4_1_q8_1", "gemm_q5_0_q8_1", "gemm_q5_1_q8_1", "gemm_q8_0_q8_1", "gemm_w4a8",
-    "block_sumi", "launch_count", "reset_launch_count", "last_path",
+    "block_sumi", "launch_count", "reset_launch_count", "last_path", "hint_next_weights",
 ]
