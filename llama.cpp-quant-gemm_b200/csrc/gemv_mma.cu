@@ -21,7 +21,7 @@ constexpr int kMmaWarps = 8;
 constexpr int kMmaThreads = (kMmaWarps + 1) * 32;
 constexpr int kMmaRows = 16;          // weight rows per tile = MMA M
 constexpr int kMmaStagesMax = 4;
-constexpr int kMmaSmemBudget = 110 * 1024;   // two CTAs per SM when two stages fit in this
+constexpr int kMmaSmemBudget = 112 * 1024;   // two CTAs per SM when two stages fit in this
 constexpr int kMmaSmemMax = 200 * 1024;      // otherwise one CTA per SM (long or 8-bit rows)
 
 struct GemvMmaParams {
@@ -81,10 +81,10 @@ __global__ void __launch_bounds__(kMmaThreads, 2) gemv_mma_kernel(const GemvMmaP
 
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);         // [kMmaStagesMax]
     uint64_t* empty = full + kMmaStagesMax;                     // [kMmaStagesMax]
-    float* red = reinterpret_cast<float*>(smem + 128);          // [2][kMmaWarps][16 rows][8 tokens]
-    float2* a_sc = reinterpret_cast<float2*>(smem + 128 + 2 * kMmaWarps * 128 * 4);  // [nb][8] (d_a, c_a)
+    float* red = reinterpret_cast<float*>(smem + 128);          // [kMmaWarps][16 rows][8 tokens]
+    float2* a_sc = reinterpret_cast<float2*>(smem + 128 + kMmaWarps * 128 * 4);  // [nb][8] (d_a, c_a)
     const uint32_t stage_bytes = (uint32_t)kMmaRows * p.pitch;
-    uint8_t* stage0 = smem + ((128u + 2u * kMmaWarps * 128u * 4u + (uint32_t)nb * 64u + 127u) & ~127u);
+    uint8_t* stage0 = smem + ((128u + kMmaWarps * 128u * 4u + (uint32_t)nb * 64u + 127u) & ~127u);
 
     const int ntiles_total = (p.F + kMmaRows - 1) / kMmaRows;
     const int t_begin = (int)(((int64_t)ntiles_total * blockIdx.x) / gridDim.x);
@@ -150,9 +150,9 @@ __global__ void __launch_bounds__(kMmaThreads, 2) gemv_mma_kernel(const GemvMmaP
     }
     ptx::bar_sync(1, kMmaWarps * 32);
 
-    int s = 0, par = 0;
+    int s = 0;
     uint32_t ph = 0;
-    for (int t = t_begin; t < t_end; t++, par ^= 1) {
+    for (int t = t_begin; t < t_end; t++) {
         ptx::mbar_wait(&full[s], ph);
         const uint8_t* r0 = stage0 + (size_t)s * stage_bytes + (size_t)g * p.pitch;
         const uint8_t* r1 = r0 + (size_t)8 * p.pitch;
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) gemv_mma_kernel(const GemvMmaP
         if (++s == p.stages) { s = 0; ph ^= 1; }
 
         // combine the 8 K-slices in warp order
-        float* rb = red + par * (kMmaWarps * 128);
+        float* rb = red;
         rb[warp * 128 + g * 8 + 2 * tig] = acc[0];
         rb[warp * 128 + g * 8 + 2 * tig + 1] = acc[1];
         rb[warp * 128 + (g + 8) * 8 + 2 * tig] = acc[2];
@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(kMmaThreads, 2) gemv_mma_kernel(const GemvMmaP
             const int f = t * kMmaRows + r;
             if (f < p.F && tok < p.T) peer_store(p.peer, p.C, (int64_t)tok * p.ldc_t + (int64_t)f * p.ldc_f, v);
         }
+        ptx::bar_sync(1, kMmaWarps * 32);  // the partials buffer is reused by the next tile
     }
     if (p.peer.world > 1) {
         if (!(p.peer.dbg & 4)) __threadfence();  // this thread's peer stores are ordered before the CTA barrier
@@ -213,7 +214,7 @@ bool gemv_mma_supported(int wtype, const void* act, const void* wgt, int T, int 
     if (rowbytes % 16 != 0) return false;
     if (reinterpret_cast<uintptr_t>(wgt) % 16 != 0 || reinterpret_cast<uintptr_t>(act) % 4 != 0) return false;
     const size_t pitch = rowbytes + 16 + ((128 - (rowbytes % 128)) % 128);
-    const size_t fixed = 128 + 2 * kMmaWarps * 128 * 4 + (size_t)nb * 64 + 128;
+    const size_t fixed = 128 + kMmaWarps * 128 * 4 + (size_t)nb * 64 + 128;
     return fixed + 2 * kMmaRows * pitch <= (size_t)kMmaSmemMax;
 }
 
@@ -263,7 +264,7 @@ cudaError_t launch_gemv_mma(int wtype, const void* act, const void* wgt, float* 
     const int nb = K / 32;
     const size_t rowbytes = (size_t)nb * block_bytes(wtype);
     const int pitch = (int)(rowbytes + 16 + ((128 - (rowbytes % 128)) % 128));
-    const size_t fixed = 128 + 2 * kMmaWarps * 128 * 4 + (size_t)nb * 64 + 128;
+    const size_t fixed = 128 + kMmaWarps * 128 * 4 + (size_t)nb * 64 + 128;
     const size_t budget = (fixed + 2 * (size_t)kMmaRows * pitch <= (size_t)kMmaSmemBudget) ? kMmaSmemBudget : kMmaSmemMax;
     int stages = (int)((budget - fixed) / ((size_t)kMmaRows * pitch));
     stages = max(2, min(kMmaStagesMax, stages));

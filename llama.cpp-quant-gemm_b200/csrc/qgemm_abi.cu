@@ -30,7 +30,7 @@ cudaError_t launch_mmq(int wtype, const void* act, const void* wgt, float* C, in
                        int64_t ldc_t, int64_t ldc_f, uint32_t flags, void* ws, size_t ws_bytes, int num_sms,
                        cudaStream_t);
 
-constexpr int kMmaMinTokens = 3;   // dp4a GEMV below, mma.sync skinny path from here
+constexpr int kMmaMinTokens = 2;   // dp4a GEMV for a single token, mma.sync skinny path from here (measured crossover)
 constexpr int kMmqMinTokens = 96;  // AUTO switches to the tcgen05 path here (below it the skinny passes are faster)
 
 static std::atomic<int64_t> g_launches{0};

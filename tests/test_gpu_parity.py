@@ -396,8 +396,8 @@ def test_mma_skinny_fuzz_and_auto(qg, O, wt):
     for fl in (0, qo.GEMM_MS_EXACT):
         check_c(run_gemm(qg, wt, aq, wq, "mma", flags=fl), O.gemm(wt, aq, wq, layout="FT", flags=fl), "mma fuzz")
     run_gemm(qg, wt, aq, wq, "auto")
-    assert qg.last_path() == 0x300        # AUTO: dp4a GEMV for T <= 2, mma.sync from 3, tcgen05 from 64
-    run_gemm(qg, wt, aq[:2], wq, "auto")
+    assert qg.last_path() == 0x300        # AUTO: dp4a GEMV for T = 1, mma.sync from 2, tcgen05 from 96
+    run_gemm(qg, wt, aq[:1], wq, "auto")
     assert qg.last_path() == 0x200
 
 
