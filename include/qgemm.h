@@ -160,6 +160,17 @@ QGEMM_API int qgemm_gemm(int wtype, const void *act_q8_1, const void *weight, fl
 QGEMM_API int qgemm_set_default_workspace(void *workspace, size_t workspace_bytes);
 
 /*
+ * Grouped decode GEMM: `nmat` weight matrices of the same type and K applied to the SAME
+ * activations in one launch (fused q/k/v or gate/up projections -- what a concatenated weight
+ * matrix would give, without concatenating).  Cs[m][t*ldc_t + f*ldc_f] receives matrix m's rows.
+ * One weight stream across the group: no launch bubble between the members.  Results are
+ * identical to nmat separate qgemm_gemm() calls on the decode path.  nmat <= 8; T <= 8 takes the
+ * fused kernel, anything else falls back to one launch per matrix.
+ */
+QGEMM_API int qgemm_gemm_group(int wtype, const void *act_q8_1, int nmat, const void *const *weights, float *const *Cs,
+                               const int *Fs, int T, int K, int64_t ldc_t, int64_t ldc_f, uint32_t flags, void *stream);
+
+/*
  * One-shot hint for the calling thread's NEXT decode-path qgemm_gemm*() call: once that launch
  * has issued its own weight stream it also pulls [next_weights, next_weights + bytes) into L2
  * (cp.async.bulk.prefetch.L2), i.e. the weights of the GEMV that will follow it.  Back-to-back

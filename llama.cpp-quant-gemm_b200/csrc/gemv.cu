@@ -37,6 +37,7 @@ constexpr int kGemvMaxStages = 8;
 constexpr int kGemvActOff = (128 + 2 * kGemvWarps * 8 * 4 + 127) / 128 * 128;  // barriers + slots
 constexpr int kGemvSmemBudget = 110 * 1024;          // two CTAs per SM, always
 constexpr int kGemvCtasPerSm = 2;
+constexpr int kGemvMaxGroup = 8;                      // matrices per grouped launch
 constexpr int kGemvTileTarget = 24 * 1024;           // bytes per tile we aim for
 
 // ---- a pair of adjacent weight blocks as 32-bit words --------------------------
@@ -159,7 +160,27 @@ struct GemvParams {
     PeerOut peer;         // fused all-gather (world <= 1: plain store to C)
     const uint8_t* pf_ptr; // next launch's weights to pull into L2 (or null)
     unsigned long long pf_bytes;
+    // grouped launch: nmat matrices that share the activations (fused q/k/v, gate/up); rows are
+    // numbered across the group, matrix m owns [fstart[m], fstart[m+1]); nmat <= 1: wgt / C above
+    int nmat;
+    const uint8_t* wgt_m[kGemvMaxGroup];
+    float* C_m[kGemvMaxGroup];
+    int fstart[kGemvMaxGroup + 1];
 };
+
+// tile that starts at group row r0: rows until the tile size, the CTA's span or the matrix ends
+struct TileRef { int m, local, rows; };
+__device__ __forceinline__ TileRef tile_at(const GemvParams& p, int r0, int r_end) {
+    TileRef t{0, r0, min(p.RT, r_end - r0)};
+    if (p.nmat > 1) {
+        int m = 0;
+        while (m + 1 < p.nmat && r0 >= p.fstart[m + 1]) m++;
+        t.m = m;
+        t.local = r0 - p.fstart[m];
+        t.rows = min(t.rows, p.fstart[m + 1] - r0);
+    }
+    return t;
+}
 
 // PPL > 0: activations in registers, PPL pairs per lane.  PPL == 0: activations in smem.
 // kFull: every lane owns exactly PPL valid pairs (np == PPL * WPR * 32): no bounds checks, so the
@@ -185,8 +206,6 @@ __global__ void __launch_bounds__(kGemvThreads, kGemvCtasPerSm) gemv_kernel(cons
     // ---- this CTA's contiguous span of weight rows
     const int r_begin = (int)(((int64_t)p.F * blockIdx.x) / gridDim.x);
     const int r_end = (int)(((int64_t)p.F * (blockIdx.x + 1)) / gridDim.x);
-    const int RT = p.RT;
-    const int ntiles = (r_end - r_begin + RT - 1) / RT;
     const size_t rowbytes = (size_t)nb * Fm::bytes;
 
     if (tid == 0) {
@@ -204,13 +223,15 @@ __global__ void __launch_bounds__(kGemvThreads, kGemvCtasPerSm) gemv_kernel(cons
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            for (int t = 0; t < ntiles; t++) {
-                const int r0 = r_begin + t * RT;
-                const uint32_t bytes = (uint32_t)(min(RT, r_end - r0) * rowbytes);
+            for (int r0 = r_begin; r0 < r_end;) {
+                const TileRef tr = tile_at(p, r0, r_end);
+                const uint8_t* src = (p.nmat > 1 ? p.wgt_m[tr.m] : p.wgt) + (size_t)tr.local * rowbytes;
+                const uint32_t bytes = (uint32_t)(tr.rows * rowbytes);
                 ptx::mbar_wait(&empty[s], ph ^ 1);
                 ptx::mbar_arrive_expect_tx(&full[s], bytes);
-                ptx::bulk_g2s(stage0 + (size_t)s * p.stage_bytes, p.wgt + (size_t)r0 * rowbytes, bytes, &full[s]);
+                ptx::bulk_g2s(stage0 + (size_t)s * p.stage_bytes, src, bytes, &full[s]);
                 if (++s == p.stages) { s = 0; ph ^= 1; }
+                r0 += tr.rows;
             }
             // own stream issued: now pull this CTA's share of the NEXT launch's weights into L2
             if (p.pf_ptr) {
@@ -287,9 +308,11 @@ __global__ void __launch_bounds__(kGemvThreads, kGemvCtasPerSm) gemv_kernel(cons
     int s = 0, spar = 0;
     uint32_t ph = 0;
     const int npl = (PPL > 0) ? PPL : (np + WPR * 32 - 1) / (WPR * 32);  // pairs per lane
-    for (int t = 0; t < ntiles; t++) {
-        const int r0 = r_begin + t * RT;
-        const int rows = min(RT, r_end - r0);
+    for (int g0 = r_begin; g0 < r_end;) {
+        const TileRef tr = tile_at(p, g0, r_end);
+        const int r0 = tr.local, rows = tr.rows;      // rows r0 .. r0+rows-1 of matrix tr.m
+        float* Cm = p.nmat > 1 ? p.C_m[tr.m] : p.C;
+        g0 += rows;
         ptx::mbar_wait(&full[s], ph);
         const uint8_t* tile = stage0 + (size_t)s * p.stage_bytes;
         for (int pass = 0; pass * rpp < rows && !p.nocompute; pass++) {
@@ -350,7 +373,7 @@ __global__ void __launch_bounds__(kGemvThreads, kGemvCtasPerSm) gemv_kernel(cons
                     float v = acc[0];
 #pragma unroll
                     for (int tt = 1; tt < TT; tt++) v = (lane == tt) ? acc[tt] : v;
-                    peer_store(p.peer, p.C, (int64_t)lane * p.ldc_t + (int64_t)(r0 + r) * p.ldc_f, v);
+                    peer_store(p.peer, Cm, (int64_t)lane * p.ldc_t + (int64_t)(r0 + r) * p.ldc_f, v);
                 }
             } else {
                 float* sl = slots + spar * (kGemvWarps * 8);
@@ -365,7 +388,7 @@ __global__ void __launch_bounds__(kGemvThreads, kGemvCtasPerSm) gemv_kernel(cons
                     if (rr < rows) {
                         float v = 0.f;
                         for (int k = 0; k < WPR; k++) v += sl[(rs * WPR + k) * 8 + tt];
-                        peer_store(p.peer, p.C, (int64_t)tt * p.ldc_t + (int64_t)(r0 + rr) * p.ldc_f, v);
+                        peer_store(p.peer, Cm, (int64_t)tt * p.ldc_t + (int64_t)(r0 + rr) * p.ldc_f, v);
                     }
                 }
                 spar ^= 1;
@@ -486,9 +509,22 @@ static cudaError_t launch_gemv_wt(const GemvPlan& pl, const GemvParams& p, int g
     return cudaErrorInvalidValue;
 }
 
+struct GemvGroup { int nmat; const void* wgt[kGemvMaxGroup]; float* C[kGemvMaxGroup]; int F[kGemvMaxGroup]; };
+
+cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
+                        int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t st, const PeerOut* peer,
+                        const void* pf_ptr, size_t pf_bytes, const GemvGroup* group);
+
 cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
                         int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t st, const PeerOut* peer,
                         const void* pf_ptr, size_t pf_bytes) {
+    return launch_gemv(wtype, act, wgt, C, T, F, K, ldc_t, ldc_f, flags, num_sms, st, peer, pf_ptr, pf_bytes, nullptr);
+}
+
+// grouped: F = total rows of the group; wgt / C ignored when group != nullptr
+cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
+                        int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t st, const PeerOut* peer,
+                        const void* pf_ptr, size_t pf_bytes, const GemvGroup* group) {
     const int nb = K / 32;
     const bool ms = flags & QGEMM_MS_EXACT;
     GemvPlan pl;
@@ -508,6 +544,16 @@ cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, i
         p.nocompute = getenv("QGEMM_GEMV_NOCOMPUTE") ? 1 : 0;
         p.pf_ptr = (t0 + pl.tt >= T && reinterpret_cast<uintptr_t>(pf_ptr) % 16 == 0) ? (const uint8_t*)pf_ptr : nullptr;
         p.pf_bytes = pf_bytes;
+        p.nmat = 0;
+        if (group) {
+            p.nmat = group->nmat;
+            p.fstart[0] = 0;
+            for (int m = 0; m < group->nmat; m++) {
+                p.wgt_m[m] = (const uint8_t*)group->wgt[m];
+                p.C_m[m] = group->C[m] + (int64_t)t0 * ldc_t;
+                p.fstart[m + 1] = p.fstart[m] + group->F[m];
+            }
+        }
         p.peer = PeerOut{};
         if (peer) {
             if (T > pl.tt) return cudaErrorInvalidValue;  // peer mode: one pass per launch (flag accounting)

@@ -21,6 +21,10 @@ bool gemv_supported(int wtype, const void* act, const void* wgt, int F, int K);
 cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
                         int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t, const PeerOut* peer = nullptr,
                         const void* pf_ptr = nullptr, size_t pf_bytes = 0);
+struct GemvGroup { int nmat; const void* wgt[8]; float* C[8]; int F[8]; };
+cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
+                        int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t, const PeerOut* peer, const void* pf_ptr,
+                        size_t pf_bytes, const GemvGroup* group);
 bool gemv_mma_supported(int wtype, const void* act, const void* wgt, int T, int F, int K);
 cudaError_t launch_gemv_mma(int wtype, const void* act, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
                             int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t, const PeerOut* peer = nullptr);
@@ -239,6 +243,38 @@ int qgemm_set_default_workspace(void* workspace, size_t workspace_bytes) {
     g_default_ws[d].ptr = workspace;
     g_default_ws[d].bytes = workspace_bytes;
     return QGEMM_OK;
+}
+
+int qgemm_gemm_group(int wtype, const void* act_q8_1, int nmat, const void* const* weights, float* const* Cs, const int* Fs,
+                     int T, int K, int64_t ldc_t, int64_t ldc_f, uint32_t flags, void* stream) {
+    if (nmat < 1 || nmat > 8 || !weights || !Cs || !Fs) return QGEMM_E_BADARG;
+    GemvGroup g{};
+    g.nmat = nmat;
+    int Ftot = 0;
+    for (int m = 0; m < nmat; m++) {
+        if (int rc = check_gemm_args(wtype, act_q8_1, weights[m], Cs[m], T, Fs[m], K)) return rc;
+        if (Fs[m] < 1) return QGEMM_E_BADARG;
+        g.wgt[m] = weights[m]; g.C[m] = Cs[m]; g.F[m] = Fs[m];
+        Ftot += Fs[m];
+    }
+    if (T < 1 || K < 32) return QGEMM_E_BADARG;
+    DeviceInfo dev;
+    if (int rc = device_check(&dev)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    bool fast = true;
+    for (int m = 0; m < nmat; m++) fast = fast && gemv_supported(wtype, act_q8_1, weights[m], Fs[m], K);
+    if (!fast || T > 8) {  // same results, one launch per matrix
+        for (int m = 0; m < nmat; m++)
+            if (int rc = run_gemm(wtype, act_q8_1, weights[m], Cs[m], T, Fs[m], K, ldc_t, ldc_f, flags, nullptr, 0, st, dev))
+                return rc;
+        return QGEMM_OK;
+    }
+    cudaError_t e = launch_gemv(wtype, act_q8_1, nullptr, nullptr, T, Ftot, K, ldc_t, ldc_f, flags, dev.sms, st, nullptr,
+                                t_pf_ptr, t_pf_bytes, &g);
+    t_pf_ptr = nullptr;
+    t_pf_bytes = 0;
+    t_last_path = QGEMM_PATH_GEMV;
+    return e == cudaSuccess ? QGEMM_OK : cuda_fail(e, "gemm_group launch");
 }
 
 int qgemm_hint_next_weights(const void* next_weights, size_t bytes) {

@@ -176,6 +176,32 @@ def gemm(weight_q: torch.Tensor, activation_q: torch.Tensor, M: int, N: int, K: 
     return out
 
 
+def gemm_group(weights_q: list, activation_q: torch.Tensor, Ms: list, N: int, K: int, wtype: int, flags: int = 0,
+               outs: list | None = None) -> list:
+    """Several weight matrices (same type, same K) against the same activations in ONE launch: fused
+    q/k/v or gate/up projections.  Returns [M_i, N] outputs identical to separate gemm() calls."""
+    import ctypes as C
+    n = len(weights_q)
+    _check(1 <= n <= 8 and len(Ms) == n, "gemm_group takes 1..8 matrices")
+    nb = K // 32
+    _check(K % 32 == 0, f"K must be divisible by 32, got {K}")
+    _check(activation_q.is_cuda and activation_q.dtype == torch.uint8 and activation_q.numel() == N * nb * 36,
+           "Activation shape mismatch")
+    activation_q = activation_q.contiguous()
+    ws = [w.contiguous() for w in weights_q]
+    for w, M in zip(ws, Ms):
+        _check(w.is_cuda and w.dtype == torch.uint8 and w.numel() == M * nb * BLOCK_BYTES[wtype], "Weight shape mismatch")
+    if outs is None:
+        outs = [torch.empty((M, N), dtype=torch.float32, device=activation_q.device) for M in Ms]
+    wp = (C.c_void_p * n)(*[w.data_ptr() for w in ws])
+    cp = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+    fs = (C.c_int * n)(*Ms)
+    with torch.cuda.device(activation_q.device):
+        rc = _lib.lib().qgemm_gemm_group(wtype, activation_q.data_ptr(), n, wp, cp, fs, N, K, 1, N, flags, _stream(activation_q))
+    _lib.raise_on_error(rc, "gemm_group")
+    return outs
+
+
 def gemm_q4_0_q8_1(weight_q, activation_q, M, N, K, flags: int = 0):
     """Q4_0 x Q8_1 GEMM -> [M, N] float32 (python/quant_gemm/__init__.py:59-75)."""
     return gemm(weight_q, activation_q, M, N, K, TYPE_Q4_0, flags)
@@ -261,5 +287,5 @@ __all__ = [
     # supersets
     "quantize_q4_1", "quantize_q5_0", "quantize_q5_1", "quantize_q8_0", "dequantize",
     "gemm", "gemm_q4_1_q8_1", "gemm_q5_0_q8_1", "gemm_q5_1_q8_1", "gemm_q8_0_q8_1", "gemm_w4a8",
-    "block_sumi", "launch_count", "reset_launch_count", "last_path", "hint_next_weights",
+    "gemm_group", "block_sumi", "launch_count", "reset_launch_count", "last_path", "hint_next_weights",
 ]

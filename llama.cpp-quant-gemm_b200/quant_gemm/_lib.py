@@ -28,6 +28,7 @@ SYMBOLS = {
     "qgemm_dequantize": (_i, [_i, _p, _p, _i64, _i64, _p]),
     "qgemm_set_default_workspace": (_i, [_p, _sz]),
     "qgemm_hint_next_weights": (_i, [_p, _sz]),
+    "qgemm_gemm_group": (_i, [_i, _p, _i, C.POINTER(_p), C.POINTER(_p), C.POINTER(_i), _i, _i, _i64, _i64, _u32, _p]),
     "qgemm_workspace_bytes": (_sz, [_i, _i, _i, _i, _u32]),
     "qgemm_gemm": (_i, [_i, _p, _p, _p, _i, _i, _i, _i64, _i64, _u32, _p, _sz, _p]),
     "qgemm_gemm_f32act": (_i, [_i, _p, _p, _p, _i, _i, _i, _i64, _i64, _u32, _p, _sz, _p]),

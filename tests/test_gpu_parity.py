@@ -441,3 +441,28 @@ def test_peer_store_protocol_single_gpu(qg, O, wt, T):
     assert L.qgemm_gemm_peers(wt, da.data_ptr(), dw.data_ptr(), ps, T, F, K, 1, T, 0, st) == -1
     ps.launch_index = 0
     assert L.qgemm_gemm_peers(wt, da.data_ptr(), dw.data_ptr(), ps, 64, F, K, 1, 64, 0, st) in (-1, -2)
+
+
+# ------------------------------------------------------------------------------------------
+# grouped decode launch (fused q/k/v, gate/up): identical to separate calls
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("wt,T,K", [(qo.Q4_0, 1, 4096), (qo.Q5_1, 2, 1024), (qo.Q8_0, 1, 11008), (qo.Q4_1, 8, 2048)])
+def test_gemm_group_equals_separate_calls(qg, O, wt, T, K):
+    Fs = [256, 100, 37]          # sizes that are not tile multiples: tiles must break at matrix boundaries
+    x, _ = datagen.model_like(T, 8, K, seed=5)
+    aq = O.quantize_q8_1(x)
+    wqs = [O.quantize_weight(wt, datagen.model_like(1, F, K, seed=10 + i)[1]) for i, F in enumerate(Fs)]
+    da = dev(aq)
+    dws = [dev(w) for w in wqs]
+    outs = qg.gemm_group(dws, da, Fs, T, K, wt)
+    for F, wq, dw, o in zip(Fs, wqs, dws, outs):
+        c = host(o)
+        check_c(c, O.gemm(wt, aq, wq, layout="FT"), "group vs oracle")
+        sep = host(qg.gemm(dw, da, F, T, K, wt, flags=0x200))
+        assert (bits(c) == bits(sep)).all()
+    # T > 8 falls back to one launch per matrix, same answers
+    x2, _ = datagen.model_like(12, 8, K, seed=6)
+    aq2 = O.quantize_q8_1(x2)
+    outs = qg.gemm_group(dws, dev(aq2), Fs, 12, K, wt)
+    for wq, o in zip(wqs, outs):
+        check_c(host(o), O.gemm(wt, aq2, wq, layout="FT"), "group fallback")
