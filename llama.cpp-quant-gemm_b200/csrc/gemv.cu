@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(kGemvThreads, kGemvCtasPerSm) gemv_kernel(cons
             const int pg = (j * WPR + sub) * 32 + lane;
 #pragma unroll
             for (int t = 0; t < TT; t++) {
-                if (kFull || pg < np) {
+                if (kFull || j < PPL - 1 || pg < np) {
                     const uint32_t* w = dst + ((size_t)t * nb + 2 * pg) * 9;
 #pragma unroll
                     for (int b = 0; b < 2; b++) {
@@ -354,7 +354,9 @@ __global__ void __launch_bounds__(kGemvThreads, kGemvCtasPerSm) gemv_kernel(cons
 #pragma unroll
                     for (int j = 0; j < PPL; j++) {
                         const int pg = (j * WPR + sub) * 32 + lane;
-                        if (kFull || pg < np) do_pair(j, pg);
+                        // by construction of PPL only the last index can fall off the row: the others run
+                        // unpredicated so the compiler interleaves their independent chains
+                        if (kFull || j < PPL - 1 || pg < np) do_pair(j, pg);
                     }
                 } else {
                     for (int j = 0; j < npl; j++) {
@@ -376,20 +378,18 @@ __global__ void __launch_bounds__(kGemvThreads, kGemvCtasPerSm) gemv_kernel(cons
                     peer_store(p.peer, Cm, (int64_t)lane * p.ldc_t + (int64_t)(r0 + r) * p.ldc_f, v);
                 }
             } else {
+                // only the WPR warps that share this row meet (named barrier 2 + row slot); the first
+                // of them adds the partials in warp order and stores
                 float* sl = slots + spar * (kGemvWarps * 8);
                 if (lane == 0) {
 #pragma unroll
                     for (int tt = 0; tt < TT; tt++) sl[warp * 8 + tt] = acc[tt];
                 }
-                ptx::bar_sync(1, kGemvWarps * 32);
-                if (tid < rpp * TT) {
-                    const int rs = tid / TT, tt = tid - rs * TT;
-                    const int rr = pass * rpp + rs;
-                    if (rr < rows) {
-                        float v = 0.f;
-                        for (int k = 0; k < WPR; k++) v += sl[(rs * WPR + k) * 8 + tt];
-                        peer_store(p.peer, Cm, (int64_t)tt * p.ldc_t + (int64_t)(r0 + rr) * p.ldc_f, v);
-                    }
+                ptx::bar_sync(2 + rslot, WPR * 32);
+                if (sub == 0 && lane < TT && r < rows) {
+                    float v = 0.f;
+                    for (int k = 0; k < WPR; k++) v += sl[(rslot * WPR + k) * 8 + lane];
+                    peer_store(p.peer, Cm, (int64_t)lane * p.ldc_t + (int64_t)(r0 + r) * p.ldc_f, v);
                 }
                 spar ^= 1;
             }
