@@ -259,7 +259,7 @@ def main():
     for F, K, _ in mats:
         outs.append(out_all[off:off + F * world].view(F * world, 1))
         off += F * world
-    out_host = torch.empty(total_out, dtype=torch.float32).pin_memory()
+    out_host = torch.empty(total_out + 64 * len(mats), dtype=torch.float32).pin_memory()  # + pool alignment padding
     step_bytes = sum(algorithmic_bytes(WTYPE, 1, F, K) for F, K, _ in mats)
 
     from quant_gemm import sharded
@@ -269,14 +269,31 @@ def main():
         # all-gather fused into the GEMV: the kernel stores its slice of C into every rank's gathered
         # buffer over NVLink (symmetric memory) and signals with device-side counters
         plan = sharded.PeerPlan(sum(F * world for F, K, _ in mats), len(mats), dev, ctl_group=ctl)
-        # Llama dataflow: [wq wk wv] <- previous layer's down, wo <- wv, [gate up] <- wo, down <- up
-        ops = []
-        for i, (F, K, w) in enumerate(mats):
-            j = i % 7
-            wait = i - j if j < 3 else (i if j in (3, 4, 6) else i - 1)
-            ops.append(sharded.ShardedGemvP2P(w, F * world, K, WTYPE, 1, plan, wait_index=wait,
-                                              flags=READY_FLAGS if j in (1, 2, 5) else GEMV_FLAGS))
-        outs = [op.out for op in ops]
+        if args.group:
+            # 4 launches per layer: [wq wk wv] fused, wo, [gate up] fused, down -- each waits for its predecessor
+            plan.lps = 4 * args.layers
+            ops, outs = [], []
+            for l in range(args.layers):
+                b = 7 * l
+                for g in ([b, b + 1, b + 2], [b + 3], [b + 4, b + 5], [b + 6]):
+                    K = mats[g[0]][1]
+                    if len(g) == 1:
+                        op = sharded.ShardedGemvP2P(mats[g[0]][2], mats[g[0]][0] * world, K, WTYPE, 1, plan, flags=GEMV_FLAGS)
+                        outs.append(op.out)
+                    else:
+                        op = sharded.ShardedGemvGroupP2P([mats[i][2] for i in g], [mats[i][0] * world for i in g], K, WTYPE,
+                                                         1, plan, flags=GEMV_FLAGS)
+                        outs += op.outs
+                    ops.append((op, K, g))
+        else:
+            # Llama dataflow: [wq wk wv] <- previous layer's down, wo <- wv, [gate up] <- wo, down <- up
+            ops = []
+            for i, (F, K, w) in enumerate(mats):
+                j = i % 7
+                wait = i - j if j < 3 else (i if j in (3, 4, 6) else i - 1)
+                ops.append(sharded.ShardedGemvP2P(w, F * world, K, WTYPE, 1, plan, wait_index=wait,
+                                                  flags=READY_FLAGS if j in (1, 2, 5) else GEMV_FLAGS))
+            outs = [op.out for op in ops]
     else:  # baseline: in-place NCCL all-gather after every GEMV
         # Llama dataflow: wk, wv read the same (already complete) input as wq, `up` the same as `gate`
         ops = [sharded.ShardedGemm(w, F * world, K, WTYPE, flags=READY_FLAGS if (i % 7) in (1, 2, 5) else GEMV_FLAGS)
@@ -292,6 +309,13 @@ def main():
             groups += [[b, b + 1, b + 2], [b + 3], [b + 4, b + 5], [b + 6]]
 
     def gemv_all():
+        if plan is not None and args.group:
+            for oi, (op, K, g) in enumerate(ops):
+                if args.prefetch:
+                    quant_gemm.hint_next_weights(mats[ops[(oi + 1) % len(ops)][2][0]][2])
+                op(acts_q[K])
+            plan.end_step()
+            return
         if groups:
             for gi, g in enumerate(groups):
                 nxt = groups[(gi + 1) % len(groups)]
@@ -322,12 +346,9 @@ def main():
             acts_q[K] = quant_gemm.quantize_q8_1(acts_dev[K])
         gemv_all()
         if plan is not None:   # fused all-gather: the gathered outputs live in the symmetric pool
-            off = 0
-            for op in ops:
-                out_host[off:off + op.out.numel()].copy_(op.out.view(-1), non_blocking=True)
-                off += op.out.numel()
+            out_host[:plan.cursor].copy_(plan.pool[:plan.cursor], non_blocking=True)
         else:
-            out_host.copy_(out_all, non_blocking=True)
+            out_host[:total_out].copy_(out_all, non_blocking=True)
 
     stream = torch.cuda.Stream(device=dev)
     with torch.cuda.stream(stream):
@@ -381,7 +402,7 @@ def main():
         F, K, w = mats[4]
         rows = np.r_[0:4, F - 4:F]
         ref = O.gemm(WTYPE, acts_q[K].cpu().numpy(), w[torch.from_numpy(rows).to(dev)].cpu().numpy(), layout="FT")
-        got = outs[4][rank * F:(rank + 1) * F].cpu().numpy()[rows]
+        got = outs[4][rank * F:(rank + 1) * F].cpu().numpy()[rows]  # outs[] stays indexed by matrix in every mode
         check = qo.max_norm_err(got, ref)
         assert check <= 1e-5, f"timed path disagrees with the oracle: {check}"
 

@@ -228,6 +228,10 @@ typedef struct qgemm_peers {
 
 QGEMM_API int qgemm_gemm_peers(int wtype, const void *act_q8_1, const void *weight, const qgemm_peers *peers, int T,
                                int F, int K, int64_t ldc_t, int64_t ldc_f, uint32_t flags, void *stream);
+/* Grouped form (see qgemm_gemm_group): matrix m's slice goes to peers->C[r] + c_offsets[m] on every rank r. */
+QGEMM_API int qgemm_gemm_group_peers(int wtype, const void *act_q8_1, int nmat, const void *const *weights,
+                                     const int *Fs, const int64_t *c_offsets, const qgemm_peers *peers, int T, int K,
+                                     int64_t ldc_t, int64_t ldc_f, uint32_t flags, void *stream);
 QGEMM_API int qgemm_peer_step_advance(uint32_t *step, void *stream);
 QGEMM_API int qgemm_peer_wait(const qgemm_peers *peers, void *stream);
 

@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(kGemvThreads, kGemvCtasPerSm) gemv_kernel(cons
                     float v = acc[0];
 #pragma unroll
                     for (int tt = 1; tt < TT; tt++) v = (lane == tt) ? acc[tt] : v;
-                    peer_store(p.peer, Cm, (int64_t)lane * p.ldc_t + (int64_t)(r0 + r) * p.ldc_f, v);
+                    peer_store(p.peer, Cm, (int64_t)lane * p.ldc_t + (int64_t)(r0 + r) * p.ldc_f, v, tr.m);
                 }
             } else {
                 // only the WPR warps that share this row meet (named barrier 2 + row slot); the first
@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(kGemvThreads, kGemvCtasPerSm) gemv_kernel(cons
                 if (sub == 0 && lane < TT && r < rows) {
                     float v = 0.f;
                     for (int k = 0; k < WPR; k++) v += sl[(rslot * WPR + k) * 8 + lane];
-                    peer_store(p.peer, Cm, (int64_t)lane * p.ldc_t + (int64_t)(r0 + r) * p.ldc_f, v);
+                    peer_store(p.peer, Cm, (int64_t)lane * p.ldc_t + (int64_t)(r0 + r) * p.ldc_f, v, tr.m);
                 }
                 spar ^= 1;
             }

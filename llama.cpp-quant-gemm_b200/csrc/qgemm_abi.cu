@@ -330,24 +330,58 @@ int qgemm_sumi(int wtype, const void* act_q8_1, const void* weight, int32_t* sum
     return e == cudaSuccess ? QGEMM_OK : QGEMM_E_CUDA;
 }
 
-int qgemm_gemm_peers(int wtype, const void* act_q8_1, const void* weight, const qgemm_peers* peers, int T, int F, int K,
-                     int64_t ldc_t, int64_t ldc_f, uint32_t flags, void* stream) {
+static int make_peer_out(const qgemm_peers* peers, PeerOut* po) {
     if (!peers || peers->world < 1 || peers->world > kMaxPeers || peers->rank < 0 || peers->rank >= peers->world ||
         !peers->done || !peers->step || peers->launches_per_step == 0 || peers->launch_index >= peers->launches_per_step ||
         peers->wait_index > peers->launch_index)
         return QGEMM_E_BADARG;
     for (int r = 0; r < peers->world; r++)
         if (!peers->C[r] || !peers->flag[r]) return QGEMM_E_BADARG;
+    *po = PeerOut{};
+    po->world = peers->world; po->rank = peers->rank;
+    for (int r = 0; r < peers->world; r++) { po->C[r] = peers->C[r]; po->flag[r] = peers->flag[r]; }
+    po->done = peers->done; po->step = peers->step; po->lps = peers->launches_per_step; po->li = peers->wait_index;
+    po->dbg = getenv("QGEMM_PEER_DBG") ? atoi(getenv("QGEMM_PEER_DBG")) : 0;
+    return QGEMM_OK;
+}
+
+int qgemm_gemm_group_peers(int wtype, const void* act_q8_1, int nmat, const void* const* weights, const int* Fs,
+                           const int64_t* c_offsets, const qgemm_peers* peers, int T, int K, int64_t ldc_t, int64_t ldc_f,
+                           uint32_t flags, void* stream) {
+    if (nmat < 1 || nmat > 8 || !weights || !Fs || !c_offsets) return QGEMM_E_BADARG;
+    PeerOut po;
+    if (int rc = make_peer_out(peers, &po)) return rc;
+    GemvGroup g{};
+    g.nmat = nmat;
+    int Ftot = 0;
+    for (int m = 0; m < nmat; m++) {
+        if (Fs[m] < 1) return QGEMM_E_BADARG;
+        if (int rc = check_gemm_args(wtype, act_q8_1, weights[m], peers->C[peers->rank], T, Fs[m], K)) return rc;
+        if (!gemv_supported(wtype, act_q8_1, weights[m], Fs[m], K)) return QGEMM_E_ALIGN;
+        g.wgt[m] = weights[m]; g.C[m] = peers->C[peers->rank] + c_offsets[m]; g.F[m] = Fs[m];
+        po.moff[m] = c_offsets[m];
+        Ftot += Fs[m];
+    }
+    if (T < 1 || T > 8 || K < 32) return QGEMM_E_BADARG;
+    DeviceInfo dev;
+    if (int rc = device_check(&dev)) return rc;
+    cudaError_t e = launch_gemv(wtype, act_q8_1, nullptr, nullptr, T, Ftot, K, ldc_t, ldc_f, flags, dev.sms,
+                                (cudaStream_t)stream, &po, t_pf_ptr, t_pf_bytes, &g);
+    t_pf_ptr = nullptr;
+    t_pf_bytes = 0;
+    t_last_path = QGEMM_PATH_GEMV;
+    return e == cudaSuccess ? QGEMM_OK : cuda_fail(e, "gemm_group_peers launch");
+}
+
+int qgemm_gemm_peers(int wtype, const void* act_q8_1, const void* weight, const qgemm_peers* peers, int T, int F, int K,
+                     int64_t ldc_t, int64_t ldc_f, uint32_t flags, void* stream) {
+    PeerOut po;
+    if (int rc = make_peer_out(peers, &po)) return rc;
     float* C = peers->C[peers->rank];
     if (int rc = check_gemm_args(wtype, act_q8_1, weight, C, T, F, K)) return rc;
     if (T == 0 || F == 0 || K == 0) return QGEMM_E_BADARG;  // every rank must launch: no empty shards in peer mode
     DeviceInfo dev;
     if (int rc = device_check(&dev)) return rc;
-    PeerOut po{};
-    po.world = peers->world; po.rank = peers->rank;
-    for (int r = 0; r < peers->world; r++) { po.C[r] = peers->C[r]; po.flag[r] = peers->flag[r]; }
-    po.done = peers->done; po.step = peers->step; po.lps = peers->launches_per_step; po.li = peers->wait_index;
-    po.dbg = getenv("QGEMM_PEER_DBG") ? atoi(getenv("QGEMM_PEER_DBG")) : 0;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
     if (T >= kMmaMinTokens && T <= 8 && gemv_mma_supported(wtype, act_q8_1, weight, T, F, K)) {

@@ -185,6 +185,7 @@ struct PeerOut {
     uint32_t* done;               // local CTA-completion counter (returns to 0 after each launch)
     const uint32_t* step;         // local step counter (qgemm_peer_step_advance)
     uint32_t lps, li;             // launches per step, launches of this step that must have landed first
+    long long moff[kMaxPeers];    // grouped launch: element offset of matrix m's slice from C[r]
     int dbg;                      // tuning aid: 1 skip wait, 2 local store only, 4 skip per-thread fence
 };
 
@@ -205,10 +206,11 @@ __device__ __forceinline__ void peer_wait_prior(const PeerOut& po) {
 }
 // every storing thread calls this after its last store; then, after a CTA-wide barrier, one
 // thread calls peer_signal_done()
-__device__ __forceinline__ void peer_store(const PeerOut& po, float* C, int64_t idx, float v) {
+__device__ __forceinline__ void peer_store(const PeerOut& po, float* C, int64_t idx, float v, int m = 0) {
     if (po.world > 1) {
-#pragma unroll 1
+        idx += po.moff[m];
         if (po.dbg & 2) { po.C[po.rank][idx] = v; return; }
+#pragma unroll 1
         for (int r = 0; r < po.world; r++) po.C[r][idx] = v;
     } else {
         C[idx] = v;

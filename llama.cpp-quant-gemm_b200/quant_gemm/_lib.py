@@ -46,6 +46,8 @@ class QgemmPeers(C.Structure):
 
 SYMBOLS.update({
     "qgemm_gemm_peers": (_i, [_i, _p, _p, C.POINTER(QgemmPeers), _i, _i, _i, _i64, _i64, _u32, _p]),
+    "qgemm_gemm_group_peers": (_i, [_i, _p, _i, C.POINTER(_p), C.POINTER(_i), C.POINTER(_i64), C.POINTER(QgemmPeers), _i, _i,
+                               _i64, _i64, _u32, _p]),
     "qgemm_peer_step_advance": (_i, [_p, _p]),
     "qgemm_peer_wait": (_i, [C.POINTER(QgemmPeers), _p]),
 })

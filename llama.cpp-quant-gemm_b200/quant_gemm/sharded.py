@@ -178,3 +178,37 @@ class ShardedGemvP2P:
                                 torch.cuda.current_stream(self.weight.device).cuda_stream)
         _lib.raise_on_error(rc, "gemm_peers")
         return self.out
+
+
+class ShardedGemvGroupP2P:
+    """Grouped form of ShardedGemvP2P: several row-sharded matrices that share their activations
+    (fused q/k/v, gate/up) in ONE launch and ONE cross-GPU arrival."""
+
+    def __init__(self, weight_shards: list, F_totals: list, K: int, wtype: int, T: int, plan: PeerPlan,
+                 align: int = DEFAULT_ALIGN, flags: int = 0, wait_index: Optional[int] = None):
+        import ctypes as C
+        self.plan, self.K, self.wtype, self.T, self.flags = plan, K, wtype, T, flags
+        self.n = len(weight_shards)
+        self.weights = [w.contiguous() for w in weight_shards]
+        self.outs, offs, fs = [], [], []
+        for w, Ft in zip(self.weights, F_totals):
+            f0, f1 = shard_rows(Ft, plan.world, plan.rank, align)
+            assert w.shape[0] == f1 - f0 > 0
+            off = plan.alloc(Ft * T)
+            self.outs.append(plan.pool[off:off + Ft * T].view(Ft, T))
+            offs.append(off + f0 * T)
+            fs.append(f1 - f0)
+        self.launch_index = plan.next_index
+        plan.next_index += 1
+        assert plan.next_index <= plan.lps
+        self.ps = plan.peers_struct(0, self.launch_index, wait_index)
+        self._wp = (C.c_void_p * self.n)(*[w.data_ptr() for w in self.weights])
+        self._fs = (C.c_int * self.n)(*fs)
+        self._offs = (C.c_int64 * self.n)(*offs)
+
+    def __call__(self, activation_q: torch.Tensor) -> list:
+        rc = _lib.lib().qgemm_gemm_group_peers(self.wtype, activation_q.data_ptr(), self.n, self._wp, self._fs, self._offs,
+                                               self.ps, self.T, self.K, 1, self.T, self.flags,
+                                               torch.cuda.current_stream(self.weights[0].device).cuda_stream)
+        _lib.raise_on_error(rc, "gemm_group_peers")
+        return self.outs
