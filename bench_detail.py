@@ -80,13 +80,16 @@ def time_shape(torch, quant_gemm, wtype, T, F, K, flags=0x10, reps=3, pool_bytes
             "path": hex(quant_gemm.last_path())}
 
 
-def time_prefill(torch, quant_gemm, wtype, T, F, K, flags=0, reps=5, fused_f32=False):
+def time_prefill(torch, quant_gemm, wtype, T, F, K, flags=0, reps=5, fused_f32=False, prepacked=False):
     """Whole-call time (prepass + tensor-core kernel [+ quantize_q8_1 when fused_f32]), L2 flushed between reps."""
     dev = torch.device("cuda")
     w = make_weights(torch, wtype, F, K, 1, dev)[0]
     x = torch.randn((T, K), device=dev)
     aq = quant_gemm.quantize_q8_1(x)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    if prepacked:
+        w = quant_gemm.prepack_weights(w, F, K, wtype)
+        flags |= quant_gemm.GEMM_WEIGHTS_PREPACKED
     call = (lambda: quant_gemm.gemm_w4a8(w, x, F, T, K, wtype, flags)) if fused_f32 else \
            (lambda: quant_gemm.gemm(w, aq, F, T, K, wtype, flags))
     for _ in range(2):
@@ -103,7 +106,8 @@ def time_prefill(torch, quant_gemm, wtype, T, F, K, flags=0, reps=5, fused_f32=F
         times.append(e0.elapsed_time(e1) * 1e3)
     best = min(times)
     return {"type": NAMES[wtype], "T": T, "F": F, "K": K, "us": best, "us_median": sorted(times)[len(times) // 2],
-            "tops": 2.0 * T * F * K / best / 1e6, "fused_quantize": fused_f32, "path": hex(quant_gemm.last_path())}
+            "tops": 2.0 * T * F * K / best / 1e6, "fused_quantize": fused_f32, "prepacked_weights": prepacked,
+            "path": hex(quant_gemm.last_path())}
 
 
 def run_prefill(out_path):
@@ -116,6 +120,10 @@ def run_prefill(out_path):
         r = time_prefill(torch, quant_gemm, wt, T, F, K, fused_f32=fused)
         rows.append(r)
         print(json.dumps(r), flush=True)
+        if not fused:
+            r = time_prefill(torch, quant_gemm, wt, T, F, K, prepacked=True)
+            rows.append(r)
+            print(json.dumps(r), flush=True)
     with open(out_path, "w") as f:
         json.dump({"rows": rows}, f, indent=1)
 

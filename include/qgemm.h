@@ -78,6 +78,7 @@ extern "C" {
                                    `gate`: same input, different outputs).  The decode kernel then computes
                                    without waiting for its predecessor and only waits before it exits, so
                                    stream-order completion is preserved for everything launched after it */
+#define QGEMM_WEIGHTS_PREPACKED 0x40u /* `weight` is a qgemm_prepack_weights() buffer (tensor-core path only) */
 #define QGEMM_PATH_MASK 0xF00u
 #define QGEMM_PATH_AUTO 0x000u
 #define QGEMM_PATH_GENERIC 0x100u /* same kernel as QGEMM_SEQUENTIAL                         */
@@ -158,6 +159,17 @@ QGEMM_API int qgemm_gemm(int wtype, const void *act_q8_1, const void *weight, fl
  * keep it alive and un-shared between concurrently running streams.  (NULL, 0) unregisters.
  */
 QGEMM_API int qgemm_set_default_workspace(void *workspace, size_t workspace_bytes);
+
+/*
+ * Offline weight pre-pack for the tensor-core path (static weights): unpacks the native blocks
+ * once into the operand-tile layout the prefill kernel streams (`qgemm_prepack_bytes` bytes,
+ * 256-byte aligned device memory).  Pass the packed buffer as `weight` together with
+ * QGEMM_WEIGHTS_PREPACKED | QGEMM_PATH_TCGEN05 (or AUTO with T >= 96) and the per-call weight
+ * prepass disappears; results are unchanged.  The native blocks stay the format of every other path.
+ * Data-format neighbour of the path.
+ */
+QGEMM_API size_t qgemm_prepack_bytes(int wtype, int F, int K);
+QGEMM_API int qgemm_prepack_weights(int wtype, const void *weight, int F, int K, void *packed, void *stream);
 
 /*
  * Grouped decode GEMM: `nmat` weight matrices of the same type and K applied to the SAME

@@ -77,6 +77,23 @@ static MmqWs mmq_layout(int T, int F, int K) {
     return L;
 }
 
+// Offline weight pre-pack: the weight half of the layout above in a
+// buffer of its own, built once for static weights: [ w8 | ws | wm ].
+struct MmqPack { size_t w8, ws, wm, total; int Fpad, nkc; };
+static MmqPack mmq_pack_layout(int F, int K) {
+    MmqPack P;
+    P.Fpad = (F + kBN - 1) / kBN * kBN;
+    P.nkc = (K + kKC - 1) / kKC;
+    const int nbp = P.nkc * kBlocksPerStage;
+    auto up = [](size_t v) { return (v + 1023) / 1024 * 1024; };
+    size_t o = 0;
+    P.w8 = o; o = up(o + (size_t)P.nkc * P.Fpad * kKC);
+    P.ws = o; o = up(o + (size_t)nbp * P.Fpad * 4);
+    P.wm = o; o = up(o + (size_t)nbp * P.Fpad * 4);
+    P.total = o;
+    return P;
+}
+
 // ---------------------------------------------------------------------------
 // prepass 1: q8_1 AoS -> swizzled s8 tiles + (d_a, c_a) slabs
 //   a8[kc][t][16-byte chunk c ^ (t & 7)]            (chunk c = (b & 3) * 2 + {0, 1})
@@ -450,7 +467,15 @@ static cudaError_t launch_mmq_t(const void* act, const void* wgt, float* C, int3
             (const uint8_t*)act, base + L.a8, (float2*)(base + L.as), T, L.Tpad, nb, nbp, coef);
         note_launch();
     }
-    {
+    const uint8_t* w8 = base + L.w8;
+    const float* wsp = (const float*)(base + L.ws);
+    const float* wmp = (const float*)(base + L.wm);
+    if (flags & QGEMM_WEIGHTS_PREPACKED) {  // `wgt` is a qgemm_prepack_weights() buffer: nothing to unpack
+        const MmqPack P = mmq_pack_layout(F, K);
+        w8 = (const uint8_t*)wgt + P.w8;
+        wsp = (const float*)((const uint8_t*)wgt + P.ws);
+        wmp = (const float*)((const uint8_t*)wgt + P.wm);
+    } else {
         const int64_t n = (int64_t)L.Fpad * nbp;
         mmq_unpack_weight_kernel<WT><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
             (const uint8_t*)wgt, base + L.w8, (float*)(base + L.ws), (float*)(base + L.wm), F, L.Fpad, nb, nbp);
@@ -467,7 +492,7 @@ static cudaError_t launch_mmq_t(const void* act, const void* wgt, float* C, int3
     }
     MmqParams p;
     p.a8 = base + L.a8; p.as = (const float2*)(base + L.as);
-    p.w8 = base + L.w8; p.ws = (const float*)(base + L.ws); p.wm = (const float*)(base + L.wm);
+    p.w8 = w8; p.ws = wsp; p.wm = wmp;
     p.C = C; p.sumi = sumi;
     p.T = T; p.F = F; p.nb = nb; p.nkc = L.nkc; p.Tpad = L.Tpad; p.Fpad = L.Fpad;
     p.ldc_t = ldc_t; p.ldc_f = ldc_f;
@@ -476,6 +501,32 @@ static cudaError_t launch_mmq_t(const void* act, const void* wgt, float* C, int3
     const int ntiles = p.tiles_m * p.tiles_n;
     if (sumi) mmq_kernel<WT, true><<<min(ntiles, num_sms), kMmqThreads, kMmqSmem, st>>>(p);
     else mmq_kernel<WT, false><<<min(ntiles, num_sms), kMmqThreads, kMmqSmem, st>>>(p);
+    note_launch();
+    return cudaGetLastError();
+}
+
+size_t mmq_prepack_bytes(int wtype, int F, int K) {
+    if (block_bytes(wtype) == 0 || wtype == QGEMM_TYPE_Q8_1 || F < 1 || K < 32) return 0;
+    return mmq_pack_layout(F, K).total;
+}
+
+cudaError_t launch_mmq_prepack(int wtype, const void* wgt, void* packed, int F, int K, cudaStream_t st) {
+    const MmqPack P = mmq_pack_layout(F, K);
+    const int nb = K / 32, nbp = P.nkc * kBlocksPerStage;
+    uint8_t* base = (uint8_t*)packed;
+    const int64_t n = (int64_t)P.Fpad * nbp;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    const uint8_t* w = (const uint8_t*)wgt;
+    float* ws = (float*)(base + P.ws);
+    float* wm = (float*)(base + P.wm);
+    switch (wtype) {
+    case QGEMM_TYPE_Q4_0: mmq_unpack_weight_kernel<QGEMM_TYPE_Q4_0><<<grid, 256, 0, st>>>(w, base + P.w8, ws, wm, F, P.Fpad, nb, nbp); break;
+    case QGEMM_TYPE_Q4_1: mmq_unpack_weight_kernel<QGEMM_TYPE_Q4_1><<<grid, 256, 0, st>>>(w, base + P.w8, ws, wm, F, P.Fpad, nb, nbp); break;
+    case QGEMM_TYPE_Q5_0: mmq_unpack_weight_kernel<QGEMM_TYPE_Q5_0><<<grid, 256, 0, st>>>(w, base + P.w8, ws, wm, F, P.Fpad, nb, nbp); break;
+    case QGEMM_TYPE_Q5_1: mmq_unpack_weight_kernel<QGEMM_TYPE_Q5_1><<<grid, 256, 0, st>>>(w, base + P.w8, ws, wm, F, P.Fpad, nb, nbp); break;
+    case QGEMM_TYPE_Q8_0: mmq_unpack_weight_kernel<QGEMM_TYPE_Q8_0><<<grid, 256, 0, st>>>(w, base + P.w8, ws, wm, F, P.Fpad, nb, nbp); break;
+    default: return cudaErrorInvalidValue;
+    }
     note_launch();
     return cudaGetLastError();
 }

@@ -28,6 +28,8 @@ cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, i
 bool gemv_mma_supported(int wtype, const void* act, const void* wgt, int T, int F, int K);
 cudaError_t launch_gemv_mma(int wtype, const void* act, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
                             int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t, const PeerOut* peer = nullptr);
+size_t mmq_prepack_bytes(int wtype, int F, int K);
+cudaError_t launch_mmq_prepack(int wtype, const void* wgt, void* packed, int F, int K, cudaStream_t);
 bool mmq_supported(int wtype, const void* act, const void* wgt, int T, int F, int K);
 size_t mmq_workspace_bytes(int wtype, int T, int F, int K);
 cudaError_t launch_mmq(int wtype, const void* act, const void* wgt, float* C, int32_t* sumi_out, int T, int F, int K,
@@ -127,6 +129,10 @@ static int run_gemm(int wtype, const void* act, const void* wgt, float* C, int T
     }
     uint32_t path = flags & QGEMM_PATH_MASK;
     if (flags & QGEMM_SEQUENTIAL) path = QGEMM_PATH_GENERIC;
+    if (flags & QGEMM_WEIGHTS_PREPACKED) {  // only the tensor-core path reads the packed layout
+        if (path != QGEMM_PATH_AUTO && path != QGEMM_PATH_TCGEN05) return QGEMM_E_BADARG;
+        path = QGEMM_PATH_TCGEN05;
+    }
     if (path == QGEMM_PATH_AUTO) {
         if (T >= kMmqMinTokens && mmq_supported(wtype, act, wgt, T, F, K) && ws && ws_bytes >= mmq_workspace_bytes(wtype, T, F, K))
             path = QGEMM_PATH_TCGEN05;
@@ -230,7 +236,8 @@ size_t qgemm_workspace_bytes(int wtype, int T, int F, int K, uint32_t flags) {
     // [ q8_1 copy of A for qgemm_gemm_f32act | tensor-core path scratch (only where that path can run) ]
     const size_t a_q = align_up((size_t)T * (K / kQK) * kQ81Bytes, 256);
     const uint32_t path = flags & QGEMM_PATH_MASK;
-    const bool mmq = (path == QGEMM_PATH_TCGEN05 || (path == QGEMM_PATH_AUTO && T >= kMmqMinTokens)) &&
+    const bool mmq = (path == QGEMM_PATH_TCGEN05 || (flags & QGEMM_WEIGHTS_PREPACKED) ||
+                      (path == QGEMM_PATH_AUTO && T >= kMmqMinTokens)) &&
                      !(flags & QGEMM_SEQUENTIAL);
     return a_q + (mmq ? align_up(mmq_workspace_bytes(wtype, T, F, K), 256) : 0);
 }
@@ -275,6 +282,20 @@ int qgemm_gemm_group(int wtype, const void* act_q8_1, int nmat, const void* cons
     t_pf_bytes = 0;
     t_last_path = QGEMM_PATH_GEMV;
     return e == cudaSuccess ? QGEMM_OK : cuda_fail(e, "gemm_group launch");
+}
+
+size_t qgemm_prepack_bytes(int wtype, int F, int K) {
+    if (!is_weight_type(wtype) || F <= 0 || K <= 0 || (K % kQK) != 0) return 0;
+    return mmq_prepack_bytes(wtype, F, K);
+}
+
+int qgemm_prepack_weights(int wtype, const void* weight, int F, int K, void* packed, void* stream) {
+    if (!is_weight_type(wtype) || F <= 0 || K <= 0 || (K % kQK) != 0 || !weight || !packed) return QGEMM_E_BADARG;
+    if (!aligned(weight, 2) || !aligned(packed, 256)) return QGEMM_E_ALIGN;
+    DeviceInfo dev;
+    if (int rc = device_check(&dev)) return rc;
+    cudaError_t e = launch_mmq_prepack(wtype, weight, packed, F, K, (cudaStream_t)stream);
+    return e == cudaSuccess ? QGEMM_OK : cuda_fail(e, "prepack launch");
 }
 
 int qgemm_hint_next_weights(const void* next_weights, size_t bytes) {

@@ -23,7 +23,7 @@ import torch
 
 from . import _lib
 from ._lib import (  # noqa: F401  (re-exported constants)
-    GEMM_INPUTS_READY, GEMM_MS_EXACT, GEMM_SEQUENTIAL, GEMM_WEIGHTS_STATIC, PATH_AUTO, PATH_GEMV, PATH_GENERIC, PATH_MMA, PATH_TCGEN05,
+    GEMM_INPUTS_READY, GEMM_MS_EXACT, GEMM_WEIGHTS_PREPACKED, GEMM_SEQUENTIAL, GEMM_WEIGHTS_STATIC, PATH_AUTO, PATH_GEMV, PATH_GENERIC, PATH_MMA, PATH_TCGEN05,
     Q81_CLAMP127, Q81_ROUND_AWAY, Q81_ROUND_EVEN, Q81_S_FROM_QSUM,
     TYPE_Q4_0, TYPE_Q4_1, TYPE_Q5_0, TYPE_Q5_1, TYPE_Q8_0, TYPE_Q8_1,
 )
@@ -132,6 +132,20 @@ def dequantize_q4_0(x_q: torch.Tensor, K: int) -> torch.Tensor:
     return dequantize(x_q, K, TYPE_Q4_0)
 
 
+def prepack_weights(weight_q: torch.Tensor, M: int, K: int, wtype: int) -> torch.Tensor:
+    """Static weights -> the prefill kernel's operand-tile layout, once.  Use the result as `weight_q` of
+    gemm(..., flags=GEMM_WEIGHTS_PREPACKED) for calls with >= 96 tokens; keep the native blocks for decode."""
+    weight_q = weight_q.contiguous()
+    L = _lib.lib()
+    n = L.qgemm_prepack_bytes(wtype, M, K)
+    _check(n > 0, "unsupported type / shape for prepack")
+    packed = torch.empty(n, dtype=torch.uint8, device=weight_q.device)
+    with torch.cuda.device(weight_q.device):
+        rc = L.qgemm_prepack_weights(wtype, weight_q.data_ptr(), M, K, packed.data_ptr(), _stream(weight_q))
+    _lib.raise_on_error(rc, "prepack_weights")
+    return packed
+
+
 def hint_next_weights(next_weight_q: torch.Tensor | None) -> None:
     """Decode hint: the next gemm() call also prefetches `next_weight_q` (the weights of the GEMV after
     it) into L2 while it runs.  No effect on results."""
@@ -154,8 +168,11 @@ def gemm(weight_q: torch.Tensor, activation_q: torch.Tensor, M: int, N: int, K: 
     _check(K % 32 == 0, f"K must be divisible by 32, got {K}")
     nb = K // 32
     bs = BLOCK_BYTES[wtype]
-    _check(weight_q.numel() == M * nb * bs,
-           f"Weight shape mismatch: expected {M * nb * bs} elements, got {weight_q.numel()}")
+    if flags & GEMM_WEIGHTS_PREPACKED:
+        _check(weight_q.numel() == _lib.lib().qgemm_prepack_bytes(wtype, M, K), "Prepacked weight size mismatch")
+    else:
+        _check(weight_q.numel() == M * nb * bs,
+               f"Weight shape mismatch: expected {M * nb * bs} elements, got {weight_q.numel()}")
     _check(activation_q.numel() == N * nb * 36,
            f"Activation shape mismatch: expected {N * nb * 36} elements, got {activation_q.numel()}")
     weight_q = weight_q.contiguous()
@@ -287,5 +304,5 @@ __all__ = [
     # supersets
     "quantize_q4_1", "quantize_q5_0", "quantize_q5_1", "quantize_q8_0", "dequantize",
     "gemm", "gemm_q4_1_q8_1", "gemm_q5_0_q8_1", "gemm_q5_1_q8_1", "gemm_q8_0_q8_1", "gemm_w4a8",
-    "gemm_group", "block_sumi", "launch_count", "reset_launch_count", "last_path", "hint_next_weights",
+    "gemm_group", "prepack_weights", "block_sumi", "launch_count", "reset_launch_count", "last_path", "hint_next_weights",
 ]

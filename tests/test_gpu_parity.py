@@ -466,3 +466,22 @@ def test_gemm_group_equals_separate_calls(qg, O, wt, T, K):
     outs = qg.gemm_group(dws, dev(aq2), Fs, 12, K, wt)
     for wq, o in zip(wqs, outs):
         check_c(host(o), O.gemm(wt, aq2, wq, layout="FT"), "group fallback")
+
+
+def test_prepacked_weights_give_identical_results(qg, O):
+    """qgemm_prepack_weights + QGEMM_WEIGHTS_PREPACKED: same bits as the per-call path, no weight prepass."""
+    T, F, K = 200, 300, 1056
+    x, w = datagen.model_like(T, F, K, seed=88)
+    aq = O.quantize_q8_1(x)
+    for wt in (qo.Q4_0, qo.Q5_1, qo.Q8_0):
+        wq = O.quantize_weight(wt, w)
+        dw, da = dev(wq), dev(aq)
+        packed = qg.prepack_weights(dw, F, K, wt)
+        ref = host(qg.gemm(dw, da, F, T, K, wt, flags=0x400))
+        qg.reset_launch_count()
+        got = host(qg.gemm(packed, da, F, T, K, wt, flags=qg.GEMM_WEIGHTS_PREPACKED))
+        assert qg.last_path() == 0x400 and qg.launch_count() == 2   # activation repack + the MMA kernel only
+        assert (bits(got) == bits(ref)).all()
+        check_c(got, O.gemm(wt, aq, wq, layout="FT"), "prepacked")
+    with pytest.raises(RuntimeError):
+        qg.gemm(packed, da, F, T, K, qo.Q8_0, flags=qg.GEMM_WEIGHTS_PREPACKED | 0x200)   # decode path cannot read it
