@@ -205,17 +205,211 @@ __global__ void __launch_bounds__(kMmaThreads, 2) gemv_mma_kernel(const GemvMmaP
 }
 
 // ---------------------------------------------------------------------------
+// Long rows (K > 8192): the same mapping with the activation fragments in shared memory and
+// the 16-row tile streamed in K-chunks, so neither registers nor one stage have to hold a row.
+//   smem: [barriers | partials | a_sc[nb][8] | frag[nb][32 lanes] (2 words) | stages of 16 x chunk]
+// ---------------------------------------------------------------------------
+constexpr int kBigChunk = 64;   // K-blocks per stage (multiple of 8: row segments stay 16-byte multiples)
+
+struct GemvMmaBigParams {
+    const uint8_t* act;
+    const uint8_t* wgt;
+    float* C;
+    int T, F, nb;
+    int64_t ldc_t, ldc_f;
+    int pitch;        // smem bytes per row segment (kBigChunk blocks + pad, pitch % 128 == 16)
+    int stages;
+    int pdl;
+    PeerOut peer;
+};
+
+template <int WT, bool kMsExact>
+__global__ void __launch_bounds__(kMmaThreads, 1) gemv_mma_bigk_kernel(const GemvMmaBigParams p) {
+    using Fm = Fmt<WT>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tig = lane & 3;
+    const int nb = p.nb;
+
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + kMmaStagesMax;
+    float* red = reinterpret_cast<float*>(smem + 128);                                   // [kMmaWarps][128]
+    float2* a_sc = reinterpret_cast<float2*>(smem + 128 + kMmaWarps * 128 * 4);          // [nb][8]
+    uint2* frag = reinterpret_cast<uint2*>(smem + 128 + kMmaWarps * 128 * 4 + (size_t)nb * 64);  // [nb][32]
+    const uint32_t stage_bytes = (uint32_t)kMmaRows * p.pitch;
+    uint8_t* stage0 = smem + ((128u + kMmaWarps * 128u * 4u + (uint32_t)nb * 320u + 127u) & ~127u);
+
+    const int ntiles_total = (p.F + kMmaRows - 1) / kMmaRows;
+    const int t_begin = (int)(((int64_t)ntiles_total * blockIdx.x) / gridDim.x);
+    const int t_end = (int)(((int64_t)ntiles_total * (blockIdx.x + 1)) / gridDim.x);
+    const size_t rowbytes = (size_t)nb * Fm::bytes;
+    const int nchunks = (nb + kBigChunk - 1) / kBigChunk;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.stages; s++) {
+            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&empty[s], kMmaWarps);
+        }
+        ptx::fence_mbar_init();
+    }
+    __syncthreads();
+    if (p.pdl) ptx::griddep_launch_dependents();
+
+    if (warp == kMmaWarps) {
+        int s = 0;
+        uint32_t ph = 0;
+        for (int t = t_begin; t < t_end; t++) {
+            for (int c = 0; c < nchunks; c++) {
+                const int cb = min(kBigChunk, nb - c * kBigChunk);
+                const uint32_t seg = (uint32_t)cb * Fm::bytes;
+                ptx::mbar_wait(&empty[s], ph ^ 1);
+                if (lane == 0) ptx::mbar_arrive_expect_tx(&full[s], seg * kMmaRows);
+                __syncwarp();
+                if (lane < kMmaRows) {
+                    const int f = min(t * kMmaRows + lane, p.F - 1);
+                    ptx::bulk_g2s(stage0 + (size_t)s * stage_bytes + (size_t)lane * p.pitch,
+                                  p.wgt + (size_t)f * rowbytes + (size_t)c * kBigChunk * Fm::bytes, seg, &full[s]);
+                }
+                if (++s == p.stages) { s = 0; ph ^= 1; }
+            }
+        }
+        return;
+    }
+
+    if (p.pdl == 1) ptx::griddep_wait();
+    if (p.peer.world > 1) {
+        if (tid == 0) peer_wait_prior(p.peer);
+        ptx::bar_sync(1, kMmaWarps * 32);
+    }
+    for (int b = warp; b < nb; b += kMmaWarps) {   // fragments of token g: elements 4*tig.. and 16+4*tig..
+        uint2 v = make_uint2(0u, 0u);
+        if (g < p.T) {
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(p.act + ((size_t)g * nb + b) * kQ81Bytes);
+            v.x = __ldg(q + 1 + tig);
+            v.y = __ldg(q + 5 + tig);
+        }
+        frag[b * 32 + lane] = v;
+    }
+    for (int i = tid; i < nb * 8; i += kMmaWarps * 32) {
+        const int b = i >> 3, t = i & 7;
+        ActScale sc{0.f, 0.f};
+        if (t < p.T) {
+            const uint32_t ds = __ldg(reinterpret_cast<const uint32_t*>(p.act + ((size_t)t * nb + b) * kQ81Bytes));
+            sc = prep_act_scale<WT, kMsExact>(half_bits_to_float(ds), half_bits_to_float(ds >> 16));
+        }
+        a_sc[i] = make_float2(sc.d, sc.s);
+    }
+    ptx::bar_sync(1, kMmaWarps * 32);
+
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = t_begin; t < t_end; t++) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c = 0; c < nchunks; c++) {
+            const int cb = min(kBigChunk, nb - c * kBigChunk);
+            ptx::mbar_wait(&full[s], ph);
+            const uint8_t* r0 = stage0 + (size_t)s * stage_bytes + (size_t)g * p.pitch;
+            const uint8_t* r1 = r0 + (size_t)8 * p.pitch;
+#pragma unroll 2
+            for (int i = warp; i < cb; i += kMmaWarps) {
+                const int b = c * kBigChunk + i;
+                uint32_t a[4];
+                WScale w0, w1;
+                row_frag<WT>(r0 + (size_t)i * Fm::bytes, tig, a[0], a[2], w0);
+                row_frag<WT>(r1 + (size_t)i * Fm::bytes, tig, a[1], a[3], w1);
+                const uint2 bfr = frag[b * 32 + lane];
+                int cc[4] = {0, 0, 0, 0};
+                if constexpr (Fm::bits == 8) mma_s8s8(cc, a, bfr.x, bfr.y);
+                else mma_u8s8(cc, a, bfr.x, bfr.y);
+                const float4 sc = *reinterpret_cast<const float4*>(&a_sc[b * 8 + 2 * tig]);
+                acc[0] = fold_block_pre<WT>(acc[0], cc[0], w0, ActScale{sc.x, sc.y});
+                acc[1] = fold_block_pre<WT>(acc[1], cc[1], w0, ActScale{sc.z, sc.w});
+                acc[2] = fold_block_pre<WT>(acc[2], cc[2], w1, ActScale{sc.x, sc.y});
+                acc[3] = fold_block_pre<WT>(acc[3], cc[3], w1, ActScale{sc.z, sc.w});
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&empty[s]);
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+        red[warp * 128 + g * 8 + 2 * tig] = acc[0];
+        red[warp * 128 + g * 8 + 2 * tig + 1] = acc[1];
+        red[warp * 128 + (g + 8) * 8 + 2 * tig] = acc[2];
+        red[warp * 128 + (g + 8) * 8 + 2 * tig + 1] = acc[3];
+        ptx::bar_sync(1, kMmaWarps * 32);
+        if (tid < 128) {
+            const int r = tid >> 3, tok = tid & 7;
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < kMmaWarps; w++) v += red[w * 128 + tid];
+            const int f = t * kMmaRows + r;
+            if (f < p.F && tok < p.T) peer_store(p.peer, p.C, (int64_t)tok * p.ldc_t + (int64_t)f * p.ldc_f, v);
+        }
+        ptx::bar_sync(1, kMmaWarps * 32);
+    }
+    if (p.peer.world > 1) {
+        if (!(p.peer.dbg & 4)) __threadfence();
+        ptx::bar_sync(1, kMmaWarps * 32);
+        if (tid == 0) peer_signal_done(p.peer, gridDim.x);
+    }
+    if (p.pdl == 2) ptx::griddep_wait();
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
-bool gemv_mma_supported(int wtype, const void* act, const void* wgt, int T, int F, int K) {
-    const int nb = K / 32;
+static int bigk_pitch(int wtype) {
+    const int seg = kBigChunk * block_bytes(wtype);
+    return seg + 16 + ((128 - (seg % 128)) % 128);
+}
+static size_t bigk_fixed(int nb) { return 128 + kMmaWarps * 128 * 4 + (size_t)nb * 320 + 128; }
+static bool bigk_supported(int wtype, int nb) {
+    return (nb % 8) == 0 && bigk_fixed(nb) + 2 * (size_t)kMmaRows * bigk_pitch(wtype) <= (size_t)kMmaSmemMax + 20 * 1024;
+}
+static bool regs_variant_supported(int wtype, int nb) {
     const size_t rowbytes = (size_t)nb * block_bytes(wtype);
-    if (T < 1 || F < 1 || nb < 8 || nb > kMmaWarps * 32) return false;     // <= 32 blocks per warp in registers
-    if (rowbytes % 16 != 0) return false;
-    if (reinterpret_cast<uintptr_t>(wgt) % 16 != 0 || reinterpret_cast<uintptr_t>(act) % 4 != 0) return false;
+    if (nb < 8 || nb > kMmaWarps * 32) return false;
     const size_t pitch = rowbytes + 16 + ((128 - (rowbytes % 128)) % 128);
     const size_t fixed = 128 + kMmaWarps * 128 * 4 + (size_t)nb * 64 + 128;
     return fixed + 2 * kMmaRows * pitch <= (size_t)kMmaSmemMax;
+}
+bool gemv_mma_supported(int wtype, const void* act, const void* wgt, int T, int F, int K) {
+    const int nb = K / 32;
+    const size_t rowbytes = (size_t)nb * block_bytes(wtype);
+    if (T < 1 || F < 1 || nb < 8) return false;
+    if (rowbytes % 16 != 0) return false;
+    if (reinterpret_cast<uintptr_t>(wgt) % 16 != 0 || reinterpret_cast<uintptr_t>(act) % 4 != 0) return false;
+    return regs_variant_supported(wtype, nb) || bigk_supported(wtype, nb);
+}
+
+template <int WT>
+static cudaError_t launch_bigk(const GemvMmaBigParams& p, size_t smem, int grid, bool ms_exact, cudaStream_t st) {
+    auto launch = [&](auto kernel, int variant) -> cudaError_t {
+        static size_t attr_set[2] = {0, 0};
+        if (smem > attr_set[variant]) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            attr_set[variant] = smem;
+        }
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kMmaThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = p.pdl ? 1 : 0;
+        return cudaLaunchKernelEx(&cfg, kernel, p);
+    };
+    cudaError_t e;
+    if constexpr (Fmt<WT>::m >= 0) {
+        e = ms_exact ? launch(gemv_mma_bigk_kernel<WT, true>, 1) : launch(gemv_mma_bigk_kernel<WT, false>, 0);
+    } else {
+        e = launch(gemv_mma_bigk_kernel<WT, false>, 0);
+    }
+    note_launch();
+    return e;
 }
 
 template <int WT, int NBW>
@@ -261,6 +455,38 @@ static cudaError_t launch_mma_wt(const GemvMmaParams& p, size_t smem, int grid, 
 cudaError_t launch_gemv_mma(int wtype, const void* act, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
                             int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t st, const PeerOut* peer) {
     if (peer && T > 8) return cudaErrorInvalidValue;  // peer mode: one pass per launch
+    if (!regs_variant_supported(wtype, K / 32)) {      // long rows: fragments in smem, K-chunked stages
+        const int nbk = K / 32;
+        const int bp = bigk_pitch(wtype);
+        const size_t fx = bigk_fixed(nbk);
+        int stg = (int)(((size_t)kMmaSmemMax + 20 * 1024 - fx) / ((size_t)kMmaRows * bp));
+        stg = max(2, min(kMmaStagesMax, stg));
+        const int nt = (F + kMmaRows - 1) / kMmaRows;
+        const int grd = min(nt, num_sms);
+        const size_t sm = fx + (size_t)stg * kMmaRows * bp;
+        for (int t0 = 0; t0 < T; t0 += 8) {
+            GemvMmaBigParams p;
+            p.act = (const uint8_t*)act + (size_t)t0 * nbk * kQ81Bytes;
+            p.wgt = (const uint8_t*)wgt;
+            p.C = C + (int64_t)t0 * ldc_t;
+            p.T = min(8, T - t0); p.F = F; p.nb = nbk; p.ldc_t = ldc_t; p.ldc_f = ldc_f;
+            p.pitch = bp; p.stages = stg;
+            p.pdl = (flags & QGEMM_WEIGHTS_STATIC) ? ((flags & QGEMM_INPUTS_READY) ? 2 : 1) : 0;
+            p.peer = peer ? *peer : PeerOut{};
+            const bool ms = flags & QGEMM_MS_EXACT;
+            cudaError_t e;
+            switch (wtype) {
+            case QGEMM_TYPE_Q4_0: e = launch_bigk<QGEMM_TYPE_Q4_0>(p, sm, grd, ms, st); break;
+            case QGEMM_TYPE_Q4_1: e = launch_bigk<QGEMM_TYPE_Q4_1>(p, sm, grd, ms, st); break;
+            case QGEMM_TYPE_Q5_0: e = launch_bigk<QGEMM_TYPE_Q5_0>(p, sm, grd, ms, st); break;
+            case QGEMM_TYPE_Q5_1: e = launch_bigk<QGEMM_TYPE_Q5_1>(p, sm, grd, ms, st); break;
+            case QGEMM_TYPE_Q8_0: e = launch_bigk<QGEMM_TYPE_Q8_0>(p, sm, grd, ms, st); break;
+            default: e = cudaErrorInvalidValue;
+            }
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
     const int nb = K / 32;
     const size_t rowbytes = (size_t)nb * block_bytes(wtype);
     const int pitch = (int)(rowbytes + 16 + ((128 - (rowbytes % 128)) % 128));

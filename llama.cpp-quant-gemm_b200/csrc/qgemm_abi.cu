@@ -136,7 +136,7 @@ static int run_gemm(int wtype, const void* act, const void* wgt, float* C, int T
     if (path == QGEMM_PATH_AUTO) {
         if (T >= kMmqMinTokens && mmq_supported(wtype, act, wgt, T, F, K) && ws && ws_bytes >= mmq_workspace_bytes(wtype, T, F, K))
             path = QGEMM_PATH_TCGEN05;
-        else if (T >= kMmaMinTokens && gemv_mma_supported(wtype, act, wgt, T, F, K))
+        else if (T >= (K > 8192 ? kMmaMinTokens + 1 : kMmaMinTokens) && gemv_mma_supported(wtype, act, wgt, T, F, K))
             path = QGEMM_PATH_MMA;
         else if (gemv_supported(wtype, act, wgt, F, K))
             path = QGEMM_PATH_GEMV;

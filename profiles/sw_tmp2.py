@@ -1,5 +1,5 @@
 import sys
 sys.path.insert(0,'profiles')
 import sweep_gemv as s
-for shape in [(2, 1, 4096, 11008, 0x10), (8, 1, 4096, 11008, 0x10), (2, 1, 4096, 14336, 0x10), (2, 1, 8192, 8192, 0x10)]:
+for shape in [(2, 4, 4096, 11008, 0x10), (2, 8, 4096, 11008, 0x10), (8, 8, 4096, 11008, 0x10), (7, 8, 4096, 14336, 0x10), (2, 2, 4096, 11008, 0x10)]:
     s.run(shape, {})

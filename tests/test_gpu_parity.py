@@ -374,7 +374,8 @@ def test_mmq_full_size_prefill_properties(qg, O):
 # skinny path: mma.sync m16n8k32 with tokens on N (QGEMM_PATH_MMA), 3 <= T < 64
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("wt", qo.WEIGHT_TYPES)
-@pytest.mark.parametrize("T,F,K", [(3, 256, 4096), (8, 130, 2048), (5, 33, 256), (8, 512, 8192), (20, 96, 1024), (1, 64, 512)])
+@pytest.mark.parametrize("T,F,K", [(3, 256, 4096), (8, 130, 2048), (5, 33, 256), (8, 512, 8192), (20, 96, 1024), (1, 64, 512),
+                                   (4, 100, 11008), (8, 48, 14336)])
 def test_mma_skinny_vs_oracle(qg, O, wt, T, F, K):
     x, w = datagen.model_like(T, F, K, seed=T * 3 + F)
     aq, wq = O.quantize_q8_1(x), O.quantize_weight(wt, w)
