@@ -46,7 +46,7 @@ inline int gemm_w4a8_from_ggml(const Tensor* activation, const Tensor* weights, 
     if (!validate_tensor_types(activation, weights, output, QGEMM_TYPE_Q8_1, (int)weights->type, /*F32*/ 0)) return QGEMM_E_BADARG;
     int M, N, K;
     extract_dims_from_tensor(activation, weights, &M, &N, &K);
-    return qgemm_gemm((int)weights->type, activation->data, weights->data, (float*)output->data, M, N, K, N, 1, 0u,
+    return qgemm_gemm((int)weights->type, activation->data, weights->data, (float*)output->data, M, N, K, N, 1, QGEMM_STREAM_ALLOC,
                       nullptr, 0, (void*)stream);
 }
 

@@ -79,6 +79,11 @@ extern "C" {
                                    without waiting for its predecessor and only waits before it exits, so
                                    stream-order completion is preserved for everything launched after it */
 #define QGEMM_WEIGHTS_PREPACKED 0x40u /* `weight` is a qgemm_prepack_weights() buffer (tensor-core path only) */
+#define QGEMM_STREAM_ALLOC 0x80u /* workspace == NULL and none registered: the library may take the scratch of the
+                                   tensor-core path from the stream's memory pool (cudaMallocAsync /
+                                   cudaFreeAsync around the launch: stream-ordered, graph-capturable, nothing
+                                   persists).  The drop-in C++ headers pass it, because the reference's launcher
+                                   signatures have no workspace argument.                                     */
 #define QGEMM_PATH_MASK 0xF00u
 #define QGEMM_PATH_AUTO 0x000u
 #define QGEMM_PATH_GENERIC 0x100u /* same kernel as QGEMM_SEQUENTIAL                         */

@@ -2,10 +2,10 @@
  * include/qgemm_dropin.h -- glue shared by the drop-in C++ headers: forwards the reference's
  * inline launchers (void, device pointers, cudaStream_t = 0, errors left sticky) to the C ABI.
  *
- * The reference's launchers take no workspace.  The tensor-core path needs one, so a caller who
- * wants it for M >= 64 registers device scratch once per device with
- * qgemm_set_default_workspace(); without it the calls still work and run the weight-streaming
- * path at every M.
+ * The reference's launchers take no workspace.  The tensor-core path needs one, so these shims
+ * pass QGEMM_STREAM_ALLOC: for M >= 96 the library borrows the scratch from the stream's memory
+ * pool for the duration of the call (cudaMallocAsync / cudaFreeAsync, stream-ordered).  A caller
+ * who prefers to own it registers scratch once per device with qgemm_set_default_workspace().
  */
 #ifndef QGEMM_DROPIN_H
 #define QGEMM_DROPIN_H
@@ -17,12 +17,12 @@
 /* include/ convention: A = q8_1 activations [M rows], B = weights [N rows], C[M, N] row-major */
 static inline void qgemm_dropin_include(int wtype, const void* A, const void* B, float* C, int M, int N, int K,
                                         cudaStream_t stream) {
-    (void)qgemm_gemm(wtype, A, B, C, M, N, K, (int64_t)N, 1, 0u, nullptr, 0, (void*)stream);
+    (void)qgemm_gemm(wtype, A, B, C, M, N, K, (int64_t)N, 1, QGEMM_STREAM_ALLOC, nullptr, 0, (void*)stream);
 }
 /* kernels/gemm convention: weight [M rows], activation [N tokens], output[m * N + n] */
 static inline void qgemm_dropin_ggml(int wtype, const void* weight, const void* activation, float* output, int M, int N,
                                      int K, cudaStream_t stream) {
-    (void)qgemm_gemm(wtype, activation, weight, output, N, M, K, 1, (int64_t)N, 0u, nullptr, 0, (void*)stream);
+    (void)qgemm_gemm(wtype, activation, weight, output, N, M, K, 1, (int64_t)N, QGEMM_STREAM_ALLOC, nullptr, 0, (void*)stream);
 }
 
 #endif /* QGEMM_DROPIN_H */

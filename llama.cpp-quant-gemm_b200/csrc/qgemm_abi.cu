@@ -129,6 +129,23 @@ static int run_gemm(int wtype, const void* act, const void* wgt, float* C, int T
     }
     uint32_t path = flags & QGEMM_PATH_MASK;
     if (flags & QGEMM_SEQUENTIAL) path = QGEMM_PATH_GENERIC;
+    // no scratch from the caller: borrow it from the stream's pool for the duration of this call
+    void* pool_ws = nullptr;
+    if (!ws && (flags & QGEMM_STREAM_ALLOC) && (path == QGEMM_PATH_TCGEN05 || (path == QGEMM_PATH_AUTO && T >= kMmqMinTokens)) &&
+        mmq_supported(wtype, act, wgt, T, F, K)) {
+        const size_t need = align_up(mmq_workspace_bytes(wtype, T, F, K), 256);
+        if (cudaMallocAsync(&pool_ws, need, st) == cudaSuccess) {
+            ws = pool_ws;
+            ws_bytes = need;
+        } else {
+            (void)cudaGetLastError();  // no pool on this device/driver: the other paths need no scratch
+            pool_ws = nullptr;
+        }
+    }
+    struct PoolFree {
+        void* p; cudaStream_t s;
+        ~PoolFree() { if (p) cudaFreeAsync(p, s); }
+    } pool_free{pool_ws, st};
     if (flags & QGEMM_WEIGHTS_PREPACKED) {  // only the tensor-core path reads the packed layout
         if (path != QGEMM_PATH_AUTO && path != QGEMM_PATH_TCGEN05) return QGEMM_E_BADARG;
         path = QGEMM_PATH_TCGEN05;

@@ -79,7 +79,9 @@ int main(int argc, char** argv) {
     if (gemm_w4a8_from_ggml(&ta, &tw, &to, "dp4a", st) != 0) return 4;
     fetch("c_adapter.f32");
 
-    // registered scratch lets the signature-compatible launchers reach the tensor-core path
+    // the unchanged launcher reaches the tensor-core path on its own (scratch from the stream's pool) ...
+    printf("launcher path 0x%x\n", qgemm_last_path());
+    // ... or with scratch the caller registered
     size_t wsb = qgemm_workspace_bytes(QGEMM_TYPE_Q4_0, T, F, K, QGEMM_PATH_TCGEN05);
     void* ws; CUDA_CHECK(cudaMalloc(&ws, wsb));
     if (qgemm_set_default_workspace(ws, wsb) != 0) return 5;

@@ -69,7 +69,8 @@ def test_dropin_program_matches_oracle(tmp_path):
     (tmp_path / "dims.txt").write_text(f"{T} {F} {K}\n")
     out = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
     assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
-    assert "last path 0x400" in out.stdout   # registered scratch -> tensor-core path through the plain launcher
+    assert "launcher path 0x400" in out.stdout  # T = 96: the plain launcher took the tcgen05 path (pool scratch)
+    assert "last path 0x400" in out.stdout      # and again with scratch registered by the caller
     aq = np.fromfile(tmp_path / "a_q8_1.bin", dtype=np.uint8).reshape(T, K // 32, 36)
     assert (aq == O.quantize_q8_1(x, qo.Q81_ROUND_EVEN)).all()       # include/quantize.h GPU semantics
     ref = {n: O.gemm(t, aq, wq[n], layout="FT") for n, t in (("q4_0", qo.Q4_0), ("q5_1", qo.Q5_1), ("q8_0", qo.Q8_0))}
