@@ -11,8 +11,12 @@ every launch streams from HBM), replayed as one CUDA graph.
             (weights once + q8_1 activations + fp32 outputs)
   e2e     = the same step through the public python API (quant_gemm) with HOST buffers: pinned
             fp32 activations H2D, quantize_q8_1, 224 GEMVs, all outputs D2H -- inside the timed region
-  N > 1   : weak scaling -- every rank owns the rows of its shard of an N-times wider model
-            (same per-GPU bytes) and the per-GEMV outputs are all-gathered over NCCL/NVLink.
+  N > 1   : weak scaling.  Decode shapes do not shard usefully ("replicas only"), so by
+            default every rank decodes its own copy of the stack with no data-path collective.
+            --gather fused|nccl runs the tensor-parallel variant instead (every rank owns the rows of
+            its shard of an N-times wider model, per-GEMV all-gather fused into the kernel or by NCCL).
+            The shape that does shard, BASELINE configs[4] (M=4096 N=28672 K=8192 Q4_0, weight rows
+            split over the ranks, all-gather of C), is timed as `extra.sharded_c5` at every N.
   --impl reference : the reference's own CPU implementation (oracle/_ref, all host threads) on
             a bounded sample (one layer = 7 GEMVs per step) of the same workload.
 
@@ -29,6 +33,7 @@ import sys
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+_JSON_OUT = sys.stdout
 for _p in (os.path.join(ROOT, "llama.cpp-quant-gemm_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
@@ -183,15 +188,77 @@ def run_reference_arm(args):
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
-def workload_config(n_gpus):
+def sharded_c5(torch, dist, quant_gemm, dev, world, rank, ctl, reps=3):
+    """BASELINE configs[4]: Q4_0 M=4096 N=28672 K=8192, weight rows sharded over the ranks (strong scaling).
+    Times (i) the local GEMM alone, (ii) GEMM + in-place NCCL all-gather, (iii) the GEMM whose tcgen05
+    epilogue stores its tiles into every rank's gathered C over NVLink; device events, max over ranks."""
+    from quant_gemm import sharded
+    import bench_detail
+    T, F, K = 4096, 28672, 8192
+    f0, f1 = sharded.shard_rows(F, world, rank)
+    w = bench_detail.make_weights(torch, WTYPE, f1 - f0, K, 1, dev, seed=99 + rank)[0]
+    x = torch.randn((T, K), device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+    aq = quant_gemm.quantize_q8_1(x)
+    del x
+    out_full = torch.empty((F, T), device=dev)
+    ops = 2.0 * T * F * K
+
+    def timed(fn):
+        best = 1e30
+        for i in range(reps + 1):
+            if world > 1:
+                dist.barrier(group=ctl)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([ms])
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=ctl)
+                ms = float(t.item())
+            if i > 0:
+                best = min(best, ms)
+        return best
+
+    res = {"shape": "Q4_0 M=4096 N=28672 K=8192", "rows_per_rank": f1 - f0, "scaling": "strong",
+           "note": "whole calls incl. operand prepass; best of %d; max over ranks" % reps}
+    local = out_full[f0:f1]
+    ms = timed(lambda: quant_gemm.gemm(w, aq, f1 - f0, T, K, WTYPE, GEMV_FLAGS, out=local))
+    res["compute_only"] = {"ms": ms, "tops": ops / ms / 1e9}
+    if world > 1:
+        op_n = sharded.ShardedGemm(w, F, K, WTYPE, flags=GEMV_FLAGS)
+        ms = timed(lambda: op_n(aq, out=out_full))
+        res["nccl_all_gather"] = {"ms": ms, "tops": ops / ms / 1e9}
+        plan = sharded.PeerPlan(F * T, 1, dev, ctl_group=ctl)
+        op_p = sharded.ShardedGemmP2P(w, F, K, WTYPE, T, plan, flags=GEMV_FLAGS)
+
+        def fused():
+            op_p(aq)
+            plan.end_step()
+        ms = timed(fused)
+        res["fused_peer_stores"] = {"ms": ms, "tops": ops / ms / 1e9}
+        res["fused_equals_nccl_bitwise"] = bool(torch.equal(op_p.out, out_full))
+    return res
+
+
+def workload_config(n_gpus, tp=1):
+    if n_gpus == 1:
+        par = "1 GPU"
+    elif tp == 1:
+        par = f"{n_gpus} independent replicas, no data-path collective (SURVEY 8e: decode shapes do not shard)"
+    else:
+        par = f"weight rows (N) sharded x{n_gpus}, all-gather of C per GEMV"
     return {"workload": "Llama-7B decode GEMV stack: M=1, 32 layers x {4x 4096x4096, 2x 11008x4096, 1x 4096x11008}, "
                         "Q4_0 weights x Q8_1 activations (BASELINE configs[1])",
             "gemvs_per_step": 224, "weight_bytes_per_gpu": 32 * sum(F * (K // 32) * 18 for _, F, K in LLAMA7B),
             "l2_defeat": "inputs larger than L2: 3.64 GB of distinct weights per step vs 126 MB L2",
-            "parallelism": f"weight rows (N) sharded x{n_gpus}, all-gather of C fused into the GEMV kernel (NVLink peer stores)" if n_gpus > 1 else "1 GPU",
+            "parallelism": par,
             "timing": "CUDA events on the launch stream around K graph replays, max over ranks"}
 
 
@@ -208,11 +275,19 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--group", type=int, default=1, help="1 GPU: fuse q/k/v and gate/up into grouped launches")
     ap.add_argument("--prefetch", type=int, default=1, help="1: hint each GEMV with the next one's weights (L2 prefetch)")
-    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"],
-                    help="N > 1: all-gather fused into the kernel (peer stores over NVLink) or NCCL per GEMV")
+    ap.add_argument("--gather", default="none", choices=["none", "fused", "nccl"],
+                    help="N > 1: none = independent replicas (default); tensor-parallel decode with the all-gather "
+                         "fused into the kernel (peer stores over NVLink) or by NCCL per GEMV")
+    ap.add_argument("--sharded-extra", type=int, default=1, help="time BASELINE configs[4] sharded over the ranks")
     ap.add_argument("--detail", default=None, help="write a per-shape sweep (all formats, M=1..8, prefill) to this JSON file")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly one JSON line: native libraries that print there (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    global _JSON_OUT
+    _JSON_OUT = os.fdopen(json_fd, "w")
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -236,6 +311,7 @@ def main():
         # that is also replayed from CUDA graphs hung on this stack
         ctl = dist.new_group(backend="gloo")
     quant_gemm._lib.lib()
+    tp = world if args.gather != "none" else 1   # ranks one GEMV is sharded over
 
     # ---- synthetic weight pool: raw-block fuzz (all nibble values), sane fp16 scales
     g = torch.Generator(device=dev)
@@ -253,22 +329,22 @@ def main():
     acts_q = {K: quant_gemm.quantize_q8_1(v) for K, v in acts_dev.items()}
     # gathered C of every GEMV, [F_total, T=1] each, carved out of one buffer so the step's result
     # goes back to the host in one copy
-    total_out = sum(F * world for F, K, _ in mats)
+    total_out = sum(F * tp for F, K, _ in mats)
     out_all = torch.empty(total_out, device=dev)
     outs, off = [], 0
     for F, K, _ in mats:
-        outs.append(out_all[off:off + F * world].view(F * world, 1))
-        off += F * world
+        outs.append(out_all[off:off + F * tp].view(F * tp, 1))
+        off += F * tp
     out_host = torch.empty(total_out + 64 * len(mats), dtype=torch.float32).pin_memory()  # + pool alignment padding
     step_bytes = sum(algorithmic_bytes(WTYPE, 1, F, K) for F, K, _ in mats)
 
     from quant_gemm import sharded
     # every rank owns rows [rank*F, (rank+1)*F) of an (N*F)-row matrix
     plan = None
-    if world > 1 and args.gather == "fused":
+    if tp > 1 and args.gather == "fused":
         # all-gather fused into the GEMV: the kernel stores its slice of C into every rank's gathered
         # buffer over NVLink (symmetric memory) and signals with device-side counters
-        plan = sharded.PeerPlan(sum(F * world for F, K, _ in mats), len(mats), dev, ctl_group=ctl)
+        plan = sharded.PeerPlan(sum(F * tp for F, K, _ in mats), len(mats), dev, ctl_group=ctl)
         if args.group:
             # 4 launches per layer: [wq wk wv] fused, wo, [gate up] fused, down -- each waits for its predecessor
             plan.lps = 4 * args.layers
@@ -278,10 +354,10 @@ def main():
                 for g in ([b, b + 1, b + 2], [b + 3], [b + 4, b + 5], [b + 6]):
                     K = mats[g[0]][1]
                     if len(g) == 1:
-                        op = sharded.ShardedGemvP2P(mats[g[0]][2], mats[g[0]][0] * world, K, WTYPE, 1, plan, flags=GEMV_FLAGS)
+                        op = sharded.ShardedGemvP2P(mats[g[0]][2], mats[g[0]][0] * tp, K, WTYPE, 1, plan, flags=GEMV_FLAGS)
                         outs.append(op.out)
                     else:
-                        op = sharded.ShardedGemvGroupP2P([mats[i][2] for i in g], [mats[i][0] * world for i in g], K, WTYPE,
+                        op = sharded.ShardedGemvGroupP2P([mats[i][2] for i in g], [mats[i][0] * tp for i in g], K, WTYPE,
                                                          1, plan, flags=GEMV_FLAGS)
                         outs += op.outs
                     ops.append((op, K, g))
@@ -291,19 +367,19 @@ def main():
             for i, (F, K, w) in enumerate(mats):
                 j = i % 7
                 wait = i - j if j < 3 else (i if j in (3, 4, 6) else i - 1)
-                ops.append(sharded.ShardedGemvP2P(w, F * world, K, WTYPE, 1, plan, wait_index=wait,
+                ops.append(sharded.ShardedGemvP2P(w, F * tp, K, WTYPE, 1, plan, wait_index=wait,
                                                   flags=READY_FLAGS if j in (1, 2, 5) else GEMV_FLAGS))
             outs = [op.out for op in ops]
-    else:  # baseline: in-place NCCL all-gather after every GEMV
+    elif tp > 1:  # baseline: in-place NCCL all-gather after every GEMV
         # Llama dataflow: wk, wv read the same (already complete) input as wq, `up` the same as `gate`
-        ops = [sharded.ShardedGemm(w, F * world, K, WTYPE, flags=READY_FLAGS if (i % 7) in (1, 2, 5) else GEMV_FLAGS)
+        ops = [sharded.ShardedGemm(w, F * tp, K, WTYPE, flags=READY_FLAGS if (i % 7) in (1, 2, 5) else GEMV_FLAGS)
                for i, (F, K, w) in enumerate(mats)]
 
     # launch plan of one step.  Single GPU: the projections that share an input go out as ONE grouped
     # launch (fused q/k/v and gate/up, qgemm_gemm_group) -- 4 launches per layer instead of 7, the
     # same weights and the same 224 outputs.
     groups = []
-    if world == 1 and args.group:
+    if tp == 1 and args.group:
         for l in range(args.layers):
             b = 7 * l
             groups += [[b, b + 1, b + 2], [b + 3], [b + 4, b + 5], [b + 6]]
@@ -330,13 +406,15 @@ def main():
             return
         # a decode runtime knows its layer order: each launch pulls the next GEMV's weights into L2
         n = len(mats)
-        for i, (op, (F, K, w)) in enumerate(zip(ops, mats)):
+        for i, (F, K, w) in enumerate(mats):
             if args.prefetch:
                 quant_gemm.hint_next_weights(mats[(i + 1) % n][2])
             if plan is not None:
-                op(acts_q[K])
+                ops[i](acts_q[K])
+            elif tp > 1:
+                ops[i](acts_q[K], out=outs[i])
             else:
-                op(acts_q[K], out=outs[i])
+                quant_gemm.gemm(w, acts_q[K], F, 1, K, WTYPE, READY_FLAGS if (i % 7) in (1, 2, 5) else GEMV_FLAGS, out=outs[i])
         if plan is not None:
             plan.end_step()
 
@@ -402,7 +480,7 @@ def main():
         F, K, w = mats[4]
         rows = np.r_[0:4, F - 4:F]
         ref = O.gemm(WTYPE, acts_q[K].cpu().numpy(), w[torch.from_numpy(rows).to(dev)].cpu().numpy(), layout="FT")
-        got = outs[4][rank * F:(rank + 1) * F].cpu().numpy()[rows]  # outs[] stays indexed by matrix in every mode
+        got = outs[4][(rank if tp > 1 else 0) * F:][:F].cpu().numpy()[rows]  # outs[] stays indexed by matrix in every mode
         check = qo.max_norm_err(got, ref)
         assert check <= 1e-5, f"timed path disagrees with the oracle: {check}"
 
@@ -416,7 +494,7 @@ def main():
     traffic, traffic_src = load_traffic()
 
     # prefill side of the metric ("Q4_0 x Q8_1 GEMM TOPS"): BASELINE configs[2], whole call, rank 0 only
-    extra = None
+    extra = {}
     if rank == 0 and world == 1:
         import bench_detail
         r = bench_detail.time_prefill(torch, quant_gemm, WTYPE, 512, 4096, 4096, reps=5)
@@ -428,7 +506,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u4 x s8 -> s32 (dp4a), fp32 fold", "data": "synthetic",
-        "config": workload_config(world),
+        "config": workload_config(world, tp),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT,
                 "h2d_bytes_per_step": sum(v.numel() * 4 for v in acts_host.values()),
@@ -444,6 +522,28 @@ def main():
         "oracle_check_max_norm_err": check,
         "extra": extra,
     }
+    def emit():
+        if rank == 0:
+            print(json.dumps(line), file=_JSON_OUT, flush=True)
+
+    # the shape that shards (configs[4]).  It comes after the headline measurement and under a watchdog: if a
+    # collective wedges, the headline line still goes out and every rank leaves.
+    if args.sharded_extra:
+        import threading
+
+        def bail():
+            extra["sharded_c5"] = {"error": "timed out after 240 s"}
+            emit()
+            sys.stdout.flush()
+            os._exit(0)
+        wd = threading.Timer(240.0, bail)
+        wd.daemon = True
+        wd.start()
+        try:
+            extra["sharded_c5"] = sharded_c5(torch, dist, quant_gemm, dev, world, rank, ctl)
+        except Exception as ex:  # noqa: BLE001 -- reported, the headline stands
+            extra["sharded_c5"] = {"error": repr(ex)[:300]}
+        wd.cancel()
     if world > 1:
         dist.barrier(group=ctl)
     if rank == 0:
@@ -453,7 +553,7 @@ def main():
         if args.detail:
             import bench_detail
             bench_detail.run(args.detail)
-        print(json.dumps(line), flush=True)
+    emit()
     if world > 1:
         dist.barrier(group=ctl)
         sys.stdout.flush()

@@ -140,6 +140,12 @@ def run(out_path, quick=False, flags=0x10):
                 r = time_shape(torch, quant_gemm, wt, T, F, K, flags)
                 rows.append(r)
                 print(json.dumps(r), flush=True)
+    if not quick:   # beyond BASELINE configs[1]: the skinny path up to the tcgen05 crossover, and a matrix large
+        for wt, T, F, K in [(2, 16, 11008, 4096), (2, 32, 11008, 4096), (2, 64, 11008, 4096), (2, 96, 11008, 4096),
+                            (2, 1, 32768, 4096), (8, 1, 32768, 4096), (2, 1, 28672, 8192)]:   # enough to hide the launch chain
+            r = time_shape(torch, quant_gemm, wt, T, F, K, flags)
+            rows.append(r)
+            print(json.dumps(r), flush=True)
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     with open(out_path, "w") as f:

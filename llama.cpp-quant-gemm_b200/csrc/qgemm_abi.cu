@@ -34,7 +34,7 @@ bool mmq_supported(int wtype, const void* act, const void* wgt, int T, int F, in
 size_t mmq_workspace_bytes(int wtype, int T, int F, int K);
 cudaError_t launch_mmq(int wtype, const void* act, const void* wgt, float* C, int32_t* sumi_out, int T, int F, int K,
                        int64_t ldc_t, int64_t ldc_f, uint32_t flags, void* ws, size_t ws_bytes, int num_sms,
-                       cudaStream_t);
+                       cudaStream_t, const PeerOut* peer = nullptr);
 
 constexpr int kMmaMinTokens = 2;   // dp4a GEMV for a single token, mma.sync skinny path from here (measured crossover)
 constexpr int kMmqMinTokens = 96;  // AUTO switches to the tcgen05 path here (below it the skinny passes are faster)
@@ -89,6 +89,34 @@ static bool is_weight_type(int t) {
 static bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// QGEMM_STREAM_ALLOC scratch comes from a pool of our own, one per device, that keeps its pages between
+// calls (release threshold = max).  The device's default pool trims at every synchronisation, which made
+// each call pay the physical allocation again (measured: +1.1 ms for a 270 MB scratch).
+static cudaMemPool_t g_scratch_pool[64];
+static cudaError_t scratch_alloc(void** ptr, size_t bytes, cudaStream_t st) {
+    int d = 0;
+    cudaError_t e = cudaGetDevice(&d);
+    if (e != cudaSuccess) return e;
+    if (d < 0 || d >= 64) return cudaErrorInvalidDevice;
+    {
+        std::lock_guard<std::mutex> lk(g_dev_mu);
+        if (!g_scratch_pool[d]) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = d;
+            cudaMemPool_t pool = nullptr;
+            e = cudaMemPoolCreate(&pool, &props);
+            if (e != cudaSuccess) return e;
+            uint64_t keep = ~0ull;
+            (void)cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            g_scratch_pool[d] = pool;
+        }
+    }
+    return cudaMallocFromPoolAsync(ptr, bytes, g_scratch_pool[d], st);
+}
+
 static int check_gemm_args(int wtype, const void* act, const void* wgt, const void* out, int T, int F, int K) {
     if (!is_weight_type(wtype) || T < 0 || F < 0 || K < 0 || (K % kQK) != 0) return QGEMM_E_BADARG;
     if (T == 0 || F == 0) return QGEMM_OK;
@@ -98,8 +126,10 @@ static int check_gemm_args(int wtype, const void* act, const void* wgt, const vo
 }
 
 __global__ void peer_step_advance_kernel(uint32_t* step) { *step = *step + 1u; }
-__global__ void peer_wait_kernel(const uint32_t* flag, const uint32_t* step, uint32_t lps, uint32_t world) {
-    const uint32_t target = (*step) * lps * world + lps * world;  // every launch of the current step, every rank
+// one thread: block the stream until `li` launches of the current step have landed here from every rank
+// (li = launches_per_step: the whole step)
+__global__ void peer_wait_kernel(const uint32_t* flag, const uint32_t* step, uint32_t lps, uint32_t li, uint32_t world) {
+    const uint32_t target = ((*step) * lps + li) * world;
     while ((int32_t)(ld_acquire_sys(flag) - target) < 0) __nanosleep(64);
 }
 
@@ -134,7 +164,7 @@ static int run_gemm(int wtype, const void* act, const void* wgt, float* C, int T
     if (!ws && (flags & QGEMM_STREAM_ALLOC) && (path == QGEMM_PATH_TCGEN05 || (path == QGEMM_PATH_AUTO && T >= kMmqMinTokens)) &&
         mmq_supported(wtype, act, wgt, T, F, K)) {
         const size_t need = align_up(mmq_workspace_bytes(wtype, T, F, K), 256);
-        if (cudaMallocAsync(&pool_ws, need, st) == cudaSuccess) {
+        if (scratch_alloc(&pool_ws, need, st) == cudaSuccess) {
             ws = pool_ws;
             ws_bytes = need;
         } else {
@@ -430,8 +460,38 @@ int qgemm_gemm_peers(int wtype, const void* act_q8_1, const void* weight, const 
         t_pf_ptr = nullptr;
         t_pf_bytes = 0;
         t_last_path = QGEMM_PATH_GEMV;
+    } else if (T > 8 && mmq_supported(wtype, act_q8_1, weight, T, F, K)) {
+        // prefill: peer stores from the tcgen05 epilogue.  Scratch = the registered default workspace, else
+        // (QGEMM_STREAM_ALLOC) the stream's pool; the operand prepass reads the activations, so the wait for
+        // earlier launches of the step runs as its own one-thread kernel in front of it.
+        const size_t need = mmq_workspace_bytes(wtype, T, F, K);
+        void* ws = nullptr;
+        size_t ws_bytes = 0;
+        int d = 0;
+        if (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < 64) {
+            std::lock_guard<std::mutex> lk(g_dev_mu);
+            ws = g_default_ws[d].ptr;
+            ws_bytes = g_default_ws[d].bytes;
+        }
+        void* pool_ws = nullptr;
+        if ((!ws || ws_bytes < need) && (flags & QGEMM_STREAM_ALLOC)) {
+            if (scratch_alloc(&pool_ws, align_up(need, 256), st) != cudaSuccess) {
+                (void)cudaGetLastError();
+                return QGEMM_E_WORKSPACE;
+            }
+            ws = pool_ws;
+            ws_bytes = align_up(need, 256);
+        }
+        if (!ws || ws_bytes < need) return QGEMM_E_WORKSPACE;
+        if (po.world > 1 && po.li > 0) {
+            peer_wait_kernel<<<1, 1, 0, st>>>(po.flag[po.rank], po.step, po.lps, po.li, (uint32_t)po.world);
+            note_launch();
+        }
+        e = launch_mmq(wtype, act_q8_1, weight, C, nullptr, T, F, K, ldc_t, ldc_f, flags, ws, ws_bytes, dev.sms, st, &po);
+        if (pool_ws) cudaFreeAsync(pool_ws, st);
+        t_last_path = QGEMM_PATH_TCGEN05;
     } else {
-        return QGEMM_E_ALIGN;  // peer stores are fused into the decode kernels only (T <= 8, bulk-copyable rows)
+        return QGEMM_E_ALIGN;  // peer stores exist in the decode kernels (T <= 8, bulk-copyable rows) and the tcgen05 path
     }
     return e == cudaSuccess ? QGEMM_OK : cuda_fail(e, "gemm_peers launch");
 }
@@ -447,7 +507,7 @@ int qgemm_peer_wait(const qgemm_peers* peers, void* stream) {
     if (!peers || peers->world < 1 || peers->world > kMaxPeers || !peers->step) return QGEMM_E_BADARG;
     if (peers->world == 1) return QGEMM_OK;
     peer_wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(peers->flag[peers->rank], peers->step, peers->launches_per_step,
-                                                        (uint32_t)peers->world);
+                                                        peers->launches_per_step, (uint32_t)peers->world);
     note_launch();
     return cudaGetLastError() == cudaSuccess ? QGEMM_OK : QGEMM_E_CUDA;
 }

@@ -149,9 +149,10 @@ class PeerPlan:
 
 
 class ShardedGemvP2P:
-    """Decode GEMV (T <= 8) over row-sharded weights whose kernel writes its slice of C[F_total, T]
-    into every rank's gathered buffer.  `out` is this rank's full gathered view (valid after the
-    next launch's prologue or PeerPlan.end_step())."""
+    """GEMM over row-sharded weights whose kernel writes its slice of C[F_total, T] into every rank's
+    gathered buffer: the decode kernels for T <= 8, the tcgen05 epilogue for larger T (scratch from the
+    registered default workspace or the stream's pool).  `out` is this rank's full gathered view (valid
+    after the next launch's prologue or PeerPlan.end_step())."""
 
     def __init__(self, weight_shard: torch.Tensor, F_total: int, K: int, wtype: int, T: int, plan: PeerPlan,
                  align: int = DEFAULT_ALIGN, flags: int = 0, wait_index: Optional[int] = None):
@@ -159,6 +160,8 @@ class ShardedGemvP2P:
         its activations (default: all earlier ones).  A model passes the index after the launch that
         produced this GEMV's input, so independent projections (q/k/v, gate/up) do not re-synchronise."""
         self.plan, self.K, self.wtype, self.T, self.flags = plan, K, wtype, T, flags
+        if T > 8:
+            self.flags |= _lib.GEMM_STREAM_ALLOC
         self.ranges = [shard_rows(F_total, plan.world, r, align) for r in range(plan.world)]
         self.f0, self.f1 = self.ranges[plan.rank]
         assert weight_shard.shape[0] == self.f1 - self.f0 > 0, "every rank needs a non-empty shard in peer mode"
@@ -178,6 +181,9 @@ class ShardedGemvP2P:
                                 torch.cuda.current_stream(self.weight.device).cuda_stream)
         _lib.raise_on_error(rc, "gemm_peers")
         return self.out
+
+
+ShardedGemmP2P = ShardedGemvP2P   # same operator at prefill sizes
 
 
 class ShardedGemvGroupP2P:

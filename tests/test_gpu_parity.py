@@ -441,7 +441,47 @@ def test_peer_store_protocol_single_gpu(qg, O, wt, T):
     ps.launch_index = 1   # outside launches_per_step
     assert L.qgemm_gemm_peers(wt, da.data_ptr(), dw.data_ptr(), ps, T, F, K, 1, T, 0, st) == -1
     ps.launch_index = 0
-    assert L.qgemm_gemm_peers(wt, da.data_ptr(), dw.data_ptr(), ps, 64, F, K, 1, 64, 0, st) in (-1, -2)
+    # T > 8 is the tensor-core path: without registered scratch or QGEMM_STREAM_ALLOC it asks for a workspace
+    assert L.qgemm_gemm_peers(wt, da.data_ptr(), dw.data_ptr(), ps, 64, F, K, 1, 64, 0, st) == -5
+
+
+@pytest.mark.parametrize("wt,T", [(qo.Q4_0, 200), (qo.Q5_1, 130), (qo.Q8_0, 96)])
+def test_peer_store_protocol_prefill_single_gpu(qg, O, wt, T):
+    """Same stand-in as above for the tcgen05 epilogue: the tile goes to both 'ranks' and is bit-identical
+    to the plain tensor-core call; launch 1 of each step waits for launch 0 through the wait kernel."""
+    from quant_gemm import _lib
+    L = _lib.lib()
+    F, K, world, steps = 300, 1056, 2, 3
+    x, w = datagen.model_like(T, F, K, seed=170 + wt)
+    aq, wq = O.quantize_q8_1(x), O.quantize_weight(wt, w)
+    da, dw = dev(aq), dev(wq)
+    bufs = [torch.full((2, F, T), -1.0, device="cuda") for _ in range(world)]
+    flag = torch.zeros(32, dtype=torch.int32, device="cuda")
+    done = torch.zeros(1, dtype=torch.int32, device="cuda")
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    pss = []
+    for li in range(2):
+        ps = _lib.QgemmPeers()
+        ps.world, ps.rank = world, 0
+        for r in range(world):
+            ps.C[r] = bufs[r][li].data_ptr()
+            ps.flag[r] = flag.data_ptr()
+        ps.done, ps.step, ps.launches_per_step, ps.launch_index = done.data_ptr(), step.data_ptr(), 2, li
+        ps.wait_index = li
+        pss.append(ps)
+    for _ in range(steps):
+        for ps in pss:
+            assert L.qgemm_gemm_peers(wt, da.data_ptr(), dw.data_ptr(), ps, T, F, K, 1, T, _lib.GEMM_STREAM_ALLOC, st) == 0
+            assert qg.last_path() == 0x400
+        assert L.qgemm_peer_wait(pss[0], st) == 0
+        assert L.qgemm_peer_step_advance(step.data_ptr(), st) == 0
+    plain = host(qg.gemm(dw, da, F, T, K, wt, flags=0x400))
+    check_c(plain, O.gemm(wt, aq, wq, layout="FT"), "tcgen05 vs oracle")
+    for b in bufs:
+        for li in range(2):
+            assert (bits(host(b[li])) == bits(plain)).all()
+    assert int(flag[0]) == steps * 2 * world and int(done[0]) == 0 and int(step[0]) == steps
 
 
 # ------------------------------------------------------------------------------------------
