@@ -528,7 +528,9 @@ cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, i
     const int nb = K / 32;
     const bool ms = flags & QGEMM_MS_EXACT;
     GemvPlan pl;
-    const int grid = min(F, kGemvCtasPerSm * num_sms);
+    int ctas_per_sm = kGemvCtasPerSm;
+    if (const char* e = getenv("QGEMM_GEMV_CTAS")) ctas_per_sm = max(1, min(kGemvCtasPerSm, atoi(e)));  // tuning aid
+    const int grid = min(F, ctas_per_sm * num_sms);
     const bool pdl = flags & QGEMM_WEIGHTS_STATIC;
     if (!gemv_plan(wtype, T, F, K, grid, pdl, &pl)) return cudaErrorInvalidValue;
     for (int t0 = 0; t0 < T; t0 += pl.tt) {

@@ -20,7 +20,7 @@ namespace qgemm {
 constexpr int kMmaWarps = 8;
 constexpr int kMmaThreads = (kMmaWarps + 1) * 32;
 constexpr int kMmaRows = 16;          // weight rows per tile = MMA M
-constexpr int kMmaStagesMax = 4;
+constexpr int kMmaStagesMax = 6;
 constexpr int kMmaSmemBudget = 112 * 1024;   // two CTAs per SM when two stages fit in this
 constexpr int kMmaSmemMax = 200 * 1024;      // otherwise one CTA per SM (long or 8-bit rows)
 
@@ -30,9 +30,10 @@ struct GemvMmaParams {
     float* C;
     int T, F, nb;
     int64_t ldc_t, ldc_f;
-    int pitch;        // smem bytes per weight row (row bytes + 16: pitch % 128 == 16)
+    int pitch;        // smem bytes per row segment of one chunk (+ 16: pitch % 128 == 16)
     int stages;
     int pdl;
+    int span;         // tuning aid: split rows, not tiles, over the CTAs
     PeerOut peer;
 };
 
@@ -51,29 +52,60 @@ __device__ __forceinline__ void mma_s8s8(int (&c)[4], const uint32_t (&a)[4], ui
 
 // A-fragment registers of one weight row for thread-in-group `tig`:
 //   lo = elements 4*tig .. 4*tig+3, hi = elements 16+4*tig .. 16+4*tig+3   (un-offset u8, or s8 for q8_0)
+//   al4: the block's quant words are 4-byte aligned in smem (known at compile time after unrolling: one word load
+//   instead of two halves)
+__device__ __forceinline__ uint32_t ld_u32_sel(const uint8_t* p, bool al4) {
+    return al4 ? *reinterpret_cast<const uint32_t*>(p) : ld_u32_a2(p);
+}
 template <int WT>
-__device__ __forceinline__ void row_frag(const uint8_t* blk, int tig, uint32_t& lo, uint32_t& hi, WScale& ws) {
+__device__ __forceinline__ void row_frag(const uint8_t* blk, int tig, uint32_t& lo, uint32_t& hi, WScale& ws,
+                                         bool al4 = false) {
     using Fm = Fmt<WT>;
     ws = load_wscale<WT>(blk);
     if constexpr (Fm::bits == 8) {
-        lo = ld_u32_a2(blk + Fm::qs + 4 * tig);
-        hi = ld_u32_a2(blk + Fm::qs + 16 + 4 * tig);
+        lo = ld_u32_sel(blk + Fm::qs + 4 * tig, al4);
+        hi = ld_u32_sel(blk + Fm::qs + 16 + 4 * tig, al4);
     } else {
-        const uint32_t v = ld_u32_a2(blk + Fm::qs + 4 * tig);
+        const uint32_t v = ld_u32_sel(blk + Fm::qs + 4 * tig, al4);
         lo = v & 0x0f0f0f0fu;
         hi = (v >> 4) & 0x0f0f0f0fu;
         if constexpr (Fm::bits == 5) {
-            const uint32_t qh = ld_u32_a2(blk + Fm::qh);
+            const uint32_t qh = ld_u32_sel(blk + Fm::qh, al4);
             lo |= spread_qh4(qh, 4 * tig);
             hi |= spread_qh4(qh, 16 + 4 * tig);
         }
     }
 }
 
-// NBW = K-blocks per warp held as register fragments
-template <int WT, int NBW, bool kMsExact>
+// K-chunks per row for a given format and register-fragment depth: the smallest split that leaves room for
+// four stages with two CTAs per SM (whole-row stages of the 8-bit and 5-bit formats did not, which cost them
+// half the resident warps)
+constexpr int mma_pitch(int seg) { return seg + 16 + ((128 - (seg % 128)) % 128); }
+constexpr size_t mma_fixed(int nb) { return 128 + kMmaWarps * 128 * 4 + (size_t)nb * 64 + 128; }
+constexpr int mma_pick_nc(int bytes, int nbw) {
+    // whole rows when two stages of them fit (measured: chunking costs the 4-bit formats ~5 %)
+    if (mma_fixed(nbw * kMmaWarps) + 2 * (size_t)kMmaRows * mma_pitch(nbw * kMmaWarps * bytes) <= (size_t)kMmaSmemBudget) return 1;
+    for (int nc = 2; nc <= 8; nc *= 2) {
+        if (nbw % nc) break;
+        const int seg = (nbw / nc) * kMmaWarps * bytes;
+        if (mma_fixed(nbw * kMmaWarps) + 4 * (size_t)kMmaRows * mma_pitch(seg) <= (size_t)kMmaSmemBudget) return nc;
+    }
+    return nbw >= 8 ? 8 : nbw;
+}
+
+// NBW = K-blocks per warp held as register fragments, NC = K-chunks a row is streamed in.
+// A CTA owns a contiguous span of weight rows at one-row granularity (so every CTA streams the same number
+// of bytes), walked in tiles of up to 16 rows; chunk c of a tile holds blocks [c*CB, (c+1)*CB) of each row and
+// warp w owns blocks c*CB + w*PER .. + PER-1 of every chunk.
+// kFull: nb == 8 * NBW, every (chunk, block) slot is real -- no guards in the unrolled loops, so the loads of
+// the next block move above the MMA of this one.
+template <int WT, int NBW, int NC, bool kMsExact, bool kFull>
 __global__ void __launch_bounds__(kMmaThreads, 2) gemv_mma_kernel(const GemvMmaParams p) {
     using Fm = Fmt<WT>;
+    constexpr int PER = NBW / NC;
+    constexpr int CB = PER * kMmaWarps;
+    // quant words of block i of a warp's slice are word-aligned when the slice starts word-aligned and ...
+    constexpr bool kSliceAl = (PER * Fm::bytes) % 4 == 0;
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, tig = lane & 3;
@@ -86,9 +118,13 @@ __global__ void __launch_bounds__(kMmaThreads, 2) gemv_mma_kernel(const GemvMmaP
     const uint32_t stage_bytes = (uint32_t)kMmaRows * p.pitch;
     uint8_t* stage0 = smem + ((128u + kMmaWarps * 128u * 4u + (uint32_t)nb * 64u + 127u) & ~127u);
 
+    // whole 16-row tiles per CTA: the kernel is issue-bound, so no CTA should spend MMAs on rows it does not own
+    // (p.span: one-row granularity instead -- equal bytes per CTA, more MMAs; tuning aid)
     const int ntiles_total = (p.F + kMmaRows - 1) / kMmaRows;
-    const int t_begin = (int)(((int64_t)ntiles_total * blockIdx.x) / gridDim.x);
-    const int t_end = (int)(((int64_t)ntiles_total * (blockIdx.x + 1)) / gridDim.x);
+    const int r_begin = p.span ? (int)(((int64_t)p.F * blockIdx.x) / gridDim.x)
+                               : kMmaRows * (int)(((int64_t)ntiles_total * blockIdx.x) / gridDim.x);
+    const int r_end = p.span ? (int)(((int64_t)p.F * (blockIdx.x + 1)) / gridDim.x)
+                             : min(p.F, kMmaRows * (int)(((int64_t)ntiles_total * (blockIdx.x + 1)) / gridDim.x));
     const size_t rowbytes = (size_t)nb * Fm::bytes;
 
     if (tid == 0) {
@@ -102,19 +138,23 @@ __global__ void __launch_bounds__(kMmaThreads, 2) gemv_mma_kernel(const GemvMmaP
     if (p.pdl) ptx::griddep_launch_dependents();
 
     if (warp == kMmaWarps) {
-        // ===== producer: one bulk copy per weight row into the padded pitch
+        // ===== producer: per chunk, one bulk copy per weight row of the tile into the padded pitch
         int s = 0;
         uint32_t ph = 0;
-        for (int t = t_begin; t < t_end; t++) {
-            ptx::mbar_wait(&empty[s], ph ^ 1);
-            if (lane == 0) ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(kMmaRows * rowbytes));
-            __syncwarp();
-            if (lane < kMmaRows) {
-                const int f = min(t * kMmaRows + lane, p.F - 1);  // tail tile: re-read a valid row, never stored
-                ptx::bulk_g2s(stage0 + (size_t)s * stage_bytes + (size_t)lane * p.pitch, p.wgt + (size_t)f * rowbytes,
-                              (uint32_t)rowbytes, &full[s]);
+        for (int r = r_begin; r < r_end; r += kMmaRows) {
+            const int nrows = min(kMmaRows, r_end - r);   // rows beyond keep stale smem: computed, never stored
+            for (int c = 0; c < NC; c++) {
+                const int cb = min(CB, nb - c * CB);
+                if (cb <= 0) break;
+                const uint32_t seg = (uint32_t)cb * Fm::bytes;
+                ptx::mbar_wait(&empty[s], ph ^ 1);
+                if (lane == 0) ptx::mbar_arrive_expect_tx(&full[s], seg * (uint32_t)nrows);
+                __syncwarp();
+                if (lane < nrows)
+                    ptx::bulk_g2s(stage0 + (size_t)s * stage_bytes + (size_t)lane * p.pitch,
+                                  p.wgt + (size_t)(r + lane) * rowbytes + (size_t)c * CB * Fm::bytes, seg, &full[s]);
+                if (++s == p.stages) { s = 0; ph ^= 1; }
             }
-            if (++s == p.stages) { s = 0; ph ^= 1; }
         }
         return;
     }
@@ -125,17 +165,19 @@ __global__ void __launch_bounds__(kMmaThreads, 2) gemv_mma_kernel(const GemvMmaP
         if (tid == 0) peer_wait_prior(p.peer);
         ptx::bar_sync(1, kMmaWarps * 32);
     }
-    const int b0 = warp * NBW;
     // B fragments: token g (zero beyond T), elements 4*tig.. and 16+4*tig.. of each of this warp's blocks
     uint32_t bf[NBW][2];
 #pragma unroll
-    for (int i = 0; i < NBW; i++) {
-        const int b = b0 + i;
-        bf[i][0] = bf[i][1] = 0u;
-        if (b < nb && g < p.T) {
-            const uint32_t* q = reinterpret_cast<const uint32_t*>(p.act + ((size_t)g * nb + b) * kQ81Bytes);
-            bf[i][0] = __ldg(q + 1 + tig);
-            bf[i][1] = __ldg(q + 5 + tig);
+    for (int c = 0; c < NC; c++) {
+#pragma unroll
+        for (int i = 0; i < PER; i++) {
+            const int b = c * CB + warp * PER + i;
+            bf[c * PER + i][0] = bf[c * PER + i][1] = 0u;
+            if ((kFull || b < nb) && g < p.T) {
+                const uint32_t* q = reinterpret_cast<const uint32_t*>(p.act + ((size_t)g * nb + b) * kQ81Bytes);
+                bf[c * PER + i][0] = __ldg(q + 1 + tig);
+                bf[c * PER + i][1] = __ldg(q + 5 + tig);
+            }
         }
     }
     // activation scales of all blocks, all 8 token slots: [b][token] (d_a, c_a)
@@ -152,32 +194,40 @@ __global__ void __launch_bounds__(kMmaThreads, 2) gemv_mma_kernel(const GemvMmaP
 
     int s = 0;
     uint32_t ph = 0;
-    for (int t = t_begin; t < t_end; t++) {
-        ptx::mbar_wait(&full[s], ph);
-        const uint8_t* r0 = stage0 + (size_t)s * stage_bytes + (size_t)g * p.pitch;
-        const uint8_t* r1 = r0 + (size_t)8 * p.pitch;
+    for (int r = r_begin; r < r_end; r += kMmaRows) {
         float acc[4] = {0.f, 0.f, 0.f, 0.f};  // (row g, tok 2tig), (row g, tok 2tig+1), (row g+8, ...)
 #pragma unroll
-        for (int i = 0; i < NBW; i++) {
-            const int b = b0 + i;
-            if (b < nb) {
-                uint32_t a[4];
-                WScale w0, w1;
-                row_frag<WT>(r0 + (size_t)b * Fm::bytes, tig, a[0], a[2], w0);
-                row_frag<WT>(r1 + (size_t)b * Fm::bytes, tig, a[1], a[3], w1);
-                int c[4] = {0, 0, 0, 0};
-                if constexpr (Fm::bits == 8) mma_s8s8(c, a, bf[i][0], bf[i][1]);
-                else mma_u8s8(c, a, bf[i][0], bf[i][1]);
-                const float4 sc = *reinterpret_cast<const float4*>(&a_sc[b * 8 + 2 * tig]);  // tokens 2tig, 2tig+1
-                acc[0] = fold_block_pre<WT>(acc[0], c[0], w0, ActScale{sc.x, sc.y});
-                acc[1] = fold_block_pre<WT>(acc[1], c[1], w0, ActScale{sc.z, sc.w});
-                acc[2] = fold_block_pre<WT>(acc[2], c[2], w1, ActScale{sc.x, sc.y});
-                acc[3] = fold_block_pre<WT>(acc[3], c[3], w1, ActScale{sc.z, sc.w});
+        for (int c = 0; c < NC; c++) {
+            if (kFull || c * CB < nb) {
+                ptx::mbar_wait(&full[s], ph);
+                const uint8_t* r0 = stage0 + (size_t)s * stage_bytes + (size_t)g * p.pitch + (size_t)(warp * PER) * Fm::bytes;
+                const uint8_t* r1 = r0 + (size_t)8 * p.pitch;
+#pragma unroll
+                for (int i = 0; i < PER; i++) {
+                    const int b = c * CB + warp * PER + i;
+                    if (kFull || b < nb) {
+                        uint32_t a[4];
+                        WScale w0, w1;
+                        // ... the block's own offset keeps the quant words on a word boundary
+                        const bool al4 = kSliceAl && (i * Fm::bytes + Fm::qs) % 4 == 0 &&
+                                         (Fm::bits != 5 || (i * Fm::bytes + Fm::qh) % 4 == 0);
+                        row_frag<WT>(r0 + (size_t)i * Fm::bytes, tig, a[0], a[2], w0, al4);
+                        row_frag<WT>(r1 + (size_t)i * Fm::bytes, tig, a[1], a[3], w1, al4);
+                        int cc[4] = {0, 0, 0, 0};
+                        if constexpr (Fm::bits == 8) mma_s8s8(cc, a, bf[c * PER + i][0], bf[c * PER + i][1]);
+                        else mma_u8s8(cc, a, bf[c * PER + i][0], bf[c * PER + i][1]);
+                        const float4 sc = *reinterpret_cast<const float4*>(&a_sc[b * 8 + 2 * tig]);  // tokens 2tig, 2tig+1
+                        acc[0] = fold_block_pre<WT>(acc[0], cc[0], w0, ActScale{sc.x, sc.y});
+                        acc[1] = fold_block_pre<WT>(acc[1], cc[1], w0, ActScale{sc.z, sc.w});
+                        acc[2] = fold_block_pre<WT>(acc[2], cc[2], w1, ActScale{sc.x, sc.y});
+                        acc[3] = fold_block_pre<WT>(acc[3], cc[3], w1, ActScale{sc.z, sc.w});
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&empty[s]);
+                if (++s == p.stages) { s = 0; ph ^= 1; }
             }
         }
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&empty[s]);
-        if (++s == p.stages) { s = 0; ph ^= 1; }
 
         // combine the 8 K-slices in warp order
         float* rb = red;
@@ -187,12 +237,12 @@ __global__ void __launch_bounds__(kMmaThreads, 2) gemv_mma_kernel(const GemvMmaP
         rb[warp * 128 + (g + 8) * 8 + 2 * tig + 1] = acc[3];
         ptx::bar_sync(1, kMmaWarps * 32);
         if (tid < 128) {
-            const int r = tid >> 3, tok = tid & 7;
+            const int row = tid >> 3, tok = tid & 7;
             float v = 0.f;
 #pragma unroll
             for (int w = 0; w < kMmaWarps; w++) v += rb[w * 128 + tid];
-            const int f = t * kMmaRows + r;
-            if (f < p.F && tok < p.T) peer_store(p.peer, p.C, (int64_t)tok * p.ldc_t + (int64_t)f * p.ldc_f, v);
+            const int f = r + row;
+            if (f < r_end && tok < p.T) peer_store(p.peer, p.C, (int64_t)tok * p.ldc_t + (int64_t)f * p.ldc_f, v);
         }
         ptx::bar_sync(1, kMmaWarps * 32);  // the partials buffer is reused by the next tile
     }
@@ -365,12 +415,16 @@ static size_t bigk_fixed(int nb) { return 128 + kMmaWarps * 128 * 4 + (size_t)nb
 static bool bigk_supported(int wtype, int nb) {
     return (nb % 8) == 0 && bigk_fixed(nb) + 2 * (size_t)kMmaRows * bigk_pitch(wtype) <= (size_t)kMmaSmemMax + 20 * 1024;
 }
+static int nbw_of(int nb) {
+    const int nbw = (nb + kMmaWarps - 1) / kMmaWarps;
+    return nbw <= 8 ? 8 : (nbw <= 16 ? 16 : 32);
+}
 static bool regs_variant_supported(int wtype, int nb) {
-    const size_t rowbytes = (size_t)nb * block_bytes(wtype);
     if (nb < 8 || nb > kMmaWarps * 32) return false;
-    const size_t pitch = rowbytes + 16 + ((128 - (rowbytes % 128)) % 128);
-    const size_t fixed = 128 + kMmaWarps * 128 * 4 + (size_t)nb * 64 + 128;
-    return fixed + 2 * kMmaRows * pitch <= (size_t)kMmaSmemMax;
+    const int nbw = nbw_of(nb);
+    const int nc = mma_pick_nc(block_bytes(wtype), nbw);
+    const int seg = (nbw / nc) * kMmaWarps * block_bytes(wtype);
+    return mma_fixed(nb) + 2 * (size_t)kMmaRows * mma_pitch(seg) <= (size_t)kMmaSmemBudget;
 }
 bool gemv_mma_supported(int wtype, const void* act, const void* wgt, int T, int F, int K) {
     const int nb = K / 32;
@@ -414,8 +468,9 @@ static cudaError_t launch_bigk(const GemvMmaBigParams& p, size_t smem, int grid,
 
 template <int WT, int NBW>
 static cudaError_t launch_mma_inst(const GemvMmaParams& p, size_t smem, int grid, bool ms_exact, cudaStream_t st) {
+    constexpr int NC = mma_pick_nc(Fmt<WT>::bytes, NBW);
     auto launch = [&](auto kernel, int variant) -> cudaError_t {
-        static size_t attr_set[2] = {0, 0};
+        static size_t attr_set[4] = {0, 0, 0, 0};
         if (smem > attr_set[variant]) {
             cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
@@ -434,10 +489,12 @@ static cudaError_t launch_mma_inst(const GemvMmaParams& p, size_t smem, int grid
         return cudaLaunchKernelEx(&cfg, kernel, p);
     };
     cudaError_t e;
+    const bool full = p.nb == NBW * kMmaWarps;
     if constexpr (Fmt<WT>::m >= 0) {
-        e = ms_exact ? launch(gemv_mma_kernel<WT, NBW, true>, 1) : launch(gemv_mma_kernel<WT, NBW, false>, 0);
+        if (full) e = ms_exact ? launch(gemv_mma_kernel<WT, NBW, NC, true, true>, 3) : launch(gemv_mma_kernel<WT, NBW, NC, false, true>, 2);
+        else e = ms_exact ? launch(gemv_mma_kernel<WT, NBW, NC, true, false>, 1) : launch(gemv_mma_kernel<WT, NBW, NC, false, false>, 0);
     } else {
-        e = launch(gemv_mma_kernel<WT, NBW, false>, 0);
+        e = full ? launch(gemv_mma_kernel<WT, NBW, NC, false, true>, 2) : launch(gemv_mma_kernel<WT, NBW, NC, false, false>, 0);
     }
     note_launch();
     return e;
@@ -488,15 +545,19 @@ cudaError_t launch_gemv_mma(int wtype, const void* act, const void* wgt, float* 
         return cudaSuccess;
     }
     const int nb = K / 32;
-    const size_t rowbytes = (size_t)nb * block_bytes(wtype);
-    const int pitch = (int)(rowbytes + 16 + ((128 - (rowbytes % 128)) % 128));
-    const size_t fixed = 128 + kMmaWarps * 128 * 4 + (size_t)nb * 64 + 128;
-    const size_t budget = (fixed + 2 * (size_t)kMmaRows * pitch <= (size_t)kMmaSmemBudget) ? kMmaSmemBudget : kMmaSmemMax;
-    int stages = (int)((budget - fixed) / ((size_t)kMmaRows * pitch));
+    const int nbw = nbw_of(nb);
+    const int nc = mma_pick_nc(block_bytes(wtype), nbw);
+    const int cb = (nbw / nc) * kMmaWarps;                 // blocks per chunk
+    const int pitch = mma_pitch(cb * block_bytes(wtype));
+    const size_t fixed = mma_fixed(nb);
+    int stages = (int)(((size_t)kMmaSmemBudget - fixed) / ((size_t)kMmaRows * pitch));
     stages = max(2, min(kMmaStagesMax, stages));
+    if (const char* e = getenv("QGEMM_MMA_STAGES")) stages = max(2, min(stages, atoi(e)));  // tuning aid
+    const int span = getenv("QGEMM_MMA_SPAN") ? 1 : 0;
     const int ntiles = (F + kMmaRows - 1) / kMmaRows;
-    const int grid = min(ntiles, 2 * num_sms);
-    stages = max(2, min(stages, (ntiles + grid - 1) / grid));
+    const int grid = span ? min(F, 2 * num_sms) : min(ntiles, 2 * num_sms);
+    const int chunks_per_cta = (span ? ((F + grid - 1) / grid + kMmaRows - 1) / kMmaRows : (ntiles + grid - 1) / grid) * ((nb + cb - 1) / cb);
+    stages = max(2, min(stages, chunks_per_cta));
     const size_t smem = fixed + (size_t)stages * kMmaRows * pitch;
     for (int t0 = 0; t0 < T; t0 += 8) {
         GemvMmaParams p;
@@ -504,7 +565,7 @@ cudaError_t launch_gemv_mma(int wtype, const void* act, const void* wgt, float* 
         p.wgt = (const uint8_t*)wgt;
         p.C = C + (int64_t)t0 * ldc_t;
         p.T = min(8, T - t0); p.F = F; p.nb = nb; p.ldc_t = ldc_t; p.ldc_f = ldc_f;
-        p.pitch = pitch; p.stages = stages; p.pdl = (flags & QGEMM_WEIGHTS_STATIC) ? ((flags & QGEMM_INPUTS_READY) ? 2 : 1) : 0;
+        p.pitch = pitch; p.stages = stages; p.span = span; p.pdl = (flags & QGEMM_WEIGHTS_STATIC) ? ((flags & QGEMM_INPUTS_READY) ? 2 : 1) : 0;
         p.peer = peer ? *peer : PeerOut{};
         const bool ms = flags & QGEMM_MS_EXACT;
         cudaError_t e;
