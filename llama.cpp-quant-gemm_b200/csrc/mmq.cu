@@ -231,7 +231,9 @@ __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
 #define QGEMM_MMQ_CVT_MAGIC 0
 #endif
 __device__ __forceinline__ uint64_t cvt2(int x0, int x1) {
-#if QGEMM_MMQ_CVT_MAGIC
+#if QGEMM_MMQ_CVT_MAGIC == 2
+    return pk(__int_as_float(x0), __int_as_float(x1));  // timing experiment only: what the fold costs without a conversion
+#elif QGEMM_MMQ_CVT_MAGIC
     const uint64_t biased = pk(__int_as_float(x0 + 0x4B400000), __int_as_float(x1 + 0x4B400000));
     return fadd2(biased, pk(-12582912.0f, -12582912.0f));
 #else
@@ -347,6 +349,7 @@ __global__ void __launch_bounds__(kMmqThreads, 1) mmq_kernel(const MmqParams p) 
                     if (lane == 0) {
                         // one instruction = one quantization block (K = 32 bytes = +2 in the >>4 address field)
                         t5::mma_i8(tmem_base + buf * kBN, adesc + 2 * j, bdesc + 2 * j, idesc, 0u);
+                        if (p.dbg & 16) t5::mma_i8(tmem_base + buf * kBN, adesc + 2 * j, bdesc + 2 * j, idesc, 1u);  // timing experiment
                         t5::commit(&tfull[buf]);
                     }
                     __syncwarp();

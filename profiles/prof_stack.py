@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, "llama.cpp-quant-gemm_b200"), ROOT]
 import torch, quant_gemm, bench_detail
 dev = torch.device("cuda")
-LAYERS = 3
+LAYERS = 8
 sq = bench_detail.make_weights(torch, 2, 4096, 4096, 4 * LAYERS, dev)
 up = bench_detail.make_weights(torch, 2, 11008, 4096, 2 * LAYERS, dev)
 dn = bench_detail.make_weights(torch, 2, 4096, 11008, LAYERS, dev)
