@@ -370,6 +370,65 @@ def test_mmq_full_size_prefill_properties(qg, O):
     assert (bits(c2) == bits(c[:, perm])).all()
 
 
+def _gpu_model_like(T, F, K, seed):
+    """Model-like fp32 operands generated on the device (the full-size shapes are too slow to draw on the host)."""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    x = torch.randn((T, K), device="cuda", generator=g)
+    w = torch.randn((F, K), device="cuda", generator=g) * 0.02
+    w[:, ::128] *= 8.0   # an outlier column every 128 elements, like datagen.model_like
+    return x, w
+
+
+def test_full_size_config4_q5_1_with_fused_quantize(qg, O):
+    """BASELINE config 4 (Llama-3-8B FFN, Q5_1, M=2048 N=14336 K=4096, quantize_q8_1 of A inside the call):
+    the one-call fp32-activation entry equals quantize + GEMM bit for bit; sampled rows against the oracle
+    (which quantizes A itself: bytes must agree too)."""
+    T, F, K = 2048, 14336, 4096
+    x, w = _gpu_model_like(T, F, K, seed=404)
+    dwq = qg.quantize_q5_1(w)
+    del w
+    c1 = qg.gemm_w4a8(dwq, x, F, T, K, wtype=qo.Q5_1)
+    assert qg.last_path() == 0x400
+    daq = qg.quantize_q8_1(x)
+    c2 = qg.gemm(dwq, daq, F, T, K, qo.Q5_1)
+    assert torch.equal(c1, c2)
+    aq = host(daq)
+    assert (aq == O.quantize_q8_1(host(x))).all()
+    rows = np.r_[0:3, 7000:7003, F - 3:F]
+    wq = host(dwq[torch.from_numpy(rows).cuda()])
+    c = host(c1[torch.from_numpy(rows).cuda()])
+    assert (bits(c) == bits(O.gemm(qo.Q5_1, aq, wq, layout="FT", flags=qo.GEMM_FMA))).all()
+    check_c(c, O.gemm(qo.Q5_1, aq, wq, layout="FT"), "config 4 vs CPU-order oracle")
+
+
+def test_full_size_config5_q4_0_properties(qg, O):
+    """BASELINE config 5 (Llama-3-70B FFN, Q4_0, M=4096 N=28672 K=8192) on one GPU: sampled rows x sampled tokens
+    against the oracle, and the row-sharded evaluation (what every rank of the N-sharded run computes) equals
+    the unsharded one bit for bit."""
+    T, F, K = 4096, 28672, 8192
+    x, w = _gpu_model_like(T, F, K, seed=505)
+    dwq = qg.quantize_q4_0(w)
+    del w
+    daq = qg.quantize_q8_1(x)
+    del x
+    c = qg.gemm(dwq, daq, F, T, K, qo.Q4_0)
+    assert qg.last_path() == 0x400
+    rows = np.r_[0:2, 14335:14337, F - 2:F]
+    toks = np.r_[0:8, 2047:2055, T - 8:T]
+    ri, ti = torch.from_numpy(rows).cuda(), torch.from_numpy(toks).cuda()
+    aq, wq = host(daq[ti]), host(dwq[ri])
+    got = host(c[ri][:, ti])
+    assert (bits(got) == bits(O.gemm(qo.Q4_0, aq, wq, layout="FT", flags=qo.GEMM_FMA))).all()
+    check_c(got, O.gemm(qo.Q4_0, aq, wq, layout="FT"), "config 5 vs CPU-order oracle")
+    from quant_gemm import sharded
+    for world in (2, 8):
+        for rank in (0, world - 1):
+            f0, f1 = sharded.shard_rows(F, world, rank)
+            part = qg.gemm(dwq[f0:f1], daq, f1 - f0, T, K, qo.Q4_0)
+            assert torch.equal(part, c[f0:f1])
+
+
 # ------------------------------------------------------------------------------------------
 # skinny path: mma.sync m16n8k32 with tokens on N (QGEMM_PATH_MMA), 3 <= T < 64
 # ------------------------------------------------------------------------------------------
