@@ -76,23 +76,36 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.p = None
+        import threading
+        self.p, self.lines, self.first = None, [], threading.Event()
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "20"],
+                                       "--format=csv,noheader,nounits", "-lms", "10"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
-            pass
+            return
+
+        def pump():
+            for line in self.p.stdout:
+                self.lines.append((time.perf_counter(), line))
+                self.first.set()
+        self.t = threading.Thread(target=pump, daemon=True)
+        self.t.start()
+        self.first.wait(timeout=5.0)   # sampling is live before the timed region starts
+        self.t_start = time.perf_counter()
 
     def stop(self):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        t_stop = time.perf_counter()
+        time.sleep(0.03)
         self.p.terminate()
-        out = self.p.communicate()[0]
+        self.t.join(timeout=2.0)
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in out.strip().splitlines():
+        for ts, line in self.lines:
+            if ts < self.t_start or ts > t_stop + 0.02:   # only samples taken while the timed regions ran
+                continue
             f = [x.strip() for x in line.split(",")]
             if len(f) < 7:
                 continue
@@ -268,7 +281,7 @@ def workload_config(n_gpus, tp=1):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layers", type=int, default=32)

@@ -52,6 +52,9 @@ constexpr int kStageWM = kStageWS + kBlocksPerStage * kBN * 4;   // [4 blocks][k
 constexpr int kStageBytes = kStageWM + kBlocksPerStage * kBN * 4;
 static_assert(kStageBytes % 1024 == 0, "stage must keep 1024-byte alignment");
 constexpr int kMmqSmem = 1024 /*align slack*/ + kMmqStages * kStageBytes + 256 /*barriers*/;
+constexpr int kOutTileBytes = kBM * kBN * 4;           // one finished fp32 tile, [f][t]
+constexpr int kMmqSmemOut = kMmqSmem + kOutTileBytes;  // peer mode: + the staging tile for the bulk stores
+static_assert(kMmqSmemOut <= 227 * 1024, "staging tile must fit next to the operand ring");
 
 // ---------------------------------------------------------------------------
 // workspace layout (all offsets 1024-byte aligned)
@@ -266,6 +269,8 @@ struct MmqParams {
     int tiles_m, tiles_n;
     int dbg;  // tuning aid: 1 = skip the fold, 2 = also load only half of the TMEM columns, 3 = no TMEM load, 4 = no C store
     PeerOut peer;  // fused all-gather: the epilogue stores its tile into every rank's gathered C (world <= 1: plain store)
+    int tma_out;   // 1: finished tiles are staged in shared memory and leave through bulk copies (needs ldc_t == 1,
+                   //    16-byte rows; kMmqSmemOut bytes of dynamic shared memory)
 };
 
 template <int WT, bool kDump>
@@ -279,6 +284,7 @@ __global__ void __launch_bounds__(kMmqThreads, 1) mmq_kernel(const MmqParams p) 
     uint64_t* tfull = empty + kMmqStages;                                           // [kTmemBufs]
     uint64_t* tempty = tfull + kTmemBufs;                                           // [kTmemBufs]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + kTmemBufs);
+    float* out_tile = reinterpret_cast<float*>(smem + kMmqStages * kStageBytes + 256);  // [kBN][kBM], only with p.tma_out
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkc = p.nkc;
@@ -421,14 +427,51 @@ __global__ void __launch_bounds__(kMmqThreads, 1) mmq_kernel(const MmqParams p) 
             }
             if constexpr (!kDump) {
                 const int t = mt * kBM + row;
-                if (t < p.T && !(p.dbg & 4)) {
-                    // world > 1: the same tile goes to every rank's copy of the gathered buffer over NVLink.
-                    // Measured on 2 B200s (4096 x 14336 x 8192): +0.05 ms for the local store pass, +0.2 ms for
-                    // the remote one, straight from the epilogue registers; forwarding finished tiles with the
-                    // two spare warps instead (512-byte rows re-read from L2) was 4x slower over NVLink.
+                if (p.tma_out) {
+                    // Fused all-gather, bulk variant: the tile is staged in shared memory as [f][t] and carried to
+                    // every rank's gathered C (this rank's included) by the TMA engine, 512-byte rows, while the
+                    // epilogue warps go on folding the next tile.  Lane 0 of every epilogue warp issues the rows of
+                    // 8 f values for all ranks and owns their bulk group.
+                    if (lane == 0) ptx::bulk_wait_read();          // my rows of the previous tile have left smem
+                    ptx::bar_sync(3, kEpiWarps * 32);
+#pragma unroll
+                    for (int i = 0; i < kEpiCols / 2; i++) {
+                        float v0, v1;
+                        unpk(acc[i], v0, v1);
+                        out_tile[(cgrp * kEpiCols + 2 * i) * kBM + row] = v0;
+                        out_tile[(cgrp * kEpiCols + 2 * i + 1) * kBM + row] = v1;
+                    }
+                    ptx::fence_proxy_async();
+                    ptx::bar_sync(3, kEpiWarps * 32);
+                    if (lane == 0) {
+                        const int t0 = mt * kBM;
+                        const uint32_t bytes = (uint32_t)min(kBM, p.T - t0) * 4u;
+                        constexpr int kRowsPerWarp = kBN / kEpiWarps;
+#pragma unroll 1
+                        for (int q = 0; q < p.peer.world; q++) {
+                            // start at the next rank and wrap: at any moment the ranks target different receivers
+                            // instead of all converging on rank 0's links first
+                            int r = p.peer.rank + 1 + q;
+                            if (r >= p.peer.world) r -= p.peer.world;
+                            float* Cr = p.peer.C[r];
+#pragma unroll 1
+                            for (int k = 0; k < kRowsPerWarp; k++) {
+                                const int fl = ew * kRowsPerWarp + k;
+                                const int f = nt * kBN + fl;
+                                if (f < p.F) ptx::bulk_s2g(Cr + (int64_t)f * p.ldc_f + t0, out_tile + fl * kBM, bytes);
+                            }
+                        }
+                        ptx::bulk_commit();
+                    }
+                } else if (t < p.T && !(p.dbg & 4)) {
+                    // world > 1 without the staging tile (odd strides): the same values go to every rank's copy of the
+                    // gathered buffer straight from the registers.  Measured on 2 B200s (4096 x 14336 x 8192): +0.05 ms
+                    // for the local store pass, +0.2 ms for the remote one; at 8 ranks the bursts stall the epilogue.
                     const int nrank = p.peer.world > 1 ? p.peer.world : 1;
 #pragma unroll 1
-                    for (int r = 0; r < nrank; r++) {
+                    for (int q = 0; q < nrank; q++) {
+                        int r = p.peer.rank + 1 + q;   // staggered start, see above
+                        if (r >= nrank) r -= nrank;
                         float* crow = (nrank > 1 ? p.peer.C[r] : p.C) + (int64_t)t * p.ldc_t;
 #pragma unroll
                         for (int i = 0; i < kEpiCols / 2; i++) {
@@ -440,6 +483,12 @@ __global__ void __launch_bounds__(kMmqThreads, 1) mmq_kernel(const MmqParams p) 
                         }
                     }
                 }
+            }
+        }
+        if constexpr (!kDump) {
+            if (p.tma_out && lane == 0) {   // every bulk store of this thread is complete before the CTA signals
+                ptx::bulk_wait_all();
+                ptx::fence_proxy_async_all();
             }
         }
     }
@@ -501,7 +550,7 @@ static cudaError_t launch_mmq_t(const void* act, const void* wgt, float* C, int3
     if (e != cudaSuccess) return e;
     static bool attr_done = false;
     if (!attr_done) {
-        e = cudaFuncSetAttribute(mmq_kernel<WT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmqSmem);
+        e = cudaFuncSetAttribute(mmq_kernel<WT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmqSmemOut);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(mmq_kernel<WT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmqSmem);
         if (e != cudaSuccess) return e;
         attr_done = true;
@@ -515,9 +564,15 @@ static cudaError_t launch_mmq_t(const void* act, const void* wgt, float* C, int3
     p.tiles_m = L.Tpad / kBM; p.tiles_n = L.Fpad / kBN;
     p.dbg = getenv("QGEMM_MMQ_DBG") ? atoi(getenv("QGEMM_MMQ_DBG")) : 0;
     p.peer = peer ? *peer : PeerOut{};
+    p.tma_out = 0;
+    if (p.peer.world > 1 && !sumi && ldc_t == 1 && T % 4 == 0 && ldc_f % 4 == 0 && !getenv("QGEMM_MMQ_NO_TMA_OUT")) {
+        p.tma_out = 1;
+        for (int r = 0; r < p.peer.world; r++)
+            if (reinterpret_cast<uintptr_t>(p.peer.C[r]) % 16 != 0) p.tma_out = 0;
+    }
     const int ntiles = p.tiles_m * p.tiles_n;
     if (sumi) mmq_kernel<WT, true><<<min(ntiles, num_sms), kMmqThreads, kMmqSmem, st>>>(p);
-    else mmq_kernel<WT, false><<<min(ntiles, num_sms), kMmqThreads, kMmqSmem, st>>>(p);
+    else mmq_kernel<WT, false><<<min(ntiles, num_sms), kMmqThreads, p.tma_out ? kMmqSmemOut : kMmqSmem, st>>>(p);
     note_launch();
     return cudaGetLastError();
 }

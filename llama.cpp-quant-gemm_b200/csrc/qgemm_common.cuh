@@ -211,7 +211,11 @@ __device__ __forceinline__ void peer_store(const PeerOut& po, float* C, int64_t 
         idx += po.moff[m];
         if (po.dbg & 2) { po.C[po.rank][idx] = v; return; }
 #pragma unroll 1
-        for (int r = 0; r < po.world; r++) po.C[r][idx] = v;
+        for (int q = 0; q < po.world; q++) {   // staggered start: ranks do not all hit the same receiver first
+            int r = po.rank + 1 + q;
+            if (r >= po.world) r -= po.world;
+            po.C[r][idx] = v;
+        }
     } else {
         C[idx] = v;
     }
