@@ -248,15 +248,20 @@ def sharded_c5(torch, dist, quant_gemm, dev, world, rank, ctl, reps=3):
         op_n = sharded.ShardedGemm(w, F, K, WTYPE, flags=GEMV_FLAGS)
         ms = timed(lambda: op_n(aq, out=out_full))
         res["nccl_all_gather"] = {"ms": ms, "tops": ops / ms / 1e9}
-        plan = sharded.PeerPlan(F * T, 1, dev, ctl_group=ctl)
-        op_p = sharded.ShardedGemmP2P(w, F, K, WTYPE, T, plan, flags=GEMV_FLAGS)
+        def fused_variant(multicast):
+            plan = sharded.PeerPlan(F * T, 1, dev, ctl_group=ctl, multicast=multicast)
+            op_p = sharded.ShardedGemmP2P(w, F, K, WTYPE, T, plan, flags=GEMV_FLAGS)
 
-        def fused():
-            op_p(aq)
-            plan.end_step()
-        ms = timed(fused)
-        res["fused_peer_stores"] = {"ms": ms, "tops": ops / ms / 1e9}
-        res["fused_equals_nccl_bitwise"] = bool(torch.equal(op_p.out, out_full))
+            def fused():
+                op_p(aq)
+                plan.end_step()
+            ms = timed(fused)
+            return {"ms": ms, "tops": ops / ms / 1e9, "nvls_multicast": bool(plan.mc_ptr),
+                    "equals_nccl_bitwise": bool(torch.equal(op_p.out, out_full))}
+        res["fused_peer_stores"] = fused_variant(True)      # one store per value, replicated by the NVSwitch (if NVLS)
+        if res["fused_peer_stores"]["nvls_multicast"]:
+            res["fused_peer_stores_unicast"] = fused_variant(False)   # one store per value and rank
+        res["fused_equals_nccl_bitwise"] = res["fused_peer_stores"]["equals_nccl_bitwise"]
     return res
 
 

@@ -241,6 +241,9 @@ typedef struct qgemm_peers {
     uint32_t wait_index;              /* launches [0, wait_index) of this step (and all earlier steps) must have
                                          landed before this launch reads its activations; launch_index = strict
                                          chain, smaller = the producer of this launch's input finished earlier   */
+    float *C_multicast;               /* optional (NULL: unused): an NVLS multicast mapping of the same slice that is
+                                         bound on every rank (this one included).  The kernels then store each value
+                                         once and the NVSwitch replicates it, instead of one store per rank.        */
 } qgemm_peers;
 
 QGEMM_API int qgemm_gemm_peers(int wtype, const void *act_q8_1, const void *weight, const qgemm_peers *peers, int T,

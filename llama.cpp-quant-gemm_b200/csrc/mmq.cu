@@ -467,12 +467,13 @@ __global__ void __launch_bounds__(kMmqThreads, 1) mmq_kernel(const MmqParams p) 
                     // world > 1 without the staging tile (odd strides): the same values go to every rank's copy of the
                     // gathered buffer straight from the registers.  Measured on 2 B200s (4096 x 14336 x 8192): +0.05 ms
                     // for the local store pass, +0.2 ms for the remote one; at 8 ranks the bursts stall the epilogue.
-                    const int nrank = p.peer.world > 1 ? p.peer.world : 1;
+                    // With an NVLS multicast mapping (p.peer.mc) one pass is enough: the switch replicates each store.
+                    const int nrank = (p.peer.world > 1 && !p.peer.mc) ? p.peer.world : 1;
 #pragma unroll 1
                     for (int q = 0; q < nrank; q++) {
                         int r = p.peer.rank + 1 + q;   // staggered start, see above
                         if (r >= nrank) r -= nrank;
-                        float* crow = (nrank > 1 ? p.peer.C[r] : p.C) + (int64_t)t * p.ldc_t;
+                        float* crow = (nrank > 1 ? p.peer.C[r] : (p.peer.mc ? p.peer.mc : p.C)) + (int64_t)t * p.ldc_t;
 #pragma unroll
                         for (int i = 0; i < kEpiCols / 2; i++) {
                             float v0, v1;
@@ -565,7 +566,7 @@ static cudaError_t launch_mmq_t(const void* act, const void* wgt, float* C, int3
     p.dbg = getenv("QGEMM_MMQ_DBG") ? atoi(getenv("QGEMM_MMQ_DBG")) : 0;
     p.peer = peer ? *peer : PeerOut{};
     p.tma_out = 0;
-    if (p.peer.world > 1 && !sumi && ldc_t == 1 && T % 4 == 0 && ldc_f % 4 == 0 && !getenv("QGEMM_MMQ_NO_TMA_OUT")) {
+    if (p.peer.world > 1 && !p.peer.mc && !sumi && ldc_t == 1 && T % 4 == 0 && ldc_f % 4 == 0 && !getenv("QGEMM_MMQ_NO_TMA_OUT")) {
         p.tma_out = 1;
         for (int r = 0; r < p.peer.world; r++)
             if (reinterpret_cast<uintptr_t>(p.peer.C[r]) % 16 != 0) p.tma_out = 0;

@@ -408,6 +408,7 @@ static int make_peer_out(const qgemm_peers* peers, PeerOut* po) {
     *po = PeerOut{};
     po->world = peers->world; po->rank = peers->rank;
     for (int r = 0; r < peers->world; r++) { po->C[r] = peers->C[r]; po->flag[r] = peers->flag[r]; }
+    po->mc = peers->world > 1 ? peers->C_multicast : nullptr;
     po->done = peers->done; po->step = peers->step; po->lps = peers->launches_per_step; po->li = peers->wait_index;
     po->dbg = getenv("QGEMM_PEER_DBG") ? atoi(getenv("QGEMM_PEER_DBG")) : 0;
     return QGEMM_OK;

@@ -185,6 +185,7 @@ struct PeerOut {
     uint32_t* done;               // local CTA-completion counter (returns to 0 after each launch)
     const uint32_t* step;         // local step counter (qgemm_peer_step_advance)
     uint32_t lps, li;             // launches per step, launches of this step that must have landed first
+    float* mc;                    // NVLS multicast mapping of the same slice on every rank (nullptr: store per rank)
     long long moff[kMaxPeers];    // grouped launch: element offset of matrix m's slice from C[r]
     int dbg;                      // tuning aid: 1 skip wait, 2 local store only, 4 skip per-thread fence
 };
@@ -210,6 +211,7 @@ __device__ __forceinline__ void peer_store(const PeerOut& po, float* C, int64_t 
     if (po.world > 1) {
         idx += po.moff[m];
         if (po.dbg & 2) { po.C[po.rank][idx] = v; return; }
+        if (po.mc) { po.mc[idx] = v; return; }   // one store, replicated to every rank by the switch
 #pragma unroll 1
         for (int q = 0; q < po.world; q++) {   // staggered start: ranks do not all hit the same receiver first
             int r = po.rank + 1 + q;

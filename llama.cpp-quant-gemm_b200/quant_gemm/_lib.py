@@ -44,7 +44,7 @@ SYMBOLS = {
 class QgemmPeers(C.Structure):
     """struct qgemm_peers of include/qgemm.h"""
     _fields_ = [("world", _i), ("rank", _i), ("C", _p * 8), ("flag", _p * 8), ("done", _p), ("step", _p),
-                ("launches_per_step", _u32), ("launch_index", _u32), ("wait_index", _u32)]
+                ("launches_per_step", _u32), ("launch_index", _u32), ("wait_index", _u32), ("C_multicast", _p)]
 
 
 SYMBOLS.update({

@@ -12,6 +12,8 @@ multi-GPU code: this module is new functionality with no reference counterpart.
 """
 from __future__ import annotations
 
+import os
+
 from typing import Callable, Optional
 
 import torch
@@ -99,7 +101,8 @@ class PeerPlan:
     kernels do the rest (include/qgemm.h, qgemm_gemm_peers)."""
 
     def __init__(self, pool_floats: int, launches_per_step: int, device: torch.device,
-                 group: Optional[dist.ProcessGroup] = None, ctl_group: Optional[dist.ProcessGroup] = None):
+                 group: Optional[dist.ProcessGroup] = None, ctl_group: Optional[dist.ProcessGroup] = None,
+                 multicast: bool = True):
         import torch.distributed._symmetric_memory as symm_mem
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
@@ -114,6 +117,10 @@ class PeerPlan:
         self.flag_hdl = symm_mem.rendezvous(self.flags, self.group)
         self.pool_ptrs = list(self.pool_hdl.buffer_ptrs)
         self.flag_ptrs = list(self.flag_hdl.buffer_ptrs)
+        # NVLS: one multicast mapping of the pool bound on every rank -- a store to it lands everywhere
+        self.mc_ptr = 0
+        if multicast and not os.environ.get("QGEMM_NO_MULTICAST"):
+            self.mc_ptr = int(getattr(self.pool_hdl, "multicast_ptr", 0) or 0)
         self.done = torch.zeros(1, dtype=torch.int32, device=device)
         self.step = torch.zeros(1, dtype=torch.int32, device=device)
         self.cursor = 0
@@ -136,6 +143,7 @@ class PeerPlan:
         ps.done, ps.step = self.done.data_ptr(), self.step.data_ptr()
         ps.launches_per_step, ps.launch_index = self.lps, launch_index
         ps.wait_index = launch_index if wait_index is None else wait_index
+        ps.C_multicast = (self.mc_ptr + 4 * elem_offset) if self.mc_ptr else None
         return ps
 
     def end_step(self) -> None:

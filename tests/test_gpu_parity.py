@@ -543,6 +543,43 @@ def test_peer_store_protocol_prefill_single_gpu(qg, O, wt, T):
     assert int(flag[0]) == steps * 2 * world and int(done[0]) == 0 and int(step[0]) == steps
 
 
+@pytest.mark.parametrize("wt,T", [(qo.Q4_0, 1), (qo.Q8_0, 5), (qo.Q5_1, 128)])
+def test_peer_multicast_destination_single_gpu(qg, O, wt, T):
+    """qgemm_peers.C_multicast: one destination stands for every rank (on a real NVLS mapping the switch replicates
+    each store).  Here it is an ordinary buffer: it must receive exactly what the plain call computes, the per-rank
+    buffers must stay untouched, and the arrival accounting must not change."""
+    from quant_gemm import _lib
+    L = _lib.lib()
+    F, K, world = 300, 1024, 2
+    x, w = datagen.model_like(T, F, K, seed=270 + wt)
+    aq, wq = O.quantize_q8_1(x), O.quantize_weight(wt, w)
+    da, dw = dev(aq), dev(wq)
+    bufs = [torch.full((F, T), -2.0, device="cuda") for _ in range(world)]
+    mc = torch.full((F, T), -1.0, device="cuda")
+    flag = torch.zeros(32, dtype=torch.int32, device="cuda")
+    done = torch.zeros(1, dtype=torch.int32, device="cuda")
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ps = _lib.QgemmPeers()
+    ps.world, ps.rank = world, 0
+    for r in range(world):
+        ps.C[r] = bufs[r].data_ptr()
+        ps.flag[r] = flag.data_ptr()
+    ps.done, ps.step, ps.launches_per_step, ps.launch_index, ps.wait_index = done.data_ptr(), step.data_ptr(), 1, 0, 0
+    ps.C_multicast = mc.data_ptr()
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(2):
+        assert L.qgemm_gemm_peers(wt, da.data_ptr(), dw.data_ptr(), ps, T, F, K, 1, T, _lib.GEMM_STREAM_ALLOC, st) == 0
+        path = qg.last_path()
+        assert L.qgemm_peer_wait(ps, st) == 0
+        assert L.qgemm_peer_step_advance(step.data_ptr(), st) == 0
+    plain = host(qg.gemm(dw, da, F, T, K, wt, flags=path))
+    assert (bits(host(mc)) == bits(plain)).all()
+    check_c(host(mc), O.gemm(wt, aq, wq, layout="FT"), "multicast destination vs oracle")
+    for b in bufs:
+        assert (host(b) == -2.0).all()
+    assert int(flag[0]) == 2 * world and int(done[0]) == 0
+
+
 # ------------------------------------------------------------------------------------------
 # grouped decode launch (fused q/k/v, gate/up): identical to separate calls
 # ------------------------------------------------------------------------------------------
