@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(kMmqThreads, 1) mmq_kernel(const MmqParams p) 
             for (int kc = 0; kc < nkc; kc++) {
                 ptx::mbar_wait(&full[s], ph);  // scale slabs of this stage are visible
                 const uint8_t* st = smem + s * kStageBytes;
-#pragma unroll 1
+#pragma unroll (Fmt<WT>::m >= 0 ? 1 : 2)
                 for (int j = 0; j < kBlocksPerStage; j++) {
                     const int b = kc * kBlocksPerStage + j;
                     ptx::mbar_wait(&tfull[buf], tph);
