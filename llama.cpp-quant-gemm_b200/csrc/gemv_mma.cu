@@ -405,6 +405,149 @@ __global__ void __launch_bounds__(kMmaThreads, 1) gemv_mma_bigk_kernel(const Gem
 }
 
 // ---------------------------------------------------------------------------
+// Small batches, 9 <= T (passes of 8*NT tokens): the same weight stream with NT token tiles per pass, so a
+// weight fragment is unpacked once and feeds NT MMAs.  One CTA per SM, 16 consumer warps splitting K (NBW blocks
+// each, nb == 16 * NBW exactly), B fragments of all NT tiles in registers (NBW * NT * 2), whole 16-row tiles per
+// stage.  The CTA-wide barrier that ends a tile's reduction also proves its stage free, so thread 0 refills it right
+// there and no producer warp or "empty" barriers are needed.  Passes of 8 through the kernel above re-stream (from L2) and re-unpack the weights for every 8 tokens:
+// q4_0 11008x4096 T=32 took 36 us that way.
+// ---------------------------------------------------------------------------
+constexpr int kWideWarps = 16;
+constexpr int kWideThreads = kWideWarps * 32;   // no producer warp: 4 warps per SM sub-partition leave 128 registers per thread
+constexpr int kWideRedPitch = 40;   // floats per row of a warp's partial tile (32 tokens + pad: 2-way conflicts at most)
+constexpr int kWideSmemMax = 220 * 1024;
+
+struct GemvMmaWideParams {
+    const uint8_t* act;
+    const uint8_t* wgt;
+    float* C;
+    int T, F, nb;         // T <= 8 * NT tokens of this pass
+    int64_t ldc_t, ldc_f;
+    int pitch, stages, pdl;
+};
+
+template <int WT, int NBW, int NT, bool kMsExact>
+__global__ void __launch_bounds__(kWideThreads, 1) gemv_mma_wide_kernel(const GemvMmaWideParams p) {
+    using Fm = Fmt<WT>;
+    constexpr int TOK = 8 * NT;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tig = lane & 3;
+    const int nb = p.nb;
+
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    float* red = reinterpret_cast<float*>(smem + 128);                                    // [16 warps][16 rows][kWideRedPitch]
+    constexpr uint32_t kRedBytes = kWideWarps * kMmaRows * kWideRedPitch * 4;
+    float2* a_sc = reinterpret_cast<float2*>(smem + 128 + kRedBytes);                     // [nb][TOK] (d_a, c_a)
+    const uint32_t stage_bytes = (uint32_t)kMmaRows * p.pitch;
+    uint8_t* stage0 = smem + ((128u + kRedBytes + (uint32_t)nb * TOK * 8u + 127u) & ~127u);
+
+    const int ntiles_total = (p.F + kMmaRows - 1) / kMmaRows;
+    const int t_begin = (int)(((int64_t)ntiles_total * blockIdx.x) / gridDim.x);
+    const int t_end = (int)(((int64_t)ntiles_total * (blockIdx.x + 1)) / gridDim.x);
+    const size_t rowbytes = (size_t)nb * Fm::bytes;
+
+    // one thread streams: tile `t` of this CTA goes to stage (t - t_begin) % stages, one bulk copy per weight row
+    auto issue_tile = [&](int t) {
+        const int st = (t - t_begin) % p.stages;
+        ptx::mbar_arrive_expect_tx(&full[st], (uint32_t)(kMmaRows * rowbytes));
+        for (int r = 0; r < kMmaRows; r++) {
+            const int f = min(t * kMmaRows + r, p.F - 1);  // tail tile: re-read a valid row, never stored
+            ptx::bulk_g2s(stage0 + (size_t)st * stage_bytes + (size_t)r * p.pitch, p.wgt + (size_t)f * rowbytes,
+                          (uint32_t)rowbytes, &full[st]);
+        }
+    };
+    if (tid == 0) {
+        for (int s = 0; s < p.stages; s++) ptx::mbar_init(&full[s], 1);
+        ptx::fence_mbar_init();
+        for (int t = t_begin; t < min(t_end, t_begin + p.stages); t++) issue_tile(t);   // weights never depend on the predecessor
+    }
+    __syncthreads();
+    if (p.pdl) ptx::griddep_launch_dependents();
+
+    if (p.pdl == 1) ptx::griddep_wait();
+    // B fragments: token 8j + g of tile j (zero beyond T), this warp's NBW blocks
+    uint32_t bf[NBW][NT][2];
+#pragma unroll
+    for (int i = 0; i < NBW; i++) {
+        const int b = warp * NBW + i;
+#pragma unroll
+        for (int j = 0; j < NT; j++) {
+            const int tok = 8 * j + g;
+            bf[i][j][0] = bf[i][j][1] = 0u;
+            if (tok < p.T) {
+                const uint32_t* q = reinterpret_cast<const uint32_t*>(p.act + ((size_t)tok * nb + b) * kQ81Bytes);
+                bf[i][j][0] = __ldg(q + 1 + tig);
+                bf[i][j][1] = __ldg(q + 5 + tig);
+            }
+        }
+    }
+    for (int i = tid; i < nb * TOK; i += kWideWarps * 32) {
+        const int b = i / TOK, t = i - b * TOK;
+        ActScale sc{0.f, 0.f};
+        if (t < p.T) {
+            const uint32_t ds = __ldg(reinterpret_cast<const uint32_t*>(p.act + ((size_t)t * nb + b) * kQ81Bytes));
+            sc = prep_act_scale<WT, kMsExact>(half_bits_to_float(ds), half_bits_to_float(ds >> 16));
+        }
+        a_sc[i] = make_float2(sc.d, sc.s);
+    }
+    ptx::bar_sync(1, kWideWarps * 32);
+
+    constexpr bool kSliceAl = (NBW * Fm::bytes) % 4 == 0;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int t = t_begin; t < t_end; t++) {
+        ptx::mbar_wait(&full[s], ph);
+        const uint8_t* r0 = stage0 + (size_t)s * stage_bytes + (size_t)g * p.pitch + (size_t)(warp * NBW) * Fm::bytes;
+        const uint8_t* r1 = r0 + (size_t)8 * p.pitch;
+        float acc[NT][4];
+#pragma unroll
+        for (int j = 0; j < NT; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll
+        for (int i = 0; i < NBW; i++) {
+            const int b = warp * NBW + i;
+            uint32_t a[4];
+            WScale w0, w1;
+            const bool al4 = kSliceAl && (i * Fm::bytes + Fm::qs) % 4 == 0 && (Fm::bits != 5 || (i * Fm::bytes + Fm::qh) % 4 == 0);
+            row_frag<WT>(r0 + (size_t)i * Fm::bytes, tig, a[0], a[2], w0, al4);
+            row_frag<WT>(r1 + (size_t)i * Fm::bytes, tig, a[1], a[3], w1, al4);
+#pragma unroll
+            for (int j = 0; j < NT; j++) {
+                int cc[4] = {0, 0, 0, 0};
+                if constexpr (Fm::bits == 8) mma_s8s8(cc, a, bf[i][j][0], bf[i][j][1]);
+                else mma_u8s8(cc, a, bf[i][j][0], bf[i][j][1]);
+                const float4 sc = *reinterpret_cast<const float4*>(&a_sc[b * TOK + 8 * j + 2 * tig]);
+                acc[j][0] = fold_block_pre<WT>(acc[j][0], cc[0], w0, ActScale{sc.x, sc.y});
+                acc[j][1] = fold_block_pre<WT>(acc[j][1], cc[1], w0, ActScale{sc.z, sc.w});
+                acc[j][2] = fold_block_pre<WT>(acc[j][2], cc[2], w1, ActScale{sc.x, sc.y});
+                acc[j][3] = fold_block_pre<WT>(acc[j][3], cc[3], w1, ActScale{sc.z, sc.w});
+            }
+        }
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+
+        // combine the 16 K-slices in warp order
+        float* rb = red + warp * (kMmaRows * kWideRedPitch);
+#pragma unroll
+        for (int j = 0; j < NT; j++) {
+            *reinterpret_cast<float2*>(&rb[g * kWideRedPitch + 8 * j + 2 * tig]) = make_float2(acc[j][0], acc[j][1]);
+            *reinterpret_cast<float2*>(&rb[(g + 8) * kWideRedPitch + 8 * j + 2 * tig]) = make_float2(acc[j][2], acc[j][3]);
+        }
+        ptx::bar_sync(1, kWideWarps * 32);
+        for (int o = tid; o < kMmaRows * TOK; o += kWideWarps * 32) {
+            const int row = o / TOK, tok = o - row * TOK;
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < kWideWarps; w++) v += red[w * (kMmaRows * kWideRedPitch) + row * kWideRedPitch + tok];
+            const int f = t * kMmaRows + row;
+            if (f < p.F && tok < p.T) p.C[(int64_t)tok * p.ldc_t + (int64_t)f * p.ldc_f] = v;
+        }
+        __syncthreads();   // partials consumed, and every warp is done with this tile's stage:
+        if (tid == 0 && t + p.stages < t_end) issue_tile(t + p.stages);   // refill it
+    }
+    if (p.pdl == 2) ptx::griddep_wait();
+}
+
+// ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 static int bigk_pitch(int wtype) {
@@ -508,10 +651,100 @@ static cudaError_t launch_mma_wt(const GemvMmaParams& p, size_t smem, int grid, 
     return launch_mma_inst<WT, 32>(p, smem, grid, ms, st);
 }
 
+// wide variant: K must fill the 16 warps' fragment slots exactly (K = 4096: NBW 8, K = 8192: NBW 16)
+static int wide_nbw(int nb) { return nb == 16 * 8 ? 8 : (nb == 16 * 16 ? 16 : 0); }
+static size_t wide_fixed(int nb, int nt) {
+    return 128 + (size_t)kWideWarps * kMmaRows * kWideRedPitch * 4 + (size_t)nb * nt * 64 + 128;
+}
+bool gemv_mma_wide_supported(int wtype, const void* act, const void* wgt, int T, int F, int K) {
+    const int nb = K / 32, nbw = wide_nbw(nb);
+    if (!nbw || T < 9 || F < 1 || block_bytes(wtype) == 0) return false;
+    if (reinterpret_cast<uintptr_t>(wgt) % 16 != 0 || reinterpret_cast<uintptr_t>(act) % 4 != 0) return false;
+    const int nt = nbw == 8 ? 4 : 2;
+    return wide_fixed(nb, nt) + 2 * (size_t)kMmaRows * mma_pitch(nb * block_bytes(wtype)) <= (size_t)kWideSmemMax;
+}
+
+template <int WT, int NBW, int NT>
+static cudaError_t launch_wide_inst(const GemvMmaWideParams& p, size_t smem, int grid, bool ms_exact, cudaStream_t st) {
+    auto launch = [&](auto kernel, int variant) -> cudaError_t {
+        static size_t attr_set[2] = {0, 0};
+        if (smem > attr_set[variant]) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            attr_set[variant] = smem;
+        }
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kWideThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = p.pdl ? 1 : 0;
+        return cudaLaunchKernelEx(&cfg, kernel, p);
+    };
+    cudaError_t e;
+    if constexpr (Fmt<WT>::m >= 0) {
+        e = ms_exact ? launch(gemv_mma_wide_kernel<WT, NBW, NT, true>, 1) : launch(gemv_mma_wide_kernel<WT, NBW, NT, false>, 0);
+    } else {
+        e = launch(gemv_mma_wide_kernel<WT, NBW, NT, false>, 0);
+    }
+    note_launch();
+    return e;
+}
+
+template <int WT>
+static cudaError_t launch_wide_wt(const GemvMmaWideParams& p, int nbw, int nt, size_t smem, int grid, bool ms, cudaStream_t st) {
+    if (nbw == 8) return nt == 4 ? launch_wide_inst<WT, 8, 4>(p, smem, grid, ms, st) : launch_wide_inst<WT, 8, 2>(p, smem, grid, ms, st);
+    return launch_wide_inst<WT, 16, 2>(p, smem, grid, ms, st);
+}
+
+// T tokens in passes of 8 * NT
+cudaError_t launch_gemv_mma_wide(int wtype, const void* act, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
+                                 int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t st) {
+    const int nb = K / 32, nbw = wide_nbw(nb);
+    if (!nbw) return cudaErrorInvalidValue;
+    const int nt_max = nbw == 8 ? 4 : 2;
+    const int pitch = mma_pitch(nb * block_bytes(wtype));
+    const int ntiles = (F + kMmaRows - 1) / kMmaRows;
+    const int grid = min(ntiles, num_sms);
+    const bool ms = flags & QGEMM_MS_EXACT;
+    for (int t0 = 0; t0 < T; t0 += 8 * nt_max) {
+        const int tp = min(8 * nt_max, T - t0);
+        const int nt = (nbw == 8 && tp > 16) ? 4 : 2;
+        const size_t fixed = wide_fixed(nb, nt);
+        int stages = (int)(((size_t)kWideSmemMax - fixed) / ((size_t)kMmaRows * pitch));
+        stages = max(2, min(kMmaStagesMax, min(stages, (ntiles + grid - 1) / grid + 1)));
+        GemvMmaWideParams p;
+        p.act = (const uint8_t*)act + (size_t)t0 * nb * kQ81Bytes;
+        p.wgt = (const uint8_t*)wgt;
+        p.C = C + (int64_t)t0 * ldc_t;
+        p.T = tp; p.F = F; p.nb = nb; p.ldc_t = ldc_t; p.ldc_f = ldc_f;
+        p.pitch = pitch; p.stages = stages;
+        p.pdl = (flags & QGEMM_WEIGHTS_STATIC) ? ((flags & QGEMM_INPUTS_READY) ? 2 : 1) : 0;
+        const size_t smem = fixed + (size_t)stages * kMmaRows * pitch;
+        cudaError_t e;
+        switch (wtype) {
+        case QGEMM_TYPE_Q4_0: e = launch_wide_wt<QGEMM_TYPE_Q4_0>(p, nbw, nt, smem, grid, ms, st); break;
+        case QGEMM_TYPE_Q4_1: e = launch_wide_wt<QGEMM_TYPE_Q4_1>(p, nbw, nt, smem, grid, ms, st); break;
+        case QGEMM_TYPE_Q5_0: e = launch_wide_wt<QGEMM_TYPE_Q5_0>(p, nbw, nt, smem, grid, ms, st); break;
+        case QGEMM_TYPE_Q5_1: e = launch_wide_wt<QGEMM_TYPE_Q5_1>(p, nbw, nt, smem, grid, ms, st); break;
+        case QGEMM_TYPE_Q8_0: e = launch_wide_wt<QGEMM_TYPE_Q8_0>(p, nbw, nt, smem, grid, ms, st); break;
+        default: e = cudaErrorInvalidValue;
+        }
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 // T tokens in passes of 8
 cudaError_t launch_gemv_mma(int wtype, const void* act, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
                             int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t st, const PeerOut* peer) {
     if (peer && T > 8) return cudaErrorInvalidValue;  // peer mode: one pass per launch
+    if (!peer && T > 8 && !getenv("QGEMM_MMA_NO_WIDE") && gemv_mma_wide_supported(wtype, act, wgt, T, F, K))
+        return launch_gemv_mma_wide(wtype, act, wgt, C, T, F, K, ldc_t, ldc_f, flags, num_sms, st);
     if (!regs_variant_supported(wtype, K / 32)) {      // long rows: fragments in smem, K-chunked stages
         const int nbk = K / 32;
         const int bp = bigk_pitch(wtype);

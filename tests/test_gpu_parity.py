@@ -448,6 +448,29 @@ def test_mma_skinny_vs_oracle(qg, O, wt, T, F, K):
     check_c(c, O.gemm(wt, aq, wq, layout="FT"), f"mma {qo.TYPE_NAMES[wt]} {T}x{F}x{K}")
 
 
+@pytest.mark.parametrize("wt", qo.WEIGHT_TYPES)
+@pytest.mark.parametrize("T,F,K", [(9, 130, 4096), (16, 256, 4096), (31, 100, 4096), (33, 64, 4096), (64, 48, 4096),
+                                   (95, 40, 4096), (12, 64, 8192), (40, 33, 8192)])
+def test_mma_wide_small_batch_vs_oracle(qg, O, wt, T, F, K):
+    """9 <= T < 96 at K = 4096 / 8192: several 8-token tiles per pass (gemv_mma_wide_kernel).  Same answers as the
+    passes of 8 it replaces, bit for bit is not required (different K split), the oracle bar is."""
+    x, w = datagen.model_like(T, F, K, seed=T * 7 + F)
+    aq, wq = O.quantize_q8_1(x), O.quantize_weight(wt, w)
+    c = run_gemm(qg, wt, aq, wq, "mma")
+    assert qg.last_path() == 0x300
+    check_c(c, O.gemm(wt, aq, wq, layout="FT"), f"mma wide {qo.TYPE_NAMES[wt]} {T}x{F}x{K}")
+    c_auto = run_gemm(qg, wt, aq, wq, "auto")
+    assert qg.last_path() == 0x300 and (bits(c_auto) == bits(c)).all()
+    # include/ convention (C[T,F]) through the same kernel
+    from quant_gemm import _lib
+    L = _lib.lib()
+    da, dw = dev(aq), dev(wq)
+    out = torch.empty((T, F), device="cuda")
+    assert L.qgemm_gemm(wt, da.data_ptr(), dw.data_ptr(), out.data_ptr(), T, F, K, F, 1, 0x300, None, 0,
+                        torch.cuda.current_stream().cuda_stream) == 0
+    assert (bits(host(out).T) == bits(c)).all()
+
+
 @pytest.mark.parametrize("wt", [qo.Q4_0, qo.Q5_1, qo.Q8_0])
 def test_mma_skinny_fuzz_and_auto(qg, O, wt):
     T, F, nb = 7, 200, 64
