@@ -658,7 +658,7 @@ static size_t wide_fixed(int nb, int nt) {
 }
 bool gemv_mma_wide_supported(int wtype, const void* act, const void* wgt, int T, int F, int K) {
     const int nb = K / 32, nbw = wide_nbw(nb);
-    if (!nbw || T < 9 || F < 1 || block_bytes(wtype) == 0) return false;
+    if (!nbw || T < 2 || F < 1 || block_bytes(wtype) == 0) return false;
     if (reinterpret_cast<uintptr_t>(wgt) % 16 != 0 || reinterpret_cast<uintptr_t>(act) % 4 != 0) return false;
     const int nt = nbw == 8 ? 4 : 2;
     return wide_fixed(nb, nt) + 2 * (size_t)kMmaRows * mma_pitch(nb * block_bytes(wtype)) <= (size_t)kWideSmemMax;
@@ -697,6 +697,7 @@ static cudaError_t launch_wide_inst(const GemvMmaWideParams& p, size_t smem, int
 
 template <int WT>
 static cudaError_t launch_wide_wt(const GemvMmaWideParams& p, int nbw, int nt, size_t smem, int grid, bool ms, cudaStream_t st) {
+    if (nt == 1) return nbw == 8 ? launch_wide_inst<WT, 8, 1>(p, smem, grid, ms, st) : launch_wide_inst<WT, 16, 1>(p, smem, grid, ms, st);
     if (nbw == 8) return nt == 4 ? launch_wide_inst<WT, 8, 4>(p, smem, grid, ms, st) : launch_wide_inst<WT, 8, 2>(p, smem, grid, ms, st);
     return launch_wide_inst<WT, 16, 2>(p, smem, grid, ms, st);
 }
@@ -713,7 +714,7 @@ cudaError_t launch_gemv_mma_wide(int wtype, const void* act, const void* wgt, fl
     const bool ms = flags & QGEMM_MS_EXACT;
     for (int t0 = 0; t0 < T; t0 += 8 * nt_max) {
         const int tp = min(8 * nt_max, T - t0);
-        const int nt = (nbw == 8 && tp > 16) ? 4 : 2;
+        const int nt = tp <= 8 ? 1 : ((nbw == 8 && tp > 16) ? 4 : 2);
         const size_t fixed = wide_fixed(nb, nt);
         int stages = (int)(((size_t)kWideSmemMax - fixed) / ((size_t)kMmaRows * pitch));
         stages = max(2, min(kMmaStagesMax, min(stages, (ntiles + grid - 1) / grid + 1)));
@@ -743,7 +744,11 @@ cudaError_t launch_gemv_mma_wide(int wtype, const void* act, const void* wgt, fl
 cudaError_t launch_gemv_mma(int wtype, const void* act, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
                             int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t st, const PeerOut* peer) {
     if (peer && T > 8) return cudaErrorInvalidValue;  // peer mode: one pass per launch
-    if (!peer && T > 8 && !getenv("QGEMM_MMA_NO_WIDE") && gemv_mma_wide_supported(wtype, act, wgt, T, F, K))
+    // T <= 8: the one-CTA-per-SM kernel wins only where the two-CTA one runs short of shared memory stages
+    // (measured: q8_0 11008x4096 12.5 -> 11.4 us at T=8; slower for the 4-bit formats and for small matrices)
+    const bool wide1 = wtype == QGEMM_TYPE_Q8_0 && (int64_t)F * K >= (1ll << 25);
+    if (!peer && (T > 8 || wide1 || getenv("QGEMM_MMA_WIDE1")) && !getenv("QGEMM_MMA_NO_WIDE") &&
+        gemv_mma_wide_supported(wtype, act, wgt, T, F, K))
         return launch_gemv_mma_wide(wtype, act, wgt, C, T, F, K, ldc_t, ldc_f, flags, num_sms, st);
     if (!regs_variant_supported(wtype, K / 32)) {      // long rows: fragments in smem, K-chunked stages
         const int nbk = K / 32;

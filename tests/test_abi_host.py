@@ -30,6 +30,22 @@ def test_header_symbols_are_exported(lib):
         assert hasattr(lib, name), name
 
 
+def test_peers_struct_layout_matches_header(tmp_path):
+    """The ctypes mirror of struct qgemm_peers has the size and field offsets a C compiler gives the header."""
+    import subprocess
+    from quant_gemm import _lib
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "qgemm.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(qgemm_peers), offsetof(qgemm_peers, C),'
+                   ' offsetof(qgemm_peers, flag), offsetof(qgemm_peers, done), offsetof(qgemm_peers, wait_index),'
+                   ' offsetof(qgemm_peers, C_multicast)); return 0;}\n')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    P = _lib.QgemmPeers
+    assert got == [C.sizeof(P), P.C.offset, P.flag.offset, P.done.offset, P.wait_index.offset, P.C_multicast.offset]
+
+
 def test_version_and_strings(lib):
     assert lib.qgemm_version() == 100
     for code in range(-5, 1):
