@@ -102,10 +102,8 @@ static MmqPack mmq_pack_layout(int F, int K) {
 //   a8[kc][t][16-byte chunk c ^ (t & 7)]            (chunk c = (b & 3) * 2 + {0, 1})
 //   as[t / 128][b][t % 128] = (d_a, coef * s_a)     coef: -8 (q4_0), -16 (q5_0), 1/4 or 1 (q4_1/q5_1), 0 (q8_0)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-mmq_repack_act_kernel(const uint8_t* __restrict__ act, uint8_t* __restrict__ a8, float2* __restrict__ as, int T,
-                      int Tpad, int nb, int nbp, float coef) {
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void repack_act_body(int64_t gid, const uint8_t* __restrict__ act, uint8_t* __restrict__ a8,
+                                                float2* __restrict__ as, int T, int Tpad, int nb, int nbp, float coef) {
     if (gid >= (int64_t)Tpad * nbp) return;
     // 4 consecutive lanes = the 4 blocks of one 128-byte operand row: contiguous reads (4 x 36 B) and
     // a contiguous 128-byte write per row, 8 rows per warp
@@ -127,17 +125,22 @@ mmq_repack_act_kernel(const uint8_t* __restrict__ act, uint8_t* __restrict__ a8,
     *reinterpret_cast<uint4*>(row + (((c + 1) ^ (t & 7)) << 4)) = q1;
     as[((size_t)(t / kBM) * nbp + b) * kBM + (t % kBM)] = sc;
 }
+__global__ void __launch_bounds__(256)
+mmq_repack_act_kernel(const uint8_t* __restrict__ act, uint8_t* __restrict__ a8, float2* __restrict__ as, int T,
+                      int Tpad, int nb, int nbp, float coef) {
+    ptx::griddep_launch_dependents();   // the GEMM kernel behind this one may set itself up while we run
+    repack_act_body((int64_t)blockIdx.x * blockDim.x + threadIdx.x, act, a8, as, T, Tpad, nb, nbp, coef);
+}
 
 // ---------------------------------------------------------------------------
 // prepass 2: weight blocks -> swizzled u8 (s8 for q8_0) tiles + d (+m) slabs
 //   w8[kc][f][chunk ^ (f & 7)],  ws[f / BN][b][f % BN] = d_w,  wm[...] = m_w
 // ---------------------------------------------------------------------------
 template <int WT>
-__global__ void __launch_bounds__(256)
-mmq_unpack_weight_kernel(const uint8_t* __restrict__ wgt, uint8_t* __restrict__ w8, float* __restrict__ ws,
-                         float* __restrict__ wm, int F, int Fpad, int nb, int nbp) {
+__device__ __forceinline__ void unpack_weight_body(int64_t gid, const uint8_t* __restrict__ wgt, uint8_t* __restrict__ w8,
+                                                   float* __restrict__ ws, float* __restrict__ wm, int F, int Fpad, int nb,
+                                                   int nbp) {
     using Fm = Fmt<WT>;
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (int64_t)Fpad * nbp) return;
     const int j4 = (int)(gid & 3);  // lanes 4i..4i+3 = the 4 blocks of one operand row (see the activation prepass)
     const int f = (int)((gid >> 2) % Fpad), b = (int)((gid >> 2) / Fpad) * 4 + j4;
@@ -155,6 +158,24 @@ mmq_unpack_weight_kernel(const uint8_t* __restrict__ wgt, uint8_t* __restrict__ 
     const size_t so = ((size_t)(f / kBN) * nbp + b) * kBN + (f % kBN);
     ws[so] = sc.d;
     if constexpr (Fm::m >= 0) wm[so] = sc.m;
+}
+template <int WT>
+__global__ void __launch_bounds__(256)
+mmq_unpack_weight_kernel(const uint8_t* __restrict__ wgt, uint8_t* __restrict__ w8, float* __restrict__ ws,
+                         float* __restrict__ wm, int F, int Fpad, int nb, int nbp) {
+    unpack_weight_body<WT>((int64_t)blockIdx.x * blockDim.x + threadIdx.x, wgt, w8, ws, wm, F, Fpad, nb, nbp);
+}
+// both prepasses as one launch: blocks [0, act_blocks) repack the activations, the rest unpack the weights
+template <int WT>
+__global__ void __launch_bounds__(256)
+mmq_prepass_kernel(const uint8_t* __restrict__ act, uint8_t* __restrict__ a8, float2* __restrict__ as, int T, int Tpad,
+                   float coef, const uint8_t* __restrict__ wgt, uint8_t* __restrict__ w8, float* __restrict__ ws,
+                   float* __restrict__ wm, int F, int Fpad, int nb, int nbp, unsigned act_blocks) {
+    ptx::griddep_launch_dependents();
+    if (blockIdx.x < act_blocks)
+        repack_act_body((int64_t)blockIdx.x * blockDim.x + threadIdx.x, act, a8, as, T, Tpad, nb, nbp, coef);
+    else
+        unpack_weight_body<WT>((int64_t)(blockIdx.x - act_blocks) * blockDim.x + threadIdx.x, wgt, w8, ws, wm, F, Fpad, nb, nbp);
 }
 
 // ---------------------------------------------------------------------------
@@ -307,6 +328,8 @@ __global__ void __launch_bounds__(kMmqThreads, 1) mmq_kernel(const MmqParams p) 
     __syncthreads();
     t5::fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::griddep_wait();   // launched behind the operand prepass with programmatic serialization: barriers and TMEM
+                           // were set up while it ran; from here on its output (and C) may be touched
 
     if (warp == 0) {
         // ===================== producer =====================
@@ -527,26 +550,24 @@ static cudaError_t launch_mmq_t(const void* act, const void* wgt, float* C, int3
     if (WT == QGEMM_TYPE_Q4_0) coef = -8.f;
     else if (WT == QGEMM_TYPE_Q5_0) coef = -16.f;
     else if (WT == QGEMM_TYPE_Q4_1 || WT == QGEMM_TYPE_Q5_1) coef = (flags & QGEMM_MS_EXACT) ? 1.f : 0.25f;
-    {
-        const int64_t n = (int64_t)L.Tpad * nbp;
-        mmq_repack_act_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
-            (const uint8_t*)act, base + L.a8, (float2*)(base + L.as), T, L.Tpad, nb, nbp, coef);
-        note_launch();
-    }
     const uint8_t* w8 = base + L.w8;
     const float* wsp = (const float*)(base + L.ws);
     const float* wmp = (const float*)(base + L.wm);
+    const unsigned act_blocks = (unsigned)(((int64_t)L.Tpad * nbp + 255) / 256);
     if (flags & QGEMM_WEIGHTS_PREPACKED) {  // `wgt` is a qgemm_prepack_weights() buffer: nothing to unpack
         const MmqPack P = mmq_pack_layout(F, K);
         w8 = (const uint8_t*)wgt + P.w8;
         wsp = (const float*)((const uint8_t*)wgt + P.ws);
         wmp = (const float*)((const uint8_t*)wgt + P.wm);
+        mmq_repack_act_kernel<<<act_blocks, 256, 0, st>>>((const uint8_t*)act, base + L.a8, (float2*)(base + L.as), T, L.Tpad,
+                                                          nb, nbp, coef);
     } else {
-        const int64_t n = (int64_t)L.Fpad * nbp;
-        mmq_unpack_weight_kernel<WT><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
-            (const uint8_t*)wgt, base + L.w8, (float*)(base + L.ws), (float*)(base + L.wm), F, L.Fpad, nb, nbp);
-        note_launch();
+        const unsigned w_blocks = (unsigned)(((int64_t)L.Fpad * nbp + 255) / 256);
+        mmq_prepass_kernel<WT><<<act_blocks + w_blocks, 256, 0, st>>>(
+            (const uint8_t*)act, base + L.a8, (float2*)(base + L.as), T, L.Tpad, coef, (const uint8_t*)wgt, base + L.w8,
+            (float*)(base + L.ws), (float*)(base + L.wm), F, L.Fpad, nb, nbp, act_blocks);
     }
+    note_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     static bool attr_done = false;
@@ -572,10 +593,21 @@ static cudaError_t launch_mmq_t(const void* act, const void* wgt, float* C, int3
             if (reinterpret_cast<uintptr_t>(p.peer.C[r]) % 16 != 0) p.tma_out = 0;
     }
     const int ntiles = p.tiles_m * p.tiles_n;
-    if (sumi) mmq_kernel<WT, true><<<min(ntiles, num_sms), kMmqThreads, kMmqSmem, st>>>(p);
-    else mmq_kernel<WT, false><<<min(ntiles, num_sms), kMmqThreads, p.tma_out ? kMmqSmemOut : kMmqSmem, st>>>(p);
+    // programmatic dependent launch behind the prepass (the kernel waits for it after its own setup)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(min(ntiles, num_sms));
+    cfg.blockDim = dim3(kMmqThreads);
+    cfg.dynamicSmemBytes = p.tma_out ? kMmqSmemOut : kMmqSmem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (sumi) e = cudaLaunchKernelEx(&cfg, mmq_kernel<WT, true>, p);
+    else e = cudaLaunchKernelEx(&cfg, mmq_kernel<WT, false>, p);
     note_launch();
-    return cudaGetLastError();
+    return e;
 }
 
 size_t mmq_prepack_bytes(int wtype, int F, int K) {
