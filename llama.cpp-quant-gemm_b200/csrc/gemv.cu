@@ -157,6 +157,7 @@ struct GemvParams {
     int stage_bytes;      // 128-byte multiple
     int pdl;              // programmatic dependent launch: 1 wait before the activations, 2 wait before exit
     int nocompute;        // tuning aid: stream the tiles, skip the math (memory-system ceiling)
+    int act_bulk;         // activations are 16-byte aligned and a 16-byte multiple: staged with one bulk copy
     PeerOut peer;         // fused all-gather (world <= 1: plain store to C)
     const uint8_t* pf_ptr; // next launch's weights to pull into L2 (or null)
     unsigned long long pf_bytes;
@@ -208,11 +209,13 @@ __global__ void __launch_bounds__(kGemvThreads, kGemvCtasPerSm) gemv_kernel(cons
     const int r_end = (int)(((int64_t)p.F * (blockIdx.x + 1)) / gridDim.x);
     const size_t rowbytes = (size_t)nb * Fm::bytes;
 
+    uint64_t* abar = reinterpret_cast<uint64_t*>(smem + 640);    // activation copy (free bytes between slots and a_raw)
     if (tid == 0) {
         for (int s = 0; s < p.stages; s++) {
             ptx::mbar_init(&full[s], 1);
             ptx::mbar_init(&empty[s], kGemvWarps);
         }
+        ptx::mbar_init(abar, 1);
         ptx::fence_mbar_init();
     }
     __syncthreads();
@@ -262,8 +265,16 @@ __global__ void __launch_bounds__(kGemvThreads, kGemvCtasPerSm) gemv_kernel(cons
         const uint32_t* a32 = reinterpret_cast<const uint32_t*>(p.act);
         uint32_t* dst = reinterpret_cast<uint32_t*>(a_raw);
         const int total = TT * nb * 9;
-        for (int i = tid; i < total; i += kGemvWarps * 32) dst[i] = __ldg(a32 + i);
-        ptx::bar_sync(1, kGemvWarps * 32);
+        if (p.act_bulk) {   // one bulk copy (TMA) instead of load / store / barrier through the registers
+            if (tid == 0) {
+                ptx::mbar_arrive_expect_tx(abar, (uint32_t)total * 4u);
+                ptx::bulk_g2s(a_raw, p.act, (uint32_t)total * 4u, abar);
+            }
+            ptx::mbar_wait(abar, 0);
+        } else {
+            for (int i = tid; i < total; i += kGemvWarps * 32) dst[i] = __ldg(a32 + i);
+            ptx::bar_sync(1, kGemvWarps * 32);
+        }
 #pragma unroll
         for (int j = 0; j < PPL; j++) {
             const int pg = (j * WPR + sub) * 32 + lane;
@@ -544,6 +555,8 @@ cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, i
         p.RT = cur.rt; p.WPR = cur.wpr; p.stages = cur.stages; p.stage_bytes = cur.stage_bytes;
         p.pdl = pdl ? ((flags & QGEMM_INPUTS_READY) ? 2 : 1) : 0;
         p.nocompute = getenv("QGEMM_GEMV_NOCOMPUTE") ? 1 : 0;
+        p.act_bulk = (reinterpret_cast<uintptr_t>(p.act) % 16 == 0 && ((size_t)cur.tt * nb * kQ81Bytes) % 16 == 0 &&
+                      !getenv("QGEMM_GEMV_NO_ACT_BULK")) ? 1 : 0;
         p.pf_ptr = (t0 + pl.tt >= T && reinterpret_cast<uintptr_t>(pf_ptr) % 16 == 0) ? (const uint8_t*)pf_ptr : nullptr;
         p.pf_bytes = pf_bytes;
         p.nmat = 0;
