@@ -34,6 +34,7 @@ namespace qgemm {
 constexpr int kGemvWarps = 8;                        // consumer warps
 constexpr int kGemvThreads = (kGemvWarps + 1) * 32;  // + 1 producer warp
 constexpr int kGemvMaxStages = 8;
+constexpr int kGemvInflightTarget = 56 * 1024;     // bytes of weight tiles a CTA keeps in flight (see gemv_plan)
 constexpr int kGemvActOff = (128 + 2 * kGemvWarps * 8 * 4 + 127) / 128 * 128;  // barriers + slots
 constexpr int kGemvSmemBudget = 110 * 1024;          // two CTAs per SM, always
 constexpr int kGemvCtasPerSm = 2;
@@ -468,6 +469,11 @@ static bool gemv_plan(int wtype, int T, int F, int K, int grid, bool pdl, GemvPl
         // shared memory when possible so the next launch's CTA can move in early
         const int rows_per_cta = (F + grid - 1) / grid;
         stages = max(2, min(stages, (rows_per_cta + rt - 1) / rt));
+        // A CTA's stream is short (a few tiles), and every bulk copy in flight shares the CTA's bandwidth: with the
+        // whole ring issued at once the FIRST tile arrives late and the consumers start late.  ~56 KB in flight per
+        // CTA (2 x 296 CTAs = 16 MB, still more than HBM latency x bandwidth) measured best: q4_0 11008x4096 T=1
+        // 7.1 -> 6.2 us, decode stack +2.3 % (A/B on one box).
+        stages = max(2, min(stages, kGemvInflightTarget / stage_bytes));
         (void)pdl;
         if (const char* e = getenv("QGEMM_GEMV_STAGES")) stages = max(2, min(kGemvMaxStages, atoi(e)));  // tuning aid
         *pl = {tt, ppl, wpr, rt, stages, stage_bytes, fixed + (size_t)stages * stage_bytes};
