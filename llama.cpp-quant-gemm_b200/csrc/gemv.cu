@@ -451,7 +451,7 @@ static bool gemv_plan(int wtype, int T, int F, int K, int grid, bool pdl, GemvPl
             const int need = (np + 32 * w - 1) / (32 * w);
             if (need * tt <= 3) { ppl = need; wpr = w; break; }  // <= 60 activation registers
         }
-        if (getenv("QGEMM_GEMV_FORCE_SMEM")) ppl = 0;  // tuning aid
+        if (QGEMM_ENV("QGEMM_GEMV_FORCE_SMEM")) ppl = 0;  // tuning aid
         if (ppl == 0) {  // smem activations: spread long rows over more warps
             wpr = 1;
             while (wpr < kGemvWarps && np > 64 * wpr) wpr <<= 1;
@@ -459,7 +459,7 @@ static bool gemv_plan(int wtype, int T, int F, int K, int grid, bool pdl, GemvPl
         const int rpp = kGemvWarps / wpr;
         int rt = rpp;
         while (rt < 8 && (size_t)(2 * rt) * rowbytes <= (size_t)kGemvTileTarget) rt <<= 1;
-        if (const char* e = getenv("QGEMM_GEMV_RT")) rt = max(rpp, atoi(e) / rpp * rpp);  // tuning aid
+        if (const char* e = QGEMM_ENV("QGEMM_GEMV_RT")) rt = max(rpp, atoi(e) / rpp * rpp);  // tuning aid
         const int stage_bytes = (int)(((size_t)rt * rowbytes + 127) / 128 * 128);
         const size_t fixed = kGemvActOff + (size_t)tt * nb * (ppl == 0 ? 40 : 36) + 128;
         if (fixed + 2 * (size_t)stage_bytes > (size_t)kGemvSmemBudget) continue;
@@ -475,7 +475,7 @@ static bool gemv_plan(int wtype, int T, int F, int K, int grid, bool pdl, GemvPl
         // 7.1 -> 6.2 us, decode stack +2.3 % (A/B on one box).
         stages = max(2, min(stages, kGemvInflightTarget / stage_bytes));
         (void)pdl;
-        if (const char* e = getenv("QGEMM_GEMV_STAGES")) stages = max(2, min(kGemvMaxStages, atoi(e)));  // tuning aid
+        if (const char* e = QGEMM_ENV("QGEMM_GEMV_STAGES")) stages = max(2, min(kGemvMaxStages, atoi(e)));  // tuning aid
         *pl = {tt, ppl, wpr, rt, stages, stage_bytes, fixed + (size_t)stages * stage_bytes};
         return true;
     }
@@ -546,7 +546,7 @@ cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, i
     const bool ms = flags & QGEMM_MS_EXACT;
     GemvPlan pl;
     int ctas_per_sm = kGemvCtasPerSm;
-    if (const char* e = getenv("QGEMM_GEMV_CTAS")) ctas_per_sm = max(1, min(kGemvCtasPerSm, atoi(e)));  // tuning aid
+    if (const char* e = QGEMM_ENV("QGEMM_GEMV_CTAS")) ctas_per_sm = max(1, min(kGemvCtasPerSm, atoi(e)));  // tuning aid
     const int grid = min(F, ctas_per_sm * num_sms);
     const bool pdl = flags & QGEMM_WEIGHTS_STATIC;
     if (!gemv_plan(wtype, T, F, K, grid, pdl, &pl)) return cudaErrorInvalidValue;
@@ -560,9 +560,9 @@ cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, i
         p.F = F; p.nb = nb; p.ldc_t = ldc_t; p.ldc_f = ldc_f;
         p.RT = cur.rt; p.WPR = cur.wpr; p.stages = cur.stages; p.stage_bytes = cur.stage_bytes;
         p.pdl = pdl ? ((flags & QGEMM_INPUTS_READY) ? 2 : 1) : 0;
-        p.nocompute = getenv("QGEMM_GEMV_NOCOMPUTE") ? 1 : 0;
+        p.nocompute = QGEMM_ENV("QGEMM_GEMV_NOCOMPUTE") ? 1 : 0;
         p.act_bulk = (reinterpret_cast<uintptr_t>(p.act) % 16 == 0 && ((size_t)cur.tt * nb * kQ81Bytes) % 16 == 0 &&
-                      !getenv("QGEMM_GEMV_NO_ACT_BULK")) ? 1 : 0;
+                      !QGEMM_ENV("QGEMM_GEMV_NO_ACT_BULK")) ? 1 : 0;
         p.pf_ptr = (t0 + pl.tt >= T && reinterpret_cast<uintptr_t>(pf_ptr) % 16 == 0) ? (const uint8_t*)pf_ptr : nullptr;
         p.pf_bytes = pf_bytes;
         p.nmat = 0;

@@ -747,7 +747,7 @@ cudaError_t launch_gemv_mma(int wtype, const void* act, const void* wgt, float* 
     // T <= 8: the one-CTA-per-SM kernel wins only where the two-CTA one runs short of shared memory stages
     // (measured: q8_0 11008x4096 12.5 -> 11.4 us at T=8; slower for the 4-bit formats and for small matrices)
     const bool wide1 = wtype == QGEMM_TYPE_Q8_0 && (int64_t)F * K >= (1ll << 25);
-    if (!peer && (T > 8 || wide1 || getenv("QGEMM_MMA_WIDE1")) && !getenv("QGEMM_MMA_NO_WIDE") &&
+    if (!peer && (T > 8 || wide1 || QGEMM_ENV("QGEMM_MMA_WIDE1")) && !QGEMM_ENV("QGEMM_MMA_NO_WIDE") &&
         gemv_mma_wide_supported(wtype, act, wgt, T, F, K))
         return launch_gemv_mma_wide(wtype, act, wgt, C, T, F, K, ldc_t, ldc_f, flags, num_sms, st);
     if (!regs_variant_supported(wtype, K / 32)) {      // long rows: fragments in smem, K-chunked stages
@@ -790,8 +790,8 @@ cudaError_t launch_gemv_mma(int wtype, const void* act, const void* wgt, float* 
     const size_t fixed = mma_fixed(nb);
     int stages = (int)(((size_t)kMmaSmemBudget - fixed) / ((size_t)kMmaRows * pitch));
     stages = max(2, min(kMmaStagesMax, stages));
-    if (const char* e = getenv("QGEMM_MMA_STAGES")) stages = max(2, min(stages, atoi(e)));  // tuning aid
-    const int span = getenv("QGEMM_MMA_SPAN") ? 1 : 0;
+    if (const char* e = QGEMM_ENV("QGEMM_MMA_STAGES")) stages = max(2, min(stages, atoi(e)));  // tuning aid
+    const int span = QGEMM_ENV("QGEMM_MMA_SPAN") ? 1 : 0;
     const int ntiles = (F + kMmaRows - 1) / kMmaRows;
     const int grid = span ? min(F, 2 * num_sms) : min(ntiles, 2 * num_sms);
     const int chunks_per_cta = (span ? ((F + grid - 1) / grid + kMmaRows - 1) / kMmaRows : (ntiles + grid - 1) / grid) * ((nb + cb - 1) / cb);

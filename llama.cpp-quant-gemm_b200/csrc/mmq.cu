@@ -584,10 +584,10 @@ static cudaError_t launch_mmq_t(const void* act, const void* wgt, float* C, int3
     p.T = T; p.F = F; p.nb = nb; p.nkc = L.nkc; p.Tpad = L.Tpad; p.Fpad = L.Fpad;
     p.ldc_t = ldc_t; p.ldc_f = ldc_f;
     p.tiles_m = L.Tpad / kBM; p.tiles_n = L.Fpad / kBN;
-    p.dbg = getenv("QGEMM_MMQ_DBG") ? atoi(getenv("QGEMM_MMQ_DBG")) : 0;
+    p.dbg = QGEMM_ENV("QGEMM_MMQ_DBG") ? atoi(QGEMM_ENV("QGEMM_MMQ_DBG")) : 0;
     p.peer = peer ? *peer : PeerOut{};
     p.tma_out = 0;
-    if (p.peer.world > 1 && !p.peer.mc && !sumi && ldc_t == 1 && T % 4 == 0 && ldc_f % 4 == 0 && !getenv("QGEMM_MMQ_NO_TMA_OUT")) {
+    if (p.peer.world > 1 && !p.peer.mc && !sumi && ldc_t == 1 && T % 4 == 0 && ldc_f % 4 == 0 && !QGEMM_ENV("QGEMM_MMQ_NO_TMA_OUT")) {
         p.tma_out = 1;
         for (int r = 0; r < p.peer.world; r++)
             if (reinterpret_cast<uintptr_t>(p.peer.C[r]) % 16 != 0) p.tma_out = 0;

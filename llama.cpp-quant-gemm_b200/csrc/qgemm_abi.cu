@@ -410,7 +410,7 @@ static int make_peer_out(const qgemm_peers* peers, PeerOut* po) {
     for (int r = 0; r < peers->world; r++) { po->C[r] = peers->C[r]; po->flag[r] = peers->flag[r]; }
     po->mc = peers->world > 1 ? peers->C_multicast : nullptr;
     po->done = peers->done; po->step = peers->step; po->lps = peers->launches_per_step; po->li = peers->wait_index;
-    po->dbg = getenv("QGEMM_PEER_DBG") ? atoi(getenv("QGEMM_PEER_DBG")) : 0;
+    po->dbg = QGEMM_ENV("QGEMM_PEER_DBG") ? atoi(QGEMM_ENV("QGEMM_PEER_DBG")) : 0;
     return QGEMM_OK;
 }
 

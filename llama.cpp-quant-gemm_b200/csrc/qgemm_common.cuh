@@ -4,6 +4,7 @@
 // Formats are llama.cpp's (reference: compat/ggml_types.h:62-191); blocks are
 // addressed as raw bytes here because weight blocks are only 2-byte aligned.
 #pragma once
+#include <cstdlib>
 
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -237,6 +238,12 @@ __device__ __forceinline__ void peer_signal_done(const PeerOut& po, unsigned gri
         }
     }
 }
+
+// ---------------------------------------------------------------------------
+// Tuning aids (QGEMM_* environment overrides used by profiles/ and the experiments DESIGN.md cites): read once
+// per process and call site, never on the launch path after the first call.
+// ---------------------------------------------------------------------------
+#define QGEMM_ENV(name) ([]() -> const char* { static const char* const v = getenv(name); return v; }())
 
 // ---------------------------------------------------------------------------
 // Host-side launch bookkeeping (defined in qgemm_abi.cu)
