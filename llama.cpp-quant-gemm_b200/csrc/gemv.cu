@@ -485,13 +485,8 @@ static bool gemv_plan(int wtype, int T, int F, int K, int grid, bool pdl, GemvPl
 template <int WT, int TT, int PPL>
 static cudaError_t launch_gemv_inst(const GemvParams& p, size_t smem, int grid, bool ms_exact, cudaStream_t st) {
     auto launch = [&](auto kernel, int variant) -> cudaError_t {
-        static size_t attr_set[4] = {0, 0, 0, 0};  // per (WT,TT,PPL) x variant; grows monotonically
-        size_t& cur = attr_set[variant];
-        if (smem > cur) {
-            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            cur = smem;
-        }
+        (void)variant;
+        if (cudaError_t e = smem_optin(reinterpret_cast<const void*>(kernel), smem)) return e;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(grid);
         cfg.blockDim = dim3(kGemvThreads);

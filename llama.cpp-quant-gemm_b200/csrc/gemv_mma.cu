@@ -581,12 +581,8 @@ bool gemv_mma_supported(int wtype, const void* act, const void* wgt, int T, int 
 template <int WT>
 static cudaError_t launch_bigk(const GemvMmaBigParams& p, size_t smem, int grid, bool ms_exact, cudaStream_t st) {
     auto launch = [&](auto kernel, int variant) -> cudaError_t {
-        static size_t attr_set[2] = {0, 0};
-        if (smem > attr_set[variant]) {
-            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            attr_set[variant] = smem;
-        }
+        (void)variant;
+        if (cudaError_t e = smem_optin(reinterpret_cast<const void*>(kernel), smem)) return e;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(grid);
         cfg.blockDim = dim3(kMmaThreads);
@@ -613,12 +609,8 @@ template <int WT, int NBW>
 static cudaError_t launch_mma_inst(const GemvMmaParams& p, size_t smem, int grid, bool ms_exact, cudaStream_t st) {
     constexpr int NC = mma_pick_nc(Fmt<WT>::bytes, NBW);
     auto launch = [&](auto kernel, int variant) -> cudaError_t {
-        static size_t attr_set[4] = {0, 0, 0, 0};
-        if (smem > attr_set[variant]) {
-            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            attr_set[variant] = smem;
-        }
+        (void)variant;
+        if (cudaError_t e = smem_optin(reinterpret_cast<const void*>(kernel), smem)) return e;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(grid);
         cfg.blockDim = dim3(kMmaThreads);
@@ -667,12 +659,8 @@ bool gemv_mma_wide_supported(int wtype, const void* act, const void* wgt, int T,
 template <int WT, int NBW, int NT>
 static cudaError_t launch_wide_inst(const GemvMmaWideParams& p, size_t smem, int grid, bool ms_exact, cudaStream_t st) {
     auto launch = [&](auto kernel, int variant) -> cudaError_t {
-        static size_t attr_set[2] = {0, 0};
-        if (smem > attr_set[variant]) {
-            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            attr_set[variant] = smem;
-        }
+        (void)variant;
+        if (cudaError_t e = smem_optin(reinterpret_cast<const void*>(kernel), smem)) return e;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(grid);
         cfg.blockDim = dim3(kWideThreads);

@@ -570,13 +570,9 @@ static cudaError_t launch_mmq_t(const void* act, const void* wgt, float* C, int3
     note_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    static bool attr_done = false;
-    if (!attr_done) {
-        e = cudaFuncSetAttribute(mmq_kernel<WT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmqSmemOut);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(mmq_kernel<WT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmqSmem);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+    e = sumi ? smem_optin(reinterpret_cast<const void*>(mmq_kernel<WT, true>), kMmqSmem)
+             : smem_optin(reinterpret_cast<const void*>(mmq_kernel<WT, false>), kMmqSmemOut);
+    if (e != cudaSuccess) return e;
     MmqParams p;
     p.a8 = base + L.a8; p.as = (const float2*)(base + L.as);
     p.w8 = w8; p.ws = wsp; p.wm = wmp;

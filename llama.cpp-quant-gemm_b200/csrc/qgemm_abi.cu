@@ -3,7 +3,9 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
 #include <mutex>
+#include <utility>
 
 #include "qgemm_common.cuh"
 
@@ -88,6 +90,22 @@ static bool is_weight_type(int t) {
 }
 static bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+cudaError_t smem_optin(const void* kernel, size_t smem) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> done;   // (device, kernel) -> bytes already granted
+    int d = 0;
+    cudaError_t e = cudaGetDevice(&d);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& cur = done[{d, kernel}];
+    if (smem > cur) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        cur = smem;
+    }
+    return cudaSuccess;
+}
 
 // QGEMM_STREAM_ALLOC scratch comes from a pool of our own, one per device, that keeps its pages between
 // calls (release threshold = max).  The device's default pool trims at every synchronisation, which made

@@ -249,5 +249,7 @@ __device__ __forceinline__ void peer_signal_done(const PeerOut& po, unsigned gri
 // Host-side launch bookkeeping (defined in qgemm_abi.cu)
 // ---------------------------------------------------------------------------
 void note_launch(int n = 1);
+// Opt a kernel in to `smem` bytes of dynamic shared memory; remembered per (device, kernel), thread-safe.
+cudaError_t smem_optin(const void* kernel, size_t smem);
 
 }  // namespace qgemm
