@@ -146,13 +146,15 @@ def prepack_weights(weight_q: torch.Tensor, M: int, K: int, wtype: int) -> torch
     return packed
 
 
-def hint_next_weights(next_weight_q: torch.Tensor | None) -> None:
+def hint_next_weights(next_weight_q: torch.Tensor | None, nbytes: int | None = None) -> None:
     """Decode hint: the next gemm() call also prefetches `next_weight_q` (the weights of the GEMV after
-    it) into L2 while it runs.  No effect on results."""
+    it) into L2 while it runs.  `nbytes` overrides the length, for weights that lie back to back in one
+    allocation (the window may then run on into the matrices that follow).  No effect on results."""
     if next_weight_q is None:
         _lib.lib().qgemm_hint_next_weights(None, 0)
     else:
-        _lib.lib().qgemm_hint_next_weights(next_weight_q.data_ptr(), next_weight_q.numel() * next_weight_q.element_size())
+        n = next_weight_q.numel() * next_weight_q.element_size() if nbytes is None else int(nbytes)
+        _lib.lib().qgemm_hint_next_weights(next_weight_q.data_ptr(), n)
 
 
 def gemm(weight_q: torch.Tensor, activation_q: torch.Tensor, M: int, N: int, K: int, wtype: int,
