@@ -554,3 +554,42 @@ void qo_gemm_sumi(int wtype, const void *act_q8_1, const void *weight, int32_t *
                     qo_block_sumi(wtype, W + ((size_t)f * nb + b) * bs,
                                   A + ((size_t)t * nb + b) * 36);
 }
+
+/* ------------------------------------------------------------------------- */
+/* W4A16 / W8A16 (fp32 activations): gemm_reference.h:73-147,                  */
+/* gemm_cuda_naive.cuh:66-143.  Next-row groundwork.             */
+/* ------------------------------------------------------------------------- */
+void qo_gemm_f32act_dequant(int wtype, const float *act, const void *weight, float *C,
+                            int T, int F, int K, int64_t ldc_t, int64_t ldc_f, unsigned flags)
+{
+    const int nb = K / 32;
+    const size_t bs = qo_block_bytes(wtype);
+    const uint8_t *W = (const uint8_t *)weight;
+    const int fma = (flags & QO_GEMM_FMA) != 0;
+    for (int t = 0; t < T; t++) {
+        const float *a = act + (size_t)t * K;
+        for (int f = 0; f < F; f++) {
+            float sum = 0.0f;
+            for (int b = 0; b < nb; b++) {
+                const uint8_t *blk = W + ((size_t)f * nb + b) * bs;
+                const float d = qo_fp16_to_fp32(ld16(blk));
+                const float *ab = a + (size_t)b * 32;
+                if (wtype == QO_Q4_0) {
+                    for (int k = 0; k < 16; k++) {
+                        const int q0 = (blk[2 + k] & 0x0F) - 8, q1 = (blk[2 + k] >> 4) - 8;
+                        const float w0 = (float)q0 * d, w1 = (float)q1 * d;
+                        if (fma) { sum = fmaf(ab[k], w0, sum); sum = fmaf(ab[k + 16], w1, sum); }
+                        else { sum += ab[k] * w0; sum += ab[k + 16] * w1; }
+                    }
+                } else { /* Q8_0 */
+                    for (int k = 0; k < 32; k++) {
+                        const float w = (float)(int8_t)blk[2 + k] * d;
+                        if (fma) sum = fmaf(ab[k], w, sum);
+                        else sum += ab[k] * w;
+                    }
+                }
+            }
+            C[(int64_t)t * ldc_t + (int64_t)f * ldc_f] = sum;
+        }
+    }
+}

@@ -94,6 +94,16 @@ void qo_gemm(int wtype, const void *act_q8_1, const void *weight, float *C,
 void qo_gemm_sumi(int wtype, const void *act_q8_1, const void *weight, int32_t *sumi,
                   int T, int F, int K, int t0, int t1);
 
+/*
+ * SURVEY.md section 8(f).3 (next row, oracle half only -- no product kernel yet): fp32 activations against
+ * dequantized Q4_0 / Q8_0 weights, include/gemm_reference.h:73-147 (CPU) and
+ * include/gemm_cuda_naive.cuh:66-143 (GPU; QO_GEMM_FMA replays its mul+add contraction).
+ * C[t*ldc_t + f*ldc_f] = sum over blocks, then over k in the reference's order
+ * (Q4_0: element k, then k+16, for k = 0..15; Q8_0: k = 0..31), w = (q - 8) * d resp. q * d.
+ */
+void qo_gemm_f32act_dequant(int wtype, const float *act, const void *weight, float *C,
+                            int T, int F, int K, int64_t ldc_t, int64_t ldc_f, unsigned flags);
+
 #ifdef __cplusplus
 }
 #endif

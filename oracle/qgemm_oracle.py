@@ -82,6 +82,7 @@ class Oracle:
         L.qo_block_dot.argtypes = [_i, _p, _p, _u]
         L.qo_gemm.argtypes = [_i, _p, _p, _p, _i, _i, _i, _i64, _i64, _u, _i, _i]
         L.qo_gemm_sumi.argtypes = [_i, _p, _p, _p, _i, _i, _i, _i, _i]
+        L.qo_gemm_f32act_dequant.argtypes = [_i, _p, _p, _p, _i, _i, _i, _i64, _i64, _u]
 
     # -- scalars
     def f2h(self, x: float) -> int:
@@ -162,6 +163,22 @@ class Oracle:
                 th.join()
         return out
 
+    def gemm_f32act_dequant(self, wtype: int, act_f32: np.ndarray, weight: np.ndarray, *, layout: str = "TF",
+                            flags: int = 0) -> np.ndarray:
+        """W4A16 / W8A16 (oracle half): act float32 [T, K], weight uint8 [F, nb, bs] (Q4_0 / Q8_0)."""
+        assert wtype in (Q4_0, Q8_0)
+        act_f32 = np.ascontiguousarray(act_f32, dtype=np.float32)
+        weight = np.ascontiguousarray(weight, dtype=np.uint8)
+        T, K = act_f32.shape
+        F = weight.shape[0]
+        assert weight.shape[1] * 32 == K and weight.shape[2] == BLOCK_BYTES[wtype]
+        if layout == "TF":
+            out, ldc_t, ldc_f = np.empty((T, F), dtype=np.float32), F, 1
+        else:
+            out, ldc_t, ldc_f = np.empty((F, T), dtype=np.float32), 1, T
+        self.lib.qo_gemm_f32act_dequant(wtype, _ptr(act_f32), _ptr(weight), _ptr(out), T, F, K, ldc_t, ldc_f, flags)
+        return out
+
     def gemm_sumi(self, wtype: int, act: np.ndarray, weight: np.ndarray) -> np.ndarray:
         act = np.ascontiguousarray(act, dtype=np.uint8)
         weight = np.ascontiguousarray(weight, dtype=np.uint8)
@@ -189,6 +206,12 @@ class Reference:
             getattr(L, n).argtypes = [_p, _p, _i]
         L.ref_gemm_w4a8_reference.argtypes = [_p, _p, _p, _i, _i, _i]
         L.ref_gemm_w8a8_reference.argtypes = [_p, _p, _p, _i, _i, _i]
+        for n in ("ref_gemm_w4a16_reference", "ref_gemm_w8a16_reference"):
+            if hasattr(L, n):   # a prebuilt library from before the fp32-activation references were added lacks them
+                getattr(L, n).argtypes = [_p, _p, _p, _i, _i, _i]
+        for n in ("ref_gpu_gemm_w4a16_naive", "ref_gpu_gemm_w8a16_naive"):
+            if hasattr(L, n):
+                getattr(L, n).argtypes = [_p, _p, _p, _i, _i, _i, _p]
         L.ref_vec_dot_q4_0_q8_1.restype = _f
         L.ref_vec_dot_q4_0_q8_1.argtypes = [_i, _p, _p]
         L.ref_vec_dot_q8_0_q8_1.restype = _f
@@ -244,6 +267,17 @@ class Reference:
         out = np.empty((T, F), dtype=np.float32)
         fn = {Q4_0: self.lib.ref_gemm_w4a8_reference, Q8_0: self.lib.ref_gemm_w8a8_reference}[wtype]
         fn(_ptr(act), _ptr(weight), _ptr(out), T, F, nb * 32)
+        return out
+
+    def gemm_f32act_include(self, wtype: int, act_f32, weight) -> np.ndarray:
+        """include/gemm_reference.h:73-147 gemm_w4a16_reference / gemm_w8a16_reference: C[M=T, N=F]."""
+        act_f32 = np.ascontiguousarray(act_f32, dtype=np.float32)
+        weight = np.ascontiguousarray(weight, dtype=np.uint8)
+        T, K = act_f32.shape
+        F = weight.shape[0]
+        out = np.empty((T, F), dtype=np.float32)
+        fn = {Q4_0: self.lib.ref_gemm_w4a16_reference, Q8_0: self.lib.ref_gemm_w8a16_reference}[wtype]
+        fn(_ptr(act_f32), _ptr(weight), _ptr(out), T, F, K)
         return out
 
     def cpu_gemm(self, wtype: int, weight, act, threads: int = 1) -> np.ndarray:

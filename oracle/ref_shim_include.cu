@@ -34,6 +34,13 @@ void ref_gemm_w4a8_reference(const void* A, const void* B, float* C, int M, int 
 void ref_gemm_w8a8_reference(const void* A, const void* B, float* C, int M, int N, int K) {
     gemm_w8a8_reference((const block_q8_1*)A, (const block_q8_0*)B, C, M, N, K);
 }
+/* fp32-activation references (next row): A fp32 [M,K], B weights [N], C[M,N] */
+void ref_gemm_w4a16_reference(const float* A, const void* B, float* C, int M, int N, int K) {
+    gemm_w4a16_reference(A, (const block_q4_0*)B, C, M, N, K);
+}
+void ref_gemm_w8a16_reference(const float* A, const void* B, float* C, int M, int N, int K) {
+    gemm_w8a16_reference(A, (const block_q8_0*)B, C, M, N, K);
+}
 float ref_vec_dot_q4_0_q8_1(int n, const void* vx, const void* vy) { float s; vec_dot_q4_0_q8_1(n, &s, vx, vy); return s; }
 float ref_vec_dot_q8_0_q8_1(int n, const void* vx, const void* vy) { float s; vec_dot_q8_0_q8_1(n, &s, vx, vy); return s; }
 
@@ -49,6 +56,12 @@ void ref_gpu_gemm_w4a8_naive(const void* A, const void* B, float* C, int M, int 
 }
 void ref_gpu_gemm_w8a8_naive(const void* A, const void* B, float* C, int M, int N, int K, void* stream) {
     gemm_w8a8_naive((const block_q8_1*)A, (const block_q8_0*)B, C, M, N, K, (cudaStream_t)stream);
+}
+void ref_gpu_gemm_w4a16_naive(const float* A, const void* B, float* C, int M, int N, int K, void* stream) {
+    gemm_w4a16_naive(A, (const block_q4_0*)B, C, M, N, K, (cudaStream_t)stream);
+}
+void ref_gpu_gemm_w8a16_naive(const float* A, const void* B, float* C, int M, int N, int K, void* stream) {
+    gemm_w8a16_naive(A, (const block_q8_0*)B, C, M, N, K, (cudaStream_t)stream);
 }
 void ref_gpu_gemm_w4a8_tiled_dp4a(const void* A, const void* B, float* C, int M, int N, int K, void* stream) {
     gemm_w4a8_tiled_dp4a((const block_q8_1*)A, (const block_q4_0*)B, C, M, N, K, (cudaStream_t)stream);

@@ -58,6 +58,8 @@ def main():
             out[f"{name}_w_{n}_inc"] = wq
             out[f"{name}_c_{n}_TF_inc"] = R.gemm_include(wt, out[f"{name}_a_q8_1_ref"], wq)
             out[f"{name}_deq_{n}_inc"] = R.dequantize(wt, wq)
+            # fp32-activation references: gemm_w4a16_reference / gemm_w8a16_reference
+            out[f"{name}_c_{n}_TF_f32act"] = R.gemm_f32act_include(wt, x, wq)
     # 4. raw-block fuzz (benchmark_best.cu:31-55 style), every format
     nb = 8
     for wt in qo.WEIGHT_TYPES:
