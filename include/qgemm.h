@@ -228,7 +228,9 @@ QGEMM_API int qgemm_sumi(int wtype, const void *act_q8_1, const void *weight, in
  *     of the step have landed locally (wait_index = launch_index: everything before it);
  *     qgemm_peer_wait() does the same for the end of the current step.
  * C[r] / flag[r] are peer-mapped device pointers (e.g. torch symmetric memory, cudaIpc, or
- * cuMem fabric handles); flag words and `done`/`step` must start at zero.  T <= 8 only.
+ * cuMem fabric handles); flag words and `done`/`step` must start at zero.  Decode kernels for T <= 8,
+ * the tensor-core epilogue for larger T.  QGEMM_INPUTS_READY is ignored by the peer entries: their
+ * launches share one completion counter, so a launch must not run ahead of its predecessor.
  */
 #define QGEMM_MAX_PEERS 8
 typedef struct qgemm_peers {

@@ -35,7 +35,11 @@ constexpr int kGemvWarps = 8;                        // consumer warps
 constexpr int kGemvThreads = (kGemvWarps + 1) * 32;  // + 1 producer warp
 constexpr int kGemvMaxStages = 8;
 constexpr int kGemvInflightTarget = 56 * 1024;     // bytes of weight tiles a CTA keeps in flight (see gemv_plan)
-constexpr int kGemvActOff = (128 + 2 * kGemvWarps * 8 * 4 + 127) / 128 * 128;  // barriers + slots
+constexpr int kGemvSlotsOff = 128;                                         // after full[] / empty[]
+constexpr int kGemvAbarOff = kGemvSlotsOff + 2 * kGemvWarps * 8 * 4;      // mbarrier of the activation bulk copy
+constexpr int kGemvActOff = (kGemvAbarOff + 8 + 127) / 128 * 128;         // barriers + slots + abar
+static_assert(2 * kGemvMaxStages * 8 <= kGemvSlotsOff, "ring barriers overlap the slots");
+static_assert(kGemvAbarOff % 8 == 0 && kGemvAbarOff + 8 <= kGemvActOff, "abar must not overlap the bulk-copy destination");
 constexpr int kGemvSmemBudget = 110 * 1024;          // two CTAs per SM, always
 constexpr int kGemvCtasPerSm = 2;
 constexpr int kGemvMaxGroup = 8;                      // matrices per grouped launch
@@ -197,7 +201,7 @@ __global__ void __launch_bounds__(kGemvThreads, kGemvCtasPerSm) gemv_kernel(cons
     // ---- carve shared memory (integer offsets from the __shared__ base keep every access an LDS)
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);          // [kGemvMaxStages]
     uint64_t* empty = full + kGemvMaxStages;                     // [kGemvMaxStages]
-    float* slots = reinterpret_cast<float*>(smem + 128);         // [2][kGemvWarps][8] cross-warp partials
+    float* slots = reinterpret_cast<float*>(smem + kGemvSlotsOff);  // [2][kGemvWarps][8] cross-warp partials
     // PPL > 0 : raw q8_1 copy [TT][nb][36 B];  PPL == 0 : [TT][np] float4 scales + [TT][4][np] quads
     uint8_t* a_raw = smem + kGemvActOff;
     float4* a_scale = reinterpret_cast<float4*>(smem + kGemvActOff);
@@ -210,7 +214,7 @@ __global__ void __launch_bounds__(kGemvThreads, kGemvCtasPerSm) gemv_kernel(cons
     const int r_end = (int)(((int64_t)p.F * (blockIdx.x + 1)) / gridDim.x);
     const size_t rowbytes = (size_t)nb * Fm::bytes;
 
-    uint64_t* abar = reinterpret_cast<uint64_t*>(smem + 640);    // activation copy (free bytes between slots and a_raw)
+    uint64_t* abar = reinterpret_cast<uint64_t*>(smem + kGemvAbarOff);  // activation copy: own 8 bytes in front of a_raw
     if (tid == 0) {
         for (int s = 0; s < p.stages; s++) {
             ptx::mbar_init(&full[s], 1);
@@ -430,7 +434,10 @@ struct GemvPlan {
     size_t smem;
 };
 
-// Rows must be bulk-copyable: whole rows 16-byte multiples from a 16-byte aligned base.
+static bool gemv_plan(int wtype, int T, int F, int K, int grid, bool pdl, GemvPlan* pl);
+
+// Rows must be bulk-copyable: whole rows 16-byte multiples from a 16-byte aligned base, and at least a
+// one-token plan must fit the shared-memory budget (very long rows do not: those shapes belong to the next path).
 bool gemv_supported(int wtype, const void* act, const void* wgt, int F, int K) {
     const int nb = K / 32;
     const size_t rowbytes = (size_t)nb * block_bytes(wtype);
@@ -438,7 +445,8 @@ bool gemv_supported(int wtype, const void* act, const void* wgt, int F, int K) {
     if (rowbytes % 16 != 0 || rowbytes > 64 * 1024) return false;
     if (reinterpret_cast<uintptr_t>(wgt) % 16 != 0) return false;
     if (reinterpret_cast<uintptr_t>(act) % 4 != 0) return false;
-    return true;
+    GemvPlan pl;
+    return gemv_plan(wtype, 1, F, K, 1, false, &pl);
 }
 
 static bool gemv_plan(int wtype, int T, int F, int K, int grid, bool pdl, GemvPlan* pl) {
@@ -460,8 +468,12 @@ static bool gemv_plan(int wtype, int T, int F, int K, int grid, bool pdl, GemvPl
         int rt = rpp;
         while (rt < 8 && (size_t)(2 * rt) * rowbytes <= (size_t)kGemvTileTarget) rt <<= 1;
         if (const char* e = QGEMM_ENV("QGEMM_GEMV_RT")) rt = max(rpp, atoi(e) / rpp * rpp);  // tuning aid
-        const int stage_bytes = (int)(((size_t)rt * rowbytes + 127) / 128 * 128);
         const size_t fixed = kGemvActOff + (size_t)tt * nb * (ppl == 0 ? 40 : 36) + 128;
+        auto stage_of = [&](int r) { return (int)(((size_t)r * rowbytes + 127) / 128 * 128); };
+        // long rows: a tile may hold fewer rows than one pass covers (the other row slots idle) before the shape
+        // is given up to the next path
+        while (rt > 1 && fixed + 2 * (size_t)stage_of(rt) > (size_t)kGemvSmemBudget) rt >>= 1;
+        const int stage_bytes = stage_of(rt);
         if (fixed + 2 * (size_t)stage_bytes > (size_t)kGemvSmemBudget) continue;
         int stages = (int)(((size_t)kGemvSmemBudget - fixed) / stage_bytes);
         stages = max(2, min(kGemvMaxStages, stages));

@@ -452,6 +452,9 @@ int qgemm_gemm_group_peers(int wtype, const void* act_q8_1, int nmat, const void
     if (T < 1 || T > 8 || K < 32) return QGEMM_E_BADARG;
     DeviceInfo dev;
     if (int rc = device_check(&dev)) return rc;
+    // peer launches share one CTA-completion counter and the step word: a launch that runs ahead of its predecessor
+    // (INPUTS_READY) would mix its arrivals with the predecessor's, so the early-start promise is not honoured here
+    flags &= ~QGEMM_INPUTS_READY;
     cudaError_t e = launch_gemv(wtype, act_q8_1, nullptr, nullptr, T, Ftot, K, ldc_t, ldc_f, flags, dev.sms,
                                 (cudaStream_t)stream, &po, t_pf_ptr, t_pf_bytes, &g);
     t_pf_ptr = nullptr;
@@ -471,6 +474,7 @@ int qgemm_gemm_peers(int wtype, const void* act_q8_1, const void* weight, const 
     if (int rc = device_check(&dev)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
+    flags &= ~QGEMM_INPUTS_READY;  // see qgemm_gemm_group_peers
     if (T >= kMmaMinTokens && T <= 8 && gemv_mma_supported(wtype, act_q8_1, weight, T, F, K)) {
         e = launch_gemv_mma(wtype, act_q8_1, weight, C, T, F, K, ldc_t, ldc_f, flags, dev.sms, st, &po);
         t_last_path = QGEMM_PATH_MMA;
