@@ -29,6 +29,16 @@
 
 #include "ptx.cuh"
 #include "qgemm_common.cuh"
+#include "tc05.cuh"
+
+#ifdef QGEMM_MMQ_PROFILE
+#include <cstdio>
+#define PROF_DECL long long pf_wait = 0, pf_wait2 = 0, pf_t0 = clock64(), pf_n = 0
+#define PROF_WAIT(acc, stmt) do { const long long c0_ = clock64(); stmt; acc += clock64() - c0_; } while (0)
+#else
+#define PROF_DECL
+#define PROF_WAIT(acc, stmt) stmt
+#endif
 
 namespace qgemm {
 
@@ -178,105 +188,6 @@ mmq_prepass_kernel(const uint8_t* __restrict__ act, uint8_t* __restrict__ a8, fl
         unpack_weight_body<WT>((int64_t)(blockIdx.x - act_blocks) * blockDim.x + threadIdx.x, wgt, w8, ws, wm, F, Fpad, nb, nbp);
 }
 
-// ---------------------------------------------------------------------------
-// tcgen05 wrappers
-// ---------------------------------------------------------------------------
-namespace t5 {
-__device__ __forceinline__ void alloc(uint32_t* smem_slot, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(smem_slot)),
-                 "r"(cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void dealloc(uint32_t taddr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                     ptx::smem_u32(bar))
-                 : "memory");
-}
-// D[tmem] = A[smem] . B[smem]^T, 8-bit integer operands, s32 accumulate; overwrite (no accumulate)
-__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-}
-__device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// 32 lanes x 32 consecutive columns -> 32 registers per thread
-__device__ __forceinline__ void ld32(uint32_t taddr, int (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
-// K-major operand tile, 128-byte rows, SWIZZLE_128B, 8-row groups 1024 bytes apart
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)(1024u >> 4) << 32) | ((uint64_t)1 << 46) |
-           ((uint64_t)2 << 61);
-}
-}  // namespace t5
-
-// ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2: one issue slot, two IEEE results) ----
-__device__ __forceinline__ uint64_t pk(float lo, float hi) {
-    uint64_t r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpk(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
-    uint64_t d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
-    uint64_t d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
-    uint64_t d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-// s32 -> f32, exact for |x| < 2^22 (|sumi| <= 524288): integer add on the ALU pipe builds the
-// bits of 12582912 + x, one packed FADD removes the bias exactly.  kCvtMagic = 0 uses I2FP.
-#ifndef QGEMM_MMQ_CVT_MAGIC
-#define QGEMM_MMQ_CVT_MAGIC 0
-#endif
-__device__ __forceinline__ uint64_t cvt2(int x0, int x1) {
-#if QGEMM_MMQ_CVT_MAGIC == 2
-    return pk(__int_as_float(x0), __int_as_float(x1));  // timing experiment only: what the fold costs without a conversion
-#elif QGEMM_MMQ_CVT_MAGIC
-    const uint64_t biased = pk(__int_as_float(x0 + 0x4B400000), __int_as_float(x1 + 0x4B400000));
-    return fadd2(biased, pk(-12582912.0f, -12582912.0f));
-#else
-    return pk(__int2float_rn(x0), __int2float_rn(x1));
-#endif
-}
-// Two outputs of one token: same rounding sequence per element as fold_block_pre() (qgemm_common.cuh).
-template <int WT>
-__device__ __forceinline__ uint64_t fold_pair(uint64_t acc, int x0, int x1, uint64_t dw, uint64_t mw, uint64_t da, uint64_t ca) {
-    const uint64_t f = cvt2(x0, x1);
-    if constexpr (WT == QGEMM_TYPE_Q4_0 || WT == QGEMM_TYPE_Q5_0) {
-        return ffma2(dw, ffma2(da, f, ca), acc);
-    } else if constexpr (WT == QGEMM_TYPE_Q4_1 || WT == QGEMM_TYPE_Q5_1) {
-        return fadd2(acc, ffma2(fmul2(dw, da), f, fmul2(mw, ca)));
-    } else {
-        return ffma2(fmul2(dw, da), f, acc);
-    }
-}
-
 struct MmqParams {
     const uint8_t* a8;
     const float2* as;
@@ -336,10 +247,11 @@ __global__ void __launch_bounds__(kMmqThreads, 1) mmq_kernel(const MmqParams p) 
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
+            PROF_DECL;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int mt = tile % p.tiles_m, nt = tile / p.tiles_m;
                 for (int kc = 0; kc < nkc; kc++) {
-                    ptx::mbar_wait_backoff(&empty[s], ph ^ 1);
+                    PROF_WAIT(pf_wait, ptx::mbar_wait_backoff(&empty[s], ph ^ 1));
                     uint8_t* st = smem + s * kStageBytes;
                     constexpr uint32_t bytes = kBM * kKC + kBN * kKC + kBlocksPerStage * kBM * 8 +
                                                kBlocksPerStage * kBN * 4 * (Fmt<WT>::m >= 0 ? 2 : 1);
@@ -356,6 +268,9 @@ __global__ void __launch_bounds__(kMmqThreads, 1) mmq_kernel(const MmqParams p) 
                     if (++s == kMmqStages) { s = 0; ph ^= 1; }
                 }
             }
+#ifdef QGEMM_MMQ_PROFILE
+            if (blockIdx.x == 0 && (p.dbg & 32)) printf("producer: total %lld, waiting for empty %lld\n", clock64() - pf_t0, pf_wait);
+#endif
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
@@ -364,16 +279,17 @@ __global__ void __launch_bounds__(kMmqThreads, 1) mmq_kernel(const MmqParams p) 
                                    ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
         int s = 0, buf = 0;
         uint32_t ph = 0, tph = 0;
+        PROF_DECL;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             for (int kc = 0; kc < nkc; kc++) {
-                ptx::mbar_wait_backoff(&full[s], ph);
+                PROF_WAIT(pf_wait, ptx::mbar_wait_backoff(&full[s], ph));
                 t5::fence_after();
                 const uint32_t sa = ptx::smem_u32(smem + s * kStageBytes + kStageA);
                 const uint32_t sw = ptx::smem_u32(smem + s * kStageBytes + kStageW);
                 const uint64_t adesc = t5::smem_desc(sa), bdesc = t5::smem_desc(sw);
 #pragma unroll
                 for (int j = 0; j < kBlocksPerStage; j++) {
-                    ptx::mbar_wait_backoff(&tempty[buf], tph ^ 1);
+                    PROF_WAIT(pf_wait2, ptx::mbar_wait_backoff(&tempty[buf], tph ^ 1));
                     t5::fence_after();
                     if (lane == 0) {
                         // one instruction = one quantization block (K = 32 bytes = +2 in the >>4 address field)
@@ -389,6 +305,9 @@ __global__ void __launch_bounds__(kMmqThreads, 1) mmq_kernel(const MmqParams p) 
                 if (++s == kMmqStages) { s = 0; ph ^= 1; }
             }
         }
+#ifdef QGEMM_MMQ_PROFILE
+        if (blockIdx.x == 0 && lane == 0 && (p.dbg & 32)) printf("mma: total %lld, waiting for full %lld, for tempty %lld\n", clock64() - pf_t0, pf_wait, pf_wait2);
+#endif
     } else if (warp >= 4) {
         // ===================== epilogue =====================
         const int ew = warp - 4;
@@ -399,18 +318,19 @@ __global__ void __launch_bounds__(kMmqThreads, 1) mmq_kernel(const MmqParams p) 
         static_assert(kEpiCols == 32, "one tcgen05.ld.x32 per block per thread");
         int s = 0, buf = 0;
         uint32_t ph = 0, tph = 0;
+        PROF_DECL;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int mt = tile % p.tiles_m, nt = tile / p.tiles_m;
             uint64_t acc[kEpiCols / 2];  // fp32 accumulators as packed pairs (columns 2i, 2i+1)
 #pragma unroll
             for (int i = 0; i < kEpiCols / 2; i++) acc[i] = 0ull;
             for (int kc = 0; kc < nkc; kc++) {
-                ptx::mbar_wait(&full[s], ph);  // scale slabs of this stage are visible
+                PROF_WAIT(pf_wait, ptx::mbar_wait(&full[s], ph));  // scale slabs of this stage are visible
                 const uint8_t* st = smem + s * kStageBytes;
 #pragma unroll (Fmt<WT>::m >= 0 ? 1 : 2)
                 for (int j = 0; j < kBlocksPerStage; j++) {
                     const int b = kc * kBlocksPerStage + j;
-                    ptx::mbar_wait(&tfull[buf], tph);
+                    PROF_WAIT(pf_wait2, ptx::mbar_wait(&tfull[buf], tph));
                     t5::fence_after();
                     int x[kEpiCols];
                     t5::ld32(tmem_base + lane_addr + buf * kBN + cgrp * kEpiCols, x);
@@ -509,6 +429,9 @@ __global__ void __launch_bounds__(kMmqThreads, 1) mmq_kernel(const MmqParams p) 
                 }
             }
         }
+#ifdef QGEMM_MMQ_PROFILE
+        if (blockIdx.x == 0 && lane == 0 && (p.dbg & 32) && (ew == 0 || ew == 15)) printf("epilogue warp %d: total %lld, waiting for full %lld, for tfull %lld\n", ew, clock64() - pf_t0, pf_wait, pf_wait2);
+#endif
         if constexpr (!kDump) {
             if (p.tma_out && lane == 0) {   // every bulk store of this thread is complete before the CTA signals
                 ptx::bulk_wait_all();
@@ -539,6 +462,11 @@ size_t mmq_workspace_bytes(int wtype, int T, int F, int K) {
     return mmq_layout(T, F, K).total;
 }
 
+bool mmq_native_supported(int wtype, const void* wgt, int T, int F, int K);
+cudaError_t launch_mmq_native(int wtype, const uint8_t* a8, const float2* as, const void* wgt, float* C, int32_t* sumi, int T,
+                              int F, int K, int Tpad, int64_t ldc_t, int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t st,
+                              const PeerOut* peer);
+
 template <int WT>
 static cudaError_t launch_mmq_t(const void* act, const void* wgt, float* C, int32_t* sumi, int T, int F, int K,
                                 int64_t ldc_t, int64_t ldc_f, uint32_t flags, void* ws, int num_sms, cudaStream_t st,
@@ -554,6 +482,15 @@ static cudaError_t launch_mmq_t(const void* act, const void* wgt, float* C, int3
     const float* wsp = (const float*)(base + L.ws);
     const float* wmp = (const float*)(base + L.wm);
     const unsigned act_blocks = (unsigned)(((int64_t)L.Tpad * nbp + 255) / 256);
+    if (!(flags & QGEMM_WEIGHTS_PREPACKED) && mmq_native_supported(WT, wgt, T, F, K) && !QGEMM_ENV("QGEMM_MMQ_LEGACY")) {
+        // native blocks are unpacked inside the kernel (mmq_native.cu): only the activations are repacked per call
+        mmq_repack_act_kernel<<<act_blocks, 256, 0, st>>>((const uint8_t*)act, base + L.a8, (float2*)(base + L.as), T, L.Tpad,
+                                                          nb, nbp, coef);
+        note_launch();
+        if (cudaError_t e = cudaGetLastError()) return e;
+        return launch_mmq_native(WT, base + L.a8, (const float2*)(base + L.as), wgt, C, sumi, T, F, K, L.Tpad, ldc_t, ldc_f, flags,
+                                 num_sms, st, peer);
+    }
     if (flags & QGEMM_WEIGHTS_PREPACKED) {  // `wgt` is a qgemm_prepack_weights() buffer: nothing to unpack
         const MmqPack P = mmq_pack_layout(F, K);
         w8 = (const uint8_t*)wgt + P.w8;

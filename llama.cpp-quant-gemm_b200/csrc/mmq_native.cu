@@ -1,0 +1,542 @@
+// mmq_native.cu -- prefill path (T >= 96), weights read in their NATIVE llama.cpp block layout.
+//
+// Same contraction as mmq.cu (one tcgen05.mma kind::i8 per quantization block, s32 block sums in TMEM, per-block scale
+// fold on the CUDA cores with the reference GPU kernel's FMA sequence, kernels/gemm/gemm_quant_formats.cuh:73-334), but the
+// 4/5/8-bit weight blocks are unpacked to the int8 operand tile INSIDE the kernel, in shared memory:
+//
+//   warps 0-15 epilogue: tcgen05.ld the s32 tiles (lane = token, 32 columns per thread) and fold them into fp32
+//              register accumulators in block order
+//   warps 16-17 unpack: per raw stage ONE 2-D TMA tensor load brings the next 8 raw blocks of the tile's 128 weight rows
+//              (box 128 x 144..272 bytes of the native matrix) into a raw ring; every thread then expands two rows of it
+//              -- nibbles / qh bits -> u8 (s8 for q8_0) -- straight into the 128-byte-swizzled K-major operand tile the
+//              UMMA descriptor expects, and drops d_w (m_w) into the scale slab of the stage.  No per-call weight
+//              prepass, no 2x workspace; the weight side of the L2 -> SM traffic shrinks from 1 byte to the native
+//              0.56 .. 1.06 bytes per element.
+//   warp 18    one elected thread issues the MMAs; TMEM is two halves of two block buffers each (2 x 2 x 128 columns),
+//              one commit per half
+//   warp 19    producer of the activation side: pre-swizzled s8 tile + (d_a, c_a) slab per operand stage (the activation
+//              prepass of mmq.cu; activations are reused by every weight tile, weights only by the token tiles)
+// The light, latency-critical roles sit in the highest warp ids: the issue arbiter favours them over the 16 math warps.
+//
+// Needs K % 256 == 0 (a raw stage is 8 blocks so that every format's row chunk is a 16-byte multiple) and a 16-byte
+// aligned weight base; other shapes take mmq.cu's prepass kernel.
+#include <cstdlib>
+
+#include <cuda.h>   // CUtensorMap + enums only; the encoder is looked up through the runtime, libcuda is not linked
+
+#include "tc05.cuh"
+
+#ifdef QGEMM_MMQ_PROFILE
+#include <cstdio>
+#define PROF_DECL long long pf_wait = 0, pf_wait2 = 0, pf_t0 = clock64()
+#define PROF_WAIT(acc, stmt) do { const long long c0_ = clock64(); stmt; acc += clock64() - c0_; } while (0)
+#else
+#define PROF_DECL
+#define PROF_WAIT(acc, stmt) stmt
+#endif
+
+namespace qgemm {
+namespace nat {
+
+constexpr int kBM = 128;            // tokens per tile = TMEM lanes
+constexpr int kBN = 128;            // weight rows per tile = TMEM columns per block buffer
+constexpr int kKC = 128;            // K elements per operand stage: 4 blocks, one 128-byte swizzle row
+constexpr int kBPS = 4;             // blocks per operand stage
+constexpr int kMaxStages = 3;       // operand ring
+constexpr int kMaxRaw = 3;          // raw ring (stage = 8 blocks of every row of the tile)
+constexpr int kRawBlocks = 8;
+constexpr int kEpiWarps = 16;       // warps 0-15: 4 per TMEM lane quarter, 32 columns each
+constexpr int kEpiCols = kBN / (kEpiWarps / 4);
+constexpr int kUnpackWarps = 2;     // warps 16-17: 64 threads, two weight rows each
+constexpr int kUT = kUnpackWarps * 32;
+constexpr int kRowsPerThread = kBN / kUT;
+constexpr int kWarpUnpack = kEpiWarps, kWarpMma = kWarpUnpack + kUnpackWarps, kWarpProd = kWarpMma + 1;
+constexpr int kThreads = (kWarpProd + 1) * 32;
+constexpr int kTmemCols = 512;
+
+// operand stage (bytes); tiles 1024-byte aligned for SWIZZLE_128B
+constexpr int kStageA = 0;                          // [128 tokens][128 B] s8
+constexpr int kStageW = kStageA + kBM * kKC;        // [128 rows][128 B] u8 / s8
+constexpr int kStageAS = kStageW + kBN * kKC;       // [4 blocks][128 tokens] float2 (d_a, c_a)
+constexpr int kStageWS = kStageAS + kBPS * kBM * 8; // [4 blocks][128 rows] float d_w
+constexpr int kStageWM = kStageWS + kBPS * kBN * 4; // [4 blocks][128 rows] float m_w
+constexpr int kStageBytes = kStageWM + kBPS * kBN * 4;
+static_assert(kStageBytes % 1024 == 0, "stage must keep 1024-byte alignment");
+constexpr int kBarBytes = 1024;    // barriers in front of the 1024-byte aligned stages
+constexpr int kOutTileBytes = kBM * kBN * 4;
+
+template <int WT> constexpr int raw_row_bytes() { return kRawBlocks * Fmt<WT>::bytes; }
+template <int WT> constexpr int raw_stage_bytes() { return kBN * raw_row_bytes<WT>(); }
+
+struct Params {
+    const uint8_t* a8;     // [nkc][Tpad][128] swizzled s8 (activation prepass)
+    const float2* as;      // [Tpad / 128][nbp][128] (d_a, c_a)
+    float* C;
+    int32_t* sumi;         // non-null: dump the raw s32 block sums instead of folding
+    int T, F, nb, nkc, Tpad;
+    int64_t ldc_t, ldc_f;
+    int tiles_m, tiles_n;
+    int stages, raw_stages;
+    int dbg;
+    PeerOut peer;
+    int tma_out;
+};
+
+// 2-D tensor load (TMA): box of the weight matrix viewed as [F][row bytes / 2] uint16 -> dense [128][box bytes] in smem
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            ptx::smem_u32(smem_dst)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(ptx::smem_u32(bar))
+        : "memory");
+}
+
+// ---- compile-time field extraction from a block's byte stream held as 32-bit words (word 0 = bytes 0..3) ----
+template <int OFF, int NW>
+__device__ __forceinline__ uint32_t word_at(const uint32_t (&y)[NW]) {
+    static_assert(OFF % 2 == 0 && OFF / 4 < NW, "field outside the block");
+    if constexpr (OFF % 4 == 0) {
+        return y[OFF / 4];
+    } else {
+        static_assert(OFF / 4 + 1 < NW, "misaligned word crosses the end of the run");
+        return __funnelshift_r(y[OFF / 4], y[OFF / 4 + 1], 16);
+    }
+}
+template <int OFF, int NW>
+__device__ __forceinline__ float half_at(const uint32_t (&y)[NW]) {
+    return half_bits_to_float(y[OFF / 4] >> ((OFF % 4) * 8));
+}
+
+// One weight block (J-th of the 4 of an operand stage) of row `row` -> two 16-byte chunks of the swizzled operand row
+// + the block's scale(s) in the slab.  y = the row's 4 blocks as 32-bit words (word 0 = bytes 0..3).
+template <int WT, int J, int NW>
+__device__ __forceinline__ void unpack_one(const uint32_t (&y)[NW], uint8_t* tile_row, int sw, float* ws, float* wm, int row) {
+    using Fm = Fmt<WT>;
+    constexpr int B = J * Fm::bytes;
+    uint32_t w[8];
+    if constexpr (Fm::bits == 8) {
+        w[0] = word_at<B + 2, NW>(y);  w[1] = word_at<B + 6, NW>(y);  w[2] = word_at<B + 10, NW>(y); w[3] = word_at<B + 14, NW>(y);
+        w[4] = word_at<B + 18, NW>(y); w[5] = word_at<B + 22, NW>(y); w[6] = word_at<B + 26, NW>(y); w[7] = word_at<B + 30, NW>(y);
+    } else {
+        const uint32_t q0 = word_at<B + Fm::qs, NW>(y), q1 = word_at<B + Fm::qs + 4, NW>(y);
+        const uint32_t q2 = word_at<B + Fm::qs + 8, NW>(y), q3 = word_at<B + Fm::qs + 12, NW>(y);
+        w[0] = q0 & 0x0f0f0f0fu; w[1] = q1 & 0x0f0f0f0fu; w[2] = q2 & 0x0f0f0f0fu; w[3] = q3 & 0x0f0f0f0fu;
+        w[4] = (q0 >> 4) & 0x0f0f0f0fu; w[5] = (q1 >> 4) & 0x0f0f0f0fu; w[6] = (q2 >> 4) & 0x0f0f0f0fu; w[7] = (q3 >> 4) & 0x0f0f0f0fu;
+        if constexpr (Fm::bits == 5) {
+            const uint32_t qh = word_at<B + (Fm::qh >= 0 ? Fm::qh : 0), NW>(y);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                w[i] |= spread_qh4(qh, 4 * i);
+                w[i + 4] |= spread_qh4(qh, 16 + 4 * i);
+            }
+        }
+    }
+    *reinterpret_cast<uint4*>(tile_row + (((2 * J) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(tile_row + (((2 * J + 1) ^ sw) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+    ws[J * kBN + row] = half_at<B, NW>(y);
+    if constexpr (Fm::m >= 0) wm[J * kBN + row] = half_at<B + (Fm::m >= 0 ? Fm::m : 0), NW>(y);
+}
+
+// The 4 blocks of one operand stage of weight row `row`: raw bytes (shared memory, 8-byte aligned) -> operand tile row.
+template <int WT>
+__device__ __forceinline__ void unpack_half_row(const uint8_t* raw_half, uint8_t* stage, int row) {
+    constexpr int kHalf = kBPS * Fmt<WT>::bytes;   // 72 / 80 / 88 / 96 / 136 bytes
+    static_assert(kHalf % 8 == 0, "half rows are read as 8-byte words");
+    constexpr int NW = kHalf / 4;
+    uint32_t y[NW];
+    const uint2* src = reinterpret_cast<const uint2*>(raw_half);
+#pragma unroll
+    for (int i = 0; i < NW / 2; i++) {
+        const uint2 v = src[i];
+        y[2 * i] = v.x;
+        y[2 * i + 1] = v.y;
+    }
+    uint8_t* tile_row = stage + kStageW + row * kKC;
+    float* ws = reinterpret_cast<float*>(stage + kStageWS);
+    float* wm = reinterpret_cast<float*>(stage + kStageWM);
+    const int sw = row & 7;
+    unpack_one<WT, 0, NW>(y, tile_row, sw, ws, wm, row);
+    unpack_one<WT, 1, NW>(y, tile_row, sw, ws, wm, row);
+    unpack_one<WT, 2, NW>(y, tile_row, sw, ws, wm, row);
+    unpack_one<WT, 3, NW>(y, tile_row, sw, ws, wm, row);
+}
+
+template <int WT, bool kDump>
+__global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p, const __grid_constant__ CUtensorMap wmap) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+    // [ barriers | operand stages | raw ring | (peer staging tile) ]: every offset below is a compile-time constant
+    // except the two ring bases
+    const int nstages = p.stages, nraw = p.raw_stages;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);       // [kMaxStages] producer tx + 2 unpack warps
+    uint64_t* empty = full + kMaxStages;                      // [kMaxStages] MMA commit + 16 epilogue warps
+    uint64_t* rawfull = empty + kMaxStages;                   // [kMaxRaw]    tx of the tensor load
+    uint64_t* tfull = rawfull + kMaxRaw;                      // [2]          MMA commit per TMEM half
+    uint64_t* tempty = tfull + 2;                             // [2]          16 epilogue warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint8_t* stages = smem + kBarBytes;
+    uint8_t* raw_ring = stages + nstages * kStageBytes;
+    float* out_tile = reinterpret_cast<float*>(raw_ring + nraw * raw_stage_bytes<WT>());   // [kBN][kBM], only with p.tma_out
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkc = p.nkc;
+    const int nbp = nkc * kBPS;
+    const int ntiles = p.tiles_m * p.tiles_n;
+
+    if (threadIdx.x == kWarpProd * 32) {
+        for (int s = 0; s < kMaxStages; s++) {
+            ptx::mbar_init(&full[s], 1 + kUnpackWarps);
+            ptx::mbar_init(&empty[s], 1 + kEpiWarps);
+        }
+        for (int r = 0; r < kMaxRaw; r++) ptx::mbar_init(&rawfull[r], 1);
+        for (int h = 0; h < 2; h++) {
+            ptx::mbar_init(&tfull[h], 1);
+            ptx::mbar_init(&tempty[h], kEpiWarps);
+        }
+        ptx::fence_mbar_init();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
+    }
+    if (warp == kWarpMma) t5::alloc(tmem_slot, kTmemCols);
+    t5::fence_before();
+    __syncthreads();
+    t5::fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    ptx::griddep_wait();   // launched behind the activation prepass with programmatic serialization
+
+    if (warp == kWarpProd) {
+        // ===================== activation producer =====================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            PROF_DECL;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int mt = tile % p.tiles_m;
+                for (int kc = 0; kc < nkc; kc++) {
+                    PROF_WAIT(pf_wait, ptx::mbar_wait_backoff(&empty[s], ph ^ 1));
+                    uint8_t* st = stages + s * kStageBytes;
+                    ptx::mbar_arrive_expect_tx(&full[s], kBM * kKC + kBPS * kBM * 8);
+                    ptx::bulk_g2s(st + kStageA, p.a8 + ((size_t)kc * p.Tpad + (size_t)mt * kBM) * kKC, kBM * kKC, &full[s]);
+                    ptx::bulk_g2s(st + kStageAS, p.as + ((size_t)mt * nbp + (size_t)kc * kBPS) * kBM, kBPS * kBM * 8, &full[s]);
+                    if (++s == nstages) { s = 0; ph ^= 1; }
+                }
+            }
+#ifdef QGEMM_MMQ_PROFILE
+            if (blockIdx.x == 0 && (p.dbg & 32)) printf("producer: total %lld, waiting for empty %lld\n", clock64() - pf_t0, pf_wait);
+#endif
+        }
+    } else if (warp == kWarpMma) {
+        // ===================== MMA issuer =====================
+        // D[token, row] (s32) = A (s8 activations, M side) . B (u8 / s8 weights, N side)^T, both K-major
+        constexpr uint32_t idesc = (2u << 4) | (1u << 7) | ((Fmt<WT>::bits == 8 ? 1u : 0u) << 10) |
+                                   ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+        int s = 0;
+        uint32_t ph = 0, tph = 0;
+        PROF_DECL;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int kc = 0; kc < nkc; kc++) {
+                PROF_WAIT(pf_wait, ptx::mbar_wait(&full[s], ph));
+                t5::fence_after();
+                const uint64_t adesc = t5::smem_desc(ptx::smem_u32(stages + s * kStageBytes + kStageA));
+                const uint64_t bdesc = t5::smem_desc(ptx::smem_u32(stages + s * kStageBytes + kStageW));
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    PROF_WAIT(pf_wait2, ptx::mbar_wait(&tempty[h], tph ^ 1));
+                    t5::fence_after();
+                    if (lane == 0) {
+                        // one instruction = one quantization block (32 bytes of K = +2 in the >>4 address field)
+                        t5::mma_i8(tmem_base + (2 * h) * kBN, adesc + 2 * (2 * h), bdesc + 2 * (2 * h), idesc, 0u);
+                        t5::mma_i8(tmem_base + (2 * h + 1) * kBN, adesc + 2 * (2 * h + 1), bdesc + 2 * (2 * h + 1), idesc, 0u);
+                        t5::commit(&tfull[h]);
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) t5::commit(&empty[s]);   // operand tiles consumed once these MMAs retire
+                __syncwarp();
+                tph ^= 1;
+                if (++s == nstages) { s = 0; ph ^= 1; }
+            }
+        }
+#ifdef QGEMM_MMQ_PROFILE
+        if (blockIdx.x == 0 && lane == 0 && (p.dbg & 32)) printf("mma: total %lld, waiting for full %lld, for tempty %lld\n", clock64() - pf_t0, pf_wait, pf_wait2);
+#endif
+    } else if (warp >= kWarpUnpack) {
+        // ===================== weight unpack =====================
+        const int u = threadIdx.x - kWarpUnpack * 32;   // this thread owns weight rows u, u + 64 of the tile
+        constexpr int kRow = raw_row_bytes<WT>();
+        constexpr int kHalf = kBPS * Fmt<WT>::bytes;
+        const int nrs = nkc >> 1;                         // raw stages per tile
+        const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int total = my_tiles * nrs;                 // raw stages of this CTA, tiles back to back
+        // issue side: (tile, rs) of the next raw stage to request, and the slot it goes to
+        int itile = blockIdx.x, irs = 0, islot = 0, issued = 0;
+        auto issue = [&]() {   // one 2-D tensor load: the next 8 raw blocks of the tile's 128 rows (rows >= F arrive as zeros)
+            if (u == 0) {
+                ptx::mbar_arrive_expect_tx(&rawfull[islot], (uint32_t)raw_stage_bytes<WT>());
+                tma_load_2d(raw_ring + islot * raw_stage_bytes<WT>(), &wmap, irs * (kRow / 2), (itile / p.tiles_m) * kBN, &rawfull[islot]);
+            }
+            if (++irs == nrs) { irs = 0; itile += gridDim.x; }
+            if (++islot == nraw) islot = 0;
+            issued++;
+        };
+        while (issued < nraw && issued < total) issue();
+        int s = 0, r = 0;
+        uint32_t ph = 0, rph = 0;
+        PROF_DECL;
+        for (int q = 0; q < total; q++) {
+            PROF_WAIT(pf_wait, ptx::mbar_wait(&rawfull[r], rph));
+            const uint8_t* rslot = raw_ring + r * raw_stage_bytes<WT>();
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                PROF_WAIT(pf_wait2, ptx::mbar_wait(&empty[s], ph ^ 1));
+#pragma unroll
+                for (int i = 0; i < kRowsPerThread; i++) {
+                    const int row = u + i * kUT;
+                    unpack_half_row<WT>(rslot + row * kRow + h * kHalf, stages + s * kStageBytes, row);
+                }
+                ptx::fence_proxy_async();                 // generic-proxy stores -> visible to the tensor core's reads
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&full[s]);
+                if (++s == nstages) { s = 0; ph ^= 1; }
+            }
+            if (++r == nraw) { r = 0; rph ^= 1; }
+            if (issued < total) {
+                ptx::bar_sync(1, kUT);                    // both warps are done reading the slot
+                issue();
+            }
+        }
+#ifdef QGEMM_MMQ_PROFILE
+        if (blockIdx.x == 0 && u == 0 && (p.dbg & 32)) printf("unpack: total %lld, waiting for raw %lld, for empty %lld\n", clock64() - pf_t0, pf_wait, pf_wait2);
+#endif
+    } else {
+        // ===================== epilogue =====================
+        const int ew = warp;
+        const int quarter = warp & 3;           // TMEM lane quarter this warp may touch
+        const int cgrp = ew >> 2;               // which 32-column group
+        const int row = quarter * 32 + lane;    // token row inside the tile
+        const uint32_t tm = tmem_base + ((uint32_t)(quarter * 32) << 16) + cgrp * kEpiCols;
+        static_assert(kEpiCols == 32, "one tcgen05.ld.x32 per block per thread");
+        int s = 0;
+        uint32_t ph = 0, tph = 0;
+        PROF_DECL;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int mt = tile % p.tiles_m, nt = tile / p.tiles_m;
+            uint64_t acc[kEpiCols / 2];  // fp32 accumulators as packed pairs (columns 2i, 2i+1)
+#pragma unroll
+            for (int i = 0; i < kEpiCols / 2; i++) acc[i] = 0ull;
+#pragma unroll 1
+            for (int kc = 0; kc < nkc; kc++) {
+                PROF_WAIT(pf_wait, ptx::mbar_wait(&full[s], ph));  // scale slabs of this stage are visible
+                const uint8_t* st = stages + s * kStageBytes;
+#pragma unroll
+                for (int j = 0; j < kBPS; j++) {
+                    if ((j & 1) == 0) {
+                        PROF_WAIT(pf_wait2, ptx::mbar_wait(&tfull[j >> 1], tph));
+                        t5::fence_after();
+                    }
+                    int x[kEpiCols];
+                    t5::ld32(tm + j * kBN, x);
+                    t5::wait_ld();
+                    if (j & 1) {   // both blocks of this half are in registers: hand the half back to the tensor core
+                        t5::fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(&tempty[j >> 1]);
+                    }
+                    if constexpr (kDump) {
+                        const int t = mt * kBM + row, b = kc * kBPS + j;
+                        if (t < p.T && b < p.nb) {
+#pragma unroll
+                            for (int i = 0; i < kEpiCols; i++) {
+                                const int f = nt * kBN + cgrp * kEpiCols + i;
+                                if (f < p.F) p.sumi[((size_t)t * p.F + f) * p.nb + b] = x[i];
+                            }
+                        }
+                    } else {
+                        const float2 a = reinterpret_cast<const float2*>(st + kStageAS)[j * kBM + row];
+                        const uint64_t da = pk(a.x, a.x), ca = pk(a.y, a.y);
+                        const ulonglong2* dw2 = reinterpret_cast<const ulonglong2*>(st + kStageWS) + (j * kBN + cgrp * kEpiCols) / 4;
+                        const ulonglong2* mw2 = reinterpret_cast<const ulonglong2*>(st + kStageWM) + (j * kBN + cgrp * kEpiCols) / 4;
+#pragma unroll
+                        for (int i4 = 0; i4 < kEpiCols / 4; i4++) {
+                            const ulonglong2 dw = dw2[i4];  // d_w of columns 4*i4 .. 4*i4+3 (broadcast read)
+                            ulonglong2 mw = make_ulonglong2(0ull, 0ull);
+                            if constexpr (Fmt<WT>::m >= 0) mw = mw2[i4];
+                            acc[2 * i4] = fold_pair<WT>(acc[2 * i4], x[4 * i4], x[4 * i4 + 1], dw.x, mw.x, da, ca);
+                            acc[2 * i4 + 1] = fold_pair<WT>(acc[2 * i4 + 1], x[4 * i4 + 2], x[4 * i4 + 3], dw.y, mw.y, da, ca);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&empty[s]);  // scale slabs consumed
+                tph ^= 1;
+                if (++s == nstages) { s = 0; ph ^= 1; }
+            }
+            if constexpr (!kDump) {
+                const int t = mt * kBM + row;
+                if (p.tma_out) {
+                    // Fused all-gather, bulk variant (see mmq.cu): the tile is staged as [f][t] and carried to every rank's
+                    // gathered C by the TMA engine, 512-byte rows, while the epilogue warps go on with the next tile.
+                    if (lane == 0) ptx::bulk_wait_read();
+                    ptx::bar_sync(3, kEpiWarps * 32);
+#pragma unroll
+                    for (int i = 0; i < kEpiCols / 2; i++) {
+                        float v0, v1;
+                        unpk(acc[i], v0, v1);
+                        out_tile[(cgrp * kEpiCols + 2 * i) * kBM + row] = v0;
+                        out_tile[(cgrp * kEpiCols + 2 * i + 1) * kBM + row] = v1;
+                    }
+                    ptx::fence_proxy_async();
+                    ptx::bar_sync(3, kEpiWarps * 32);
+                    if (lane == 0) {
+                        const int t0 = mt * kBM;
+                        const uint32_t bytes = (uint32_t)min(kBM, p.T - t0) * 4u;
+                        constexpr int kRowsPerWarp = kBN / kEpiWarps;
+#pragma unroll 1
+                        for (int q = 0; q < p.peer.world; q++) {
+                            int r = p.peer.rank + 1 + q;   // staggered start: the ranks target different receivers
+                            if (r >= p.peer.world) r -= p.peer.world;
+                            float* Cr = p.peer.C[r];
+#pragma unroll 1
+                            for (int k = 0; k < kRowsPerWarp; k++) {
+                                const int fl = ew * kRowsPerWarp + k;
+                                const int f = nt * kBN + fl;
+                                if (f < p.F) ptx::bulk_s2g(Cr + (int64_t)f * p.ldc_f + t0, out_tile + fl * kBM, bytes);
+                            }
+                        }
+                        ptx::bulk_commit();
+                    }
+                } else if (t < p.T && !(p.dbg & 4)) {
+                    const int nrank = (p.peer.world > 1 && !p.peer.mc) ? p.peer.world : 1;
+#pragma unroll 1
+                    for (int q = 0; q < nrank; q++) {
+                        int r = p.peer.rank + 1 + q;
+                        if (r >= nrank) r -= nrank;
+                        float* crow = (nrank > 1 ? p.peer.C[r] : (p.peer.mc ? p.peer.mc : p.C)) + (int64_t)t * p.ldc_t;
+#pragma unroll
+                        for (int i = 0; i < kEpiCols / 2; i++) {
+                            float v0, v1;
+                            unpk(acc[i], v0, v1);
+                            const int f = nt * kBN + cgrp * kEpiCols + 2 * i;
+                            if (f < p.F) crow[(int64_t)f * p.ldc_f] = v0;
+                            if (f + 1 < p.F) crow[(int64_t)(f + 1) * p.ldc_f] = v1;
+                        }
+                    }
+                }
+            }
+        }
+#ifdef QGEMM_MMQ_PROFILE
+        if (blockIdx.x == 0 && lane == 0 && (p.dbg & 32) && (ew == 0 || ew == 15)) printf("epilogue warp %d: total %lld, waiting for full %lld, for tfull %lld\n", ew, clock64() - pf_t0, pf_wait, pf_wait2);
+#endif
+        if constexpr (!kDump) {
+            if (p.tma_out && lane == 0) {   // every bulk store of this thread is complete before the CTA signals
+                ptx::bulk_wait_all();
+                ptx::fence_proxy_async_all();
+            }
+        }
+    }
+    t5::fence_before();
+    __syncthreads();
+    if (warp == kWarpMma) t5::dealloc(tmem_base, kTmemCols);
+    if constexpr (!kDump) {
+        if (threadIdx.x == 0) peer_signal_done(p.peer, gridDim.x);  // the barrier above ordered every epilogue store
+    }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            (void)cudaGetLastError();
+            return nullptr;
+        }
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+// the native weight matrix as a 2-D tensor of uint16 [F][row bytes / 2]; box = 128 rows x the 8 raw blocks of a stage
+template <int WT>
+static bool make_weight_map(CUtensorMap* map, const void* wgt, int F, int nb) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t rowbytes = (cuuint64_t)nb * Fmt<WT>::bytes;
+    const cuuint64_t gdim[2] = {rowbytes / 2, (cuuint64_t)F};
+    const cuuint64_t gstride[1] = {rowbytes};
+    const cuuint32_t box[2] = {(cuuint32_t)raw_row_bytes<WT>() / 2, (cuuint32_t)kBN};
+    const cuuint32_t estride[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(wgt), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int WT>
+static cudaError_t launch_t(Params p, const void* wgt, int num_sms, cudaStream_t st) {
+    CUtensorMap wmap;
+    if (!make_weight_map<WT>(&wmap, wgt, p.F, p.nb)) return cudaErrorNotSupported;
+    // operand ring 3 deep (2 next to the peer staging tile), raw ring as deep as fits
+    p.stages = p.tma_out ? 2 : kMaxStages;
+    const size_t fixed = 1024 + (size_t)p.stages * kStageBytes + kBarBytes + (p.tma_out ? kOutTileBytes : 0);
+    p.raw_stages = (int)min((size_t)kMaxRaw, (227 * 1024 - fixed) / raw_stage_bytes<WT>());
+    if (p.raw_stages < 2) return cudaErrorInvalidValue;
+    const size_t smem = fixed + (size_t)p.raw_stages * raw_stage_bytes<WT>();
+    const void* fn = p.sumi ? reinterpret_cast<const void*>(mmq_native_kernel<WT, true>)
+                            : reinterpret_cast<const void*>(mmq_native_kernel<WT, false>);
+    if (cudaError_t e = smem_optin(fn, smem)) return e;
+    const int ntiles = p.tiles_m * p.tiles_n;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(min(ntiles, num_sms));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // behind the activation prepass
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = p.sumi ? cudaLaunchKernelEx(&cfg, mmq_native_kernel<WT, true>, p, wmap) : cudaLaunchKernelEx(&cfg, mmq_native_kernel<WT, false>, p, wmap);
+    note_launch();
+    return e;
+}
+
+}  // namespace nat
+
+// K % 256 == 0 and bulk-copyable rows (a multiple of 256 elements makes every format's row a 16-byte multiple)
+bool mmq_native_supported(int wtype, const void* wgt, int T, int F, int K) {
+    if (block_bytes(wtype) == 0 || wtype == QGEMM_TYPE_Q8_1 || T < 1 || F < 1 || K < 256 || K % 256 != 0) return false;
+    return reinterpret_cast<uintptr_t>(wgt) % 16 == 0 && nat::encode_tiled_fn() != nullptr;
+}
+
+// a8 / as: the activation prepass of mmq.cu (Tpad tokens, nkc operand stages)
+cudaError_t launch_mmq_native(int wtype, const uint8_t* a8, const float2* as, const void* wgt, float* C, int32_t* sumi, int T,
+                              int F, int K, int Tpad, int64_t ldc_t, int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t st,
+                              const PeerOut* peer) {
+    nat::Params p;
+    p.a8 = a8; p.as = as; p.C = C; p.sumi = sumi;
+    p.T = T; p.F = F; p.nb = K / 32; p.nkc = K / nat::kKC; p.Tpad = Tpad;
+    p.ldc_t = ldc_t; p.ldc_f = ldc_f;
+    p.tiles_m = Tpad / nat::kBM; p.tiles_n = (F + nat::kBN - 1) / nat::kBN;
+    p.stages = 0; p.raw_stages = 0;
+    (void)flags;
+    p.dbg = QGEMM_ENV("QGEMM_MMQ_DBG") ? atoi(QGEMM_ENV("QGEMM_MMQ_DBG")) : 0;
+    p.peer = peer ? *peer : PeerOut{};
+    p.tma_out = 0;
+    if (p.peer.world > 1 && !p.peer.mc && !sumi && ldc_t == 1 && T % 4 == 0 && ldc_f % 4 == 0 && !QGEMM_ENV("QGEMM_MMQ_NO_TMA_OUT")) {
+        p.tma_out = 1;
+        for (int r = 0; r < p.peer.world; r++)
+            if (reinterpret_cast<uintptr_t>(p.peer.C[r]) % 16 != 0) p.tma_out = 0;
+    }
+    switch (wtype) {
+    case QGEMM_TYPE_Q4_0: return nat::launch_t<QGEMM_TYPE_Q4_0>(p, wgt, num_sms, st);
+    case QGEMM_TYPE_Q4_1: return nat::launch_t<QGEMM_TYPE_Q4_1>(p, wgt, num_sms, st);
+    case QGEMM_TYPE_Q5_0: return nat::launch_t<QGEMM_TYPE_Q5_0>(p, wgt, num_sms, st);
+    case QGEMM_TYPE_Q5_1: return nat::launch_t<QGEMM_TYPE_Q5_1>(p, wgt, num_sms, st);
+    case QGEMM_TYPE_Q8_0: return nat::launch_t<QGEMM_TYPE_Q8_0>(p, wgt, num_sms, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace qgemm

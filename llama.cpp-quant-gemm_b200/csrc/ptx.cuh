@@ -1,6 +1,7 @@
 // ptx.cuh -- thin inline-PTX wrappers for sm_100a: mbarrier, bulk async copy
 // (TMA engine, 1-D), named barriers, tcgen05/TMEM.
 #pragma once
+#include <cstdio>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -33,12 +34,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// A wait that would never end (a protocol bug, a lost copy) must not hang the device: after ~2 s of polling the
+// thread reports which barrier it was stuck on and traps, which fails the launch with a CUDA error instead.
+static __device__ __noinline__ void mbar_timeout(uint64_t* bar, uint32_t parity) {
+    printf("qgemm: mbarrier wait timed out: block %d thread %d barrier smem+0x%x parity %u\n", (int)blockIdx.x, (int)threadIdx.x,
+           smem_u32(bar), parity);
+    __trap();
+}
+// polls before giving up: try_wait itself suspends the thread for a hardware-defined slice, so this is seconds
+constexpr uint32_t kMbarTimeoutPolls = 1u << 26;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {}
+    if (mbar_try_wait(bar, parity)) return;
+    for (uint32_t n = 0; !mbar_try_wait(bar, parity); n++)
+        if (n > kMbarTimeoutPolls) mbar_timeout(bar, parity);
 }
 // for single-thread role warps that share a scheduler with busy math warps: sleep between polls
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) __nanosleep(32);
+    if (mbar_try_wait(bar, parity)) return;
+    for (uint32_t n = 0; !mbar_try_wait(bar, parity); n++) {
+        __nanosleep(32);
+        if (n > (kMbarTimeoutPolls >> 2)) mbar_timeout(bar, parity);
+    }
 }
 
 // ---- 1-D bulk async copy global -> shared (TMA engine, no tensor map) ---------
