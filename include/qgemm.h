@@ -84,6 +84,12 @@ extern "C" {
                                    cudaFreeAsync around the launch: stream-ordered, graph-capturable, nothing
                                    persists).  The drop-in C++ headers pass it, because the reference's launcher
                                    signatures have no workspace argument.                                     */
+#define QGEMM_FOLD_REFSEQ 0x1000u /* tensor-core path, q4_1 / q5_1 only: fold every block with the reference GPU kernel's
+                                   exact operation sequence, d_w*d_a*sumi + m_w*s_a/4 as ((d_w*d_a)*sumi + (m_w*s_a)/4) added to
+                                   the sum (gemm_quant_formats.cuh:148,266) -- bit-identical to it, one more FMA-pipe operation
+                                   per output pair and block.  Default: acc = fma(m_w, s_a/4, fma(d_w, d_a*sumi, acc)), the same
+                                   terms associated differently (~1e-7 of max|C| apart).  The other formats, and every other
+                                   path, always use the reference sequence.                                                  */
 #define QGEMM_PATH_MASK 0xF00u
 #define QGEMM_PATH_AUTO 0x000u
 #define QGEMM_PATH_GENERIC 0x100u /* same kernel as QGEMM_SEQUENTIAL                         */

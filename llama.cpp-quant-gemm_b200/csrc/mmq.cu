@@ -456,13 +456,23 @@ bool mmq_supported(int wtype, const void* act, const void* wgt, int T, int F, in
     return reinterpret_cast<uintptr_t>(act) % 4 == 0;
 }
 
+bool mmq_native_supported(int wtype, const void* wgt, int T, int F, int K);
+
+// Scratch of the tensor-core path.  Shapes the native-layout kernel takes (K % 256 == 0) need the repacked activations
+// only; the prepass kernel also keeps the unpacked weights there.  The pointer-free form (qgemm_workspace_bytes) assumes
+// a 16-byte aligned weight base, which every allocator gives; mmq_workspace_need() is what a concrete call requires.
 size_t mmq_workspace_bytes(int wtype, int T, int F, int K) {
-    (void)wtype;
     if (T < 1 || F < 1 || K < 32) return 0;
-    return mmq_layout(T, F, K).total;
+    const MmqWs L = mmq_layout(T, F, K);
+    return mmq_native_supported(wtype, nullptr, T, F, K) ? L.w8 : L.total;
+}
+size_t mmq_workspace_need(int wtype, const void* wgt, int T, int F, int K, uint32_t flags) {
+    if (T < 1 || F < 1 || K < 32) return 0;
+    const MmqWs L = mmq_layout(T, F, K);
+    if ((flags & QGEMM_WEIGHTS_PREPACKED) || (mmq_native_supported(wtype, wgt, T, F, K) && !QGEMM_ENV("QGEMM_MMQ_LEGACY"))) return L.w8;
+    return L.total;
 }
 
-bool mmq_native_supported(int wtype, const void* wgt, int T, int F, int K);
 cudaError_t launch_mmq_native(int wtype, const uint8_t* a8, const float2* as, const void* wgt, float* C, int32_t* sumi, int T,
                               int F, int K, int Tpad, int64_t ldc_t, int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t st,
                               const PeerOut* peer);
@@ -572,7 +582,7 @@ cudaError_t launch_mmq_prepack(int wtype, const void* wgt, void* packed, int F, 
 cudaError_t launch_mmq(int wtype, const void* act, const void* wgt, float* C, int32_t* sumi_out, int T, int F, int K,
                        int64_t ldc_t, int64_t ldc_f, uint32_t flags, void* ws, size_t ws_bytes, int num_sms,
                        cudaStream_t st, const PeerOut* peer) {
-    if (ws_bytes < mmq_workspace_bytes(wtype, T, F, K) || reinterpret_cast<uintptr_t>(ws) % 256 != 0)
+    if (ws_bytes < mmq_workspace_need(wtype, wgt, T, F, K, flags) || reinterpret_cast<uintptr_t>(ws) % 256 != 0)
         return cudaErrorInvalidValue;
     switch (wtype) {
     case QGEMM_TYPE_Q4_0: return launch_mmq_t<QGEMM_TYPE_Q4_0>(act, wgt, C, sumi_out, T, F, K, ldc_t, ldc_f, flags, ws, num_sms, st, peer);

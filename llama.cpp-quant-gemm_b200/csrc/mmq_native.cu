@@ -161,7 +161,7 @@ __device__ __forceinline__ void unpack_half_row(const uint8_t* raw_half, uint8_t
     unpack_one<WT, 3, NW>(y, tile_row, sw, ws, wm, row);
 }
 
-template <int WT, bool kDump>
+template <int WT, bool kDump, bool kRefSeq>
 __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p, const __grid_constant__ CUtensorMap wmap) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -328,41 +328,44 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
             for (int kc = 0; kc < nkc; kc++) {
                 PROF_WAIT(pf_wait, ptx::mbar_wait(&full[s], ph));  // scale slabs of this stage are visible
                 const uint8_t* st = stages + s * kStageBytes;
+#pragma unroll 1
+                for (int h = 0; h < 2; h++) {   // one TMEM half = two blocks per iteration; not unrolled further so that the
+                                                // accumulators keep their registers
+                    PROF_WAIT(pf_wait2, ptx::mbar_wait(&tfull[h], tph));
+                    t5::fence_after();
 #pragma unroll
-                for (int j = 0; j < kBPS; j++) {
-                    if ((j & 1) == 0) {
-                        PROF_WAIT(pf_wait2, ptx::mbar_wait(&tfull[j >> 1], tph));
-                        t5::fence_after();
-                    }
-                    int x[kEpiCols];
-                    t5::ld32(tm + j * kBN, x);
-                    t5::wait_ld();
-                    if (j & 1) {   // both blocks of this half are in registers: hand the half back to the tensor core
-                        t5::fence_before();
-                        __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive(&tempty[j >> 1]);
-                    }
-                    if constexpr (kDump) {
-                        const int t = mt * kBM + row, b = kc * kBPS + j;
-                        if (t < p.T && b < p.nb) {
-#pragma unroll
-                            for (int i = 0; i < kEpiCols; i++) {
-                                const int f = nt * kBN + cgrp * kEpiCols + i;
-                                if (f < p.F) p.sumi[((size_t)t * p.F + f) * p.nb + b] = x[i];
-                            }
+                    for (int jj = 0; jj < 2; jj++) {
+                        const int j = 2 * h + jj;
+                        int x[kEpiCols];
+                        t5::ld32(tm + j * kBN, x);
+                        t5::wait_ld();
+                        if (jj == 1) {   // both blocks of this half are in registers: hand the half back to the tensor core
+                            t5::fence_before();
+                            __syncwarp();
+                            if (lane == 0) ptx::mbar_arrive(&tempty[h]);
                         }
-                    } else {
-                        const float2 a = reinterpret_cast<const float2*>(st + kStageAS)[j * kBM + row];
-                        const uint64_t da = pk(a.x, a.x), ca = pk(a.y, a.y);
-                        const ulonglong2* dw2 = reinterpret_cast<const ulonglong2*>(st + kStageWS) + (j * kBN + cgrp * kEpiCols) / 4;
-                        const ulonglong2* mw2 = reinterpret_cast<const ulonglong2*>(st + kStageWM) + (j * kBN + cgrp * kEpiCols) / 4;
+                        if constexpr (kDump) {
+                            const int t = mt * kBM + row, b = kc * kBPS + j;
+                            if (t < p.T && b < p.nb) {
 #pragma unroll
-                        for (int i4 = 0; i4 < kEpiCols / 4; i4++) {
-                            const ulonglong2 dw = dw2[i4];  // d_w of columns 4*i4 .. 4*i4+3 (broadcast read)
-                            ulonglong2 mw = make_ulonglong2(0ull, 0ull);
-                            if constexpr (Fmt<WT>::m >= 0) mw = mw2[i4];
-                            acc[2 * i4] = fold_pair<WT>(acc[2 * i4], x[4 * i4], x[4 * i4 + 1], dw.x, mw.x, da, ca);
-                            acc[2 * i4 + 1] = fold_pair<WT>(acc[2 * i4 + 1], x[4 * i4 + 2], x[4 * i4 + 3], dw.y, mw.y, da, ca);
+                                for (int i = 0; i < kEpiCols; i++) {
+                                    const int f = nt * kBN + cgrp * kEpiCols + i;
+                                    if (f < p.F) p.sumi[((size_t)t * p.F + f) * p.nb + b] = x[i];
+                                }
+                            }
+                        } else {
+                            const float2 a = reinterpret_cast<const float2*>(st + kStageAS)[j * kBM + row];
+                            const uint64_t da = pk(a.x, a.x), ca = pk(a.y, a.y);
+                            const ulonglong2* dw2 = reinterpret_cast<const ulonglong2*>(st + kStageWS) + (j * kBN + cgrp * kEpiCols) / 4;
+                            const ulonglong2* mw2 = reinterpret_cast<const ulonglong2*>(st + kStageWM) + (j * kBN + cgrp * kEpiCols) / 4;
+#pragma unroll
+                            for (int i4 = 0; i4 < kEpiCols / 4; i4++) {
+                                const ulonglong2 dw = dw2[i4];  // d_w of columns 4*i4 .. 4*i4+3 (broadcast read)
+                                ulonglong2 mw = make_ulonglong2(0ull, 0ull);
+                                if constexpr (Fmt<WT>::m >= 0) mw = mw2[i4];
+                                acc[2 * i4] = fold_pair<WT, kRefSeq>(acc[2 * i4], x[4 * i4], x[4 * i4 + 1], dw.x, mw.x, da, ca);
+                                acc[2 * i4 + 1] = fold_pair<WT, kRefSeq>(acc[2 * i4 + 1], x[4 * i4 + 2], x[4 * i4 + 3], dw.y, mw.y, da, ca);
+                            }
                         }
                     }
                 }
@@ -474,7 +477,7 @@ static bool make_weight_map(CUtensorMap* map, const void* wgt, int F, int nb) {
 }
 
 template <int WT>
-static cudaError_t launch_t(Params p, const void* wgt, int num_sms, cudaStream_t st) {
+static cudaError_t launch_t(Params p, const void* wgt, bool refseq, int num_sms, cudaStream_t st) {
     CUtensorMap wmap;
     if (!make_weight_map<WT>(&wmap, wgt, p.F, p.nb)) return cudaErrorNotSupported;
     // operand ring 3 deep (2 next to the peer staging tile), raw ring as deep as fits
@@ -483,8 +486,12 @@ static cudaError_t launch_t(Params p, const void* wgt, int num_sms, cudaStream_t
     p.raw_stages = (int)min((size_t)kMaxRaw, (227 * 1024 - fixed) / raw_stage_bytes<WT>());
     if (p.raw_stages < 2) return cudaErrorInvalidValue;
     const size_t smem = fixed + (size_t)p.raw_stages * raw_stage_bytes<WT>();
-    const void* fn = p.sumi ? reinterpret_cast<const void*>(mmq_native_kernel<WT, true>)
-                            : reinterpret_cast<const void*>(mmq_native_kernel<WT, false>);
+    // q4_1 / q5_1 have a cheaper fold than the reference's operation sequence (tc05.cuh); refseq keeps the latter
+    constexpr bool kHasM = Fmt<WT>::m >= 0;
+    const bool fast = kHasM && !refseq;
+    const void* fn = p.sumi ? reinterpret_cast<const void*>(mmq_native_kernel<WT, true, true>)
+                     : fast ? reinterpret_cast<const void*>(mmq_native_kernel<WT, false, !kHasM>)
+                            : reinterpret_cast<const void*>(mmq_native_kernel<WT, false, true>);
     if (cudaError_t e = smem_optin(fn, smem)) return e;
     const int ntiles = p.tiles_m * p.tiles_n;
     cudaLaunchConfig_t cfg{};
@@ -497,7 +504,9 @@ static cudaError_t launch_t(Params p, const void* wgt, int num_sms, cudaStream_t
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    cudaError_t e = p.sumi ? cudaLaunchKernelEx(&cfg, mmq_native_kernel<WT, true>, p, wmap) : cudaLaunchKernelEx(&cfg, mmq_native_kernel<WT, false>, p, wmap);
+    cudaError_t e = p.sumi ? cudaLaunchKernelEx(&cfg, mmq_native_kernel<WT, true, true>, p, wmap)
+                    : fast ? cudaLaunchKernelEx(&cfg, mmq_native_kernel<WT, false, !kHasM>, p, wmap)
+                           : cudaLaunchKernelEx(&cfg, mmq_native_kernel<WT, false, true>, p, wmap);
     note_launch();
     return e;
 }
@@ -507,7 +516,7 @@ static cudaError_t launch_t(Params p, const void* wgt, int num_sms, cudaStream_t
 // K % 256 == 0 and bulk-copyable rows (a multiple of 256 elements makes every format's row a 16-byte multiple)
 bool mmq_native_supported(int wtype, const void* wgt, int T, int F, int K) {
     if (block_bytes(wtype) == 0 || wtype == QGEMM_TYPE_Q8_1 || T < 1 || F < 1 || K < 256 || K % 256 != 0) return false;
-    return reinterpret_cast<uintptr_t>(wgt) % 16 == 0 && nat::encode_tiled_fn() != nullptr;
+    return reinterpret_cast<uintptr_t>(wgt) % 16 == 0 && nat::encode_tiled_fn() != nullptr;   // nullptr counts as aligned
 }
 
 // a8 / as: the activation prepass of mmq.cu (Tpad tokens, nkc operand stages)
@@ -520,7 +529,7 @@ cudaError_t launch_mmq_native(int wtype, const uint8_t* a8, const float2* as, co
     p.ldc_t = ldc_t; p.ldc_f = ldc_f;
     p.tiles_m = Tpad / nat::kBM; p.tiles_n = (F + nat::kBN - 1) / nat::kBN;
     p.stages = 0; p.raw_stages = 0;
-    (void)flags;
+    const bool refseq = (flags & QGEMM_FOLD_REFSEQ) != 0;
     p.dbg = QGEMM_ENV("QGEMM_MMQ_DBG") ? atoi(QGEMM_ENV("QGEMM_MMQ_DBG")) : 0;
     p.peer = peer ? *peer : PeerOut{};
     p.tma_out = 0;
@@ -530,11 +539,11 @@ cudaError_t launch_mmq_native(int wtype, const uint8_t* a8, const float2* as, co
             if (reinterpret_cast<uintptr_t>(p.peer.C[r]) % 16 != 0) p.tma_out = 0;
     }
     switch (wtype) {
-    case QGEMM_TYPE_Q4_0: return nat::launch_t<QGEMM_TYPE_Q4_0>(p, wgt, num_sms, st);
-    case QGEMM_TYPE_Q4_1: return nat::launch_t<QGEMM_TYPE_Q4_1>(p, wgt, num_sms, st);
-    case QGEMM_TYPE_Q5_0: return nat::launch_t<QGEMM_TYPE_Q5_0>(p, wgt, num_sms, st);
-    case QGEMM_TYPE_Q5_1: return nat::launch_t<QGEMM_TYPE_Q5_1>(p, wgt, num_sms, st);
-    case QGEMM_TYPE_Q8_0: return nat::launch_t<QGEMM_TYPE_Q8_0>(p, wgt, num_sms, st);
+    case QGEMM_TYPE_Q4_0: return nat::launch_t<QGEMM_TYPE_Q4_0>(p, wgt, refseq, num_sms, st);
+    case QGEMM_TYPE_Q4_1: return nat::launch_t<QGEMM_TYPE_Q4_1>(p, wgt, refseq, num_sms, st);
+    case QGEMM_TYPE_Q5_0: return nat::launch_t<QGEMM_TYPE_Q5_0>(p, wgt, refseq, num_sms, st);
+    case QGEMM_TYPE_Q5_1: return nat::launch_t<QGEMM_TYPE_Q5_1>(p, wgt, refseq, num_sms, st);
+    case QGEMM_TYPE_Q8_0: return nat::launch_t<QGEMM_TYPE_Q8_0>(p, wgt, refseq, num_sms, st);
     default: return cudaErrorInvalidValue;
     }
 }

@@ -34,6 +34,7 @@ size_t mmq_prepack_bytes(int wtype, int F, int K);
 cudaError_t launch_mmq_prepack(int wtype, const void* wgt, void* packed, int F, int K, cudaStream_t);
 bool mmq_supported(int wtype, const void* act, const void* wgt, int T, int F, int K);
 size_t mmq_workspace_bytes(int wtype, int T, int F, int K);
+size_t mmq_workspace_need(int wtype, const void* wgt, int T, int F, int K, uint32_t flags);
 cudaError_t launch_mmq(int wtype, const void* act, const void* wgt, float* C, int32_t* sumi_out, int T, int F, int K,
                        int64_t ldc_t, int64_t ldc_f, uint32_t flags, void* ws, size_t ws_bytes, int num_sms,
                        cudaStream_t, const PeerOut* peer = nullptr);
@@ -181,7 +182,7 @@ static int run_gemm(int wtype, const void* act, const void* wgt, float* C, int T
     void* pool_ws = nullptr;
     if (!ws && (flags & QGEMM_STREAM_ALLOC) && (path == QGEMM_PATH_TCGEN05 || (path == QGEMM_PATH_AUTO && T >= kMmqMinTokens)) &&
         mmq_supported(wtype, act, wgt, T, F, K)) {
-        const size_t need = align_up(mmq_workspace_bytes(wtype, T, F, K), 256);
+        const size_t need = align_up(mmq_workspace_need(wtype, wgt, T, F, K, flags), 256);
         if (scratch_alloc(&pool_ws, need, st) == cudaSuccess) {
             ws = pool_ws;
             ws_bytes = need;
@@ -199,7 +200,7 @@ static int run_gemm(int wtype, const void* act, const void* wgt, float* C, int T
         path = QGEMM_PATH_TCGEN05;
     }
     if (path == QGEMM_PATH_AUTO) {
-        if (T >= kMmqMinTokens && mmq_supported(wtype, act, wgt, T, F, K) && ws && ws_bytes >= mmq_workspace_bytes(wtype, T, F, K))
+        if (T >= kMmqMinTokens && mmq_supported(wtype, act, wgt, T, F, K) && ws && ws_bytes >= mmq_workspace_need(wtype, wgt, T, F, K, flags))
             path = QGEMM_PATH_TCGEN05;
         else if (T >= (K > 8192 ? kMmaMinTokens + 1 : kMmaMinTokens) && gemv_mma_supported(wtype, act, wgt, T, F, K))
             path = QGEMM_PATH_MMA;
@@ -222,7 +223,7 @@ static int run_gemm(int wtype, const void* act, const void* wgt, float* C, int T
         break;
     case QGEMM_PATH_TCGEN05:
         if (!mmq_supported(wtype, act, wgt, T, F, K)) return QGEMM_E_ALIGN;
-        if (!ws || ws_bytes < mmq_workspace_bytes(wtype, T, F, K)) return QGEMM_E_WORKSPACE;
+        if (!ws || ws_bytes < mmq_workspace_need(wtype, wgt, T, F, K, flags)) return QGEMM_E_WORKSPACE;
         e = launch_mmq(wtype, act, wgt, C, nullptr, T, F, K, ldc_t, ldc_f, flags, ws, ws_bytes, dev.sms, st);
         break;
     case QGEMM_PATH_GENERIC:
@@ -407,7 +408,7 @@ int qgemm_sumi(int wtype, const void* act_q8_1, const void* weight, int32_t* sum
     cudaError_t e;
     if (path == QGEMM_PATH_TCGEN05) {
         if (!mmq_supported(wtype, act_q8_1, weight, T, F, K)) return QGEMM_E_ALIGN;
-        if (!workspace || workspace_bytes < mmq_workspace_bytes(wtype, T, F, K)) return QGEMM_E_WORKSPACE;
+        if (!workspace || workspace_bytes < mmq_workspace_need(wtype, weight, T, F, K, flags)) return QGEMM_E_WORKSPACE;
         e = launch_mmq(wtype, act_q8_1, weight, nullptr, sumi, T, F, K, 0, 0, flags, workspace, workspace_bytes,
                        dev.sms, st);
     } else {
@@ -487,7 +488,7 @@ int qgemm_gemm_peers(int wtype, const void* act_q8_1, const void* weight, const 
         // prefill: peer stores from the tcgen05 epilogue.  Scratch = the registered default workspace, else
         // (QGEMM_STREAM_ALLOC) the stream's pool; the operand prepass reads the activations, so the wait for
         // earlier launches of the step runs as its own one-thread kernel in front of it.
-        const size_t need = mmq_workspace_bytes(wtype, T, F, K);
+        const size_t need = mmq_workspace_need(wtype, weight, T, F, K, flags);
         void* ws = nullptr;
         size_t ws_bytes = 0;
         int d = 0;

@@ -93,18 +93,33 @@ __device__ __forceinline__ uint64_t cvt2(int x0, int x1) {
     return pk(__int2float_rn(x0), __int2float_rn(x1));
 #endif
 }
-// Two outputs of one token: same rounding sequence per element as fold_block_pre() (qgemm_common.cuh).
-template <int WT>
+// accumulate in place: the tied operand keeps the accumulator pair in one register pair for the whole K loop
+// (with a separate destination the register allocator rotated the pairs and paid a move per pair and block)
+__device__ __forceinline__ void ffma2_acc(uint64_t& acc, uint64_t a, uint64_t b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ void fadd2_acc(uint64_t& acc, uint64_t a) { asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(a)); }
+
+// Two outputs of one token.  kRefSeq: the rounding sequence per element of fold_block_pre() (qgemm_common.cuh), i.e. of
+// the reference GPU kernel -- bit-identical results.  Without it q4_1 / q5_1 use three FMA-pipe operations per pair
+// instead of four, acc = fma(m_w, c_a, fma(d_w, d_a * sumi, acc)): the same terms, associated differently (agreement
+// with the reference order ~1e-7 of max|C|); the other formats have only one sequence.
+template <int WT, bool kRefSeq = true>
 __device__ __forceinline__ uint64_t fold_pair(uint64_t acc, int x0, int x1, uint64_t dw, uint64_t mw, uint64_t da, uint64_t ca) {
     const uint64_t f = cvt2(x0, x1);
     if constexpr (WT == QGEMM_TYPE_Q4_0 || WT == QGEMM_TYPE_Q5_0) {
-        return ffma2(dw, ffma2(da, f, ca), acc);
+        ffma2_acc(acc, dw, ffma2(da, f, ca));
     } else if constexpr (WT == QGEMM_TYPE_Q4_1 || WT == QGEMM_TYPE_Q5_1) {
-        return fadd2(acc, ffma2(fmul2(dw, da), f, fmul2(mw, ca)));
+        if constexpr (kRefSeq) {
+            fadd2_acc(acc, ffma2(fmul2(dw, da), f, fmul2(mw, ca)));
+        } else {
+            ffma2_acc(acc, dw, fmul2(da, f));
+            ffma2_acc(acc, mw, ca);
+        }
     } else {
-        return ffma2(fmul2(dw, da), f, acc);
+        ffma2_acc(acc, fmul2(dw, da), f);
     }
+    return acc;
 }
-
 
 }  // namespace qgemm

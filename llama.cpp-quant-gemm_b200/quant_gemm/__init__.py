@@ -23,7 +23,7 @@ import torch
 
 from . import _lib
 from ._lib import (  # noqa: F401  (re-exported constants)
-    GEMM_INPUTS_READY, GEMM_MS_EXACT, GEMM_WEIGHTS_PREPACKED, GEMM_SEQUENTIAL, GEMM_WEIGHTS_STATIC, PATH_AUTO, PATH_GEMV, PATH_GENERIC, PATH_MMA, PATH_TCGEN05,
+    GEMM_FOLD_REFSEQ, GEMM_INPUTS_READY, GEMM_MS_EXACT, GEMM_WEIGHTS_PREPACKED, GEMM_SEQUENTIAL, GEMM_WEIGHTS_STATIC, PATH_AUTO, PATH_GEMV, PATH_GENERIC, PATH_MMA, PATH_TCGEN05,
     Q81_CLAMP127, Q81_ROUND_AWAY, Q81_ROUND_EVEN, Q81_S_FROM_QSUM,
     TYPE_Q4_0, TYPE_Q4_1, TYPE_Q5_0, TYPE_Q5_1, TYPE_Q8_0, TYPE_Q8_1,
 )

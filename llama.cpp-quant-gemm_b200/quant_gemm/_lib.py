@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_PKG, "lib", "libqgemm_sm100.so")
 TYPE_Q4_0, TYPE_Q4_1, TYPE_Q5_0, TYPE_Q5_1, TYPE_Q8_0, TYPE_Q8_1 = 2, 3, 6, 7, 8, 9
 Q81_ROUND_AWAY, Q81_ROUND_EVEN, Q81_S_FROM_QSUM, Q81_CLAMP127 = 0, 1, 2, 4
 GEMM_MS_EXACT, GEMM_SEQUENTIAL, GEMM_WEIGHTS_STATIC, GEMM_INPUTS_READY = 0x1, 0x8, 0x10, 0x20
-GEMM_WEIGHTS_PREPACKED, GEMM_STREAM_ALLOC = 0x40, 0x80
+GEMM_WEIGHTS_PREPACKED, GEMM_STREAM_ALLOC, GEMM_FOLD_REFSEQ = 0x40, 0x80, 0x1000
 PATH_AUTO, PATH_GENERIC, PATH_GEMV, PATH_MMA, PATH_TCGEN05 = 0x000, 0x100, 0x200, 0x300, 0x400
 
 # name -> (restype, argtypes): every symbol include/qgemm.h declares

@@ -297,6 +297,7 @@ def test_full_size_decode_properties(qg, O):
 # prefill path: tcgen05.mma kind::i8 with TMEM accumulators (QGEMM_PATH_TCGEN05)
 # ------------------------------------------------------------------------------------------
 PATHS["tcgen05"] = 0x400
+FOLD_REFSEQ = 0x1000   # QGEMM_FOLD_REFSEQ
 MMQ_SHAPES = [(128, 128, 128), (64, 256, 4096), (200, 300, 1056), (130, 129, 32), (512, 384, 2048)]
 
 
@@ -320,6 +321,8 @@ def test_mmq_gemm_vs_oracle(qg, O, wt, T, F, K):
     assert qg.last_path() == 0x400
     check_c(c, O.gemm(wt, aq, wq, layout="FT"), f"tcgen05 {qo.TYPE_NAMES[wt]} {T}x{F}x{K}")
     # blocks are folded in order b = 0..nb-1 with the reference GPU kernel's FMA sequence: bit-identical
+    # (q4_1 / q5_1: with QGEMM_FOLD_REFSEQ; their default fold associates the same terms differently)
+    c = run_gemm(qg, wt, aq, wq, "tcgen05", flags=FOLD_REFSEQ)
     assert (bits(c) == bits(O.gemm(wt, aq, wq, layout="FT", flags=qo.GEMM_FMA))).all()
 
 
@@ -396,10 +399,12 @@ def test_full_size_config4_q5_1_with_fused_quantize(qg, O):
     aq = host(daq)
     assert (aq == O.quantize_q8_1(host(x))).all()
     rows = np.r_[0:3, 7000:7003, F - 3:F]
-    wq = host(dwq[torch.from_numpy(rows).cuda()])
-    c = host(c1[torch.from_numpy(rows).cuda()])
-    assert (bits(c) == bits(O.gemm(qo.Q5_1, aq, wq, layout="FT", flags=qo.GEMM_FMA))).all()
-    check_c(c, O.gemm(qo.Q5_1, aq, wq, layout="FT"), "config 4 vs CPU-order oracle")
+    ri = torch.from_numpy(rows).cuda()
+    wq = host(dwq[ri])
+    check_c(host(c1[ri]), O.gemm(qo.Q5_1, aq, wq, layout="FT"), "config 4 vs CPU-order oracle")
+    # with the reference's per-block operation sequence the result is the reference GPU kernel's, bit for bit
+    c3 = qg.gemm(dwq, daq, F, T, K, qo.Q5_1, FOLD_REFSEQ)
+    assert (bits(host(c3[ri])) == bits(O.gemm(qo.Q5_1, aq, wq, layout="FT", flags=qo.GEMM_FMA))).all()
 
 
 def test_full_size_config5_q4_0_properties(qg, O):
