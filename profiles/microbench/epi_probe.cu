@@ -137,7 +137,43 @@ __global__ void __launch_bounds__(640, 1) fold_rate(float* out, long long* cyc, 
         const int row = quarter * 32 + lane;
         int x[32];
         const long long t0 = clock64();
-        if constexpr (MODE == 0 || MODE == 1) {
+        if constexpr (MODE == 7 || MODE == 8 || MODE == 9) {
+#pragma unroll 1
+            for (int b = 0; b < nblk; b++) {
+                const int buf = b & 3, j = b & 7;
+                if (MODE != 9) asm volatile("bar.sync 1, 512;" ::: "memory");   // all 16 warps start the block together
+                ld32(tmem + lane_addr + buf * 128 + cgrp * 32, x);
+                wait_ld();
+                const float dl = s_lane[j][row];
+                const float nb = dl * -8.0f;
+                const float4* dc = reinterpret_cast<const float4*>(&s_col[j][cgrp * 32]);
+                if constexpr (MODE == 7) {
+                    fold_half<0, 32>(acc, x, 0, 0, dl, nb, dc);
+                    fold_half<0, 32>(acc, x, 16, 1, dl, nb, dc);
+                } else {
+                    // conversions and FMAs alternate, FMAs two pairs behind, order pinned with asm volatile
+                    float4 d4[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) d4[i] = dc[i];
+                    auto fma_pair = [&](int q) {
+                        const float4 d = d4[q >> 1];
+                        const uint64_t dd = (q & 1) ? pk(d.z, d.w) : pk(d.x, d.y);
+                        uint64_t t;
+                        const uint64_t f = pk(__int_as_float(x[2 * q]), __int_as_float(x[2 * q + 1]));
+                        asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(t) : "l"(pk(dl, dl)), "l"(f), "l"(pk(nb, nb)));
+                        asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[q]) : "l"(dd), "l"(t));
+                    };
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        asm volatile("cvt.rn.f32.s32 %0, %0;" : "+r"(x[2 * i]));
+                        asm volatile("cvt.rn.f32.s32 %0, %0;" : "+r"(x[2 * i + 1]));
+                        if (i >= 2) fma_pair(i - 2);
+                    }
+                    fma_pair(14);
+                    fma_pair(15);
+                }
+            }
+        } else if constexpr (MODE == 0 || MODE == 1) {
 #pragma unroll 1
             for (int b = 0; b < nblk; b++) {
                 const int buf = b & 3, j = b & 7;
@@ -518,6 +554,9 @@ int main(int argc, char** argv) {
         fold_rate<4><<<sms, 640>>>(out, cyc, nblk); if (rep) report("4: 2 x x16 pipelined, magic IADD, 2 scalar FFMA");
         fold_rate<5><<<sms, 640>>>(out, cyc, nblk); if (rep) report("5: 2 x x16 pipelined, I2FP, 2 FFMA2");
         fold_rate<6><<<sms, 640>>>(out, cyc, nblk); if (rep) report("6: as 2, block loop unrolled by 4");
+        fold_rate<7><<<sms, 640>>>(out, cyc, nblk); if (rep) report("7: as 0, all 16 warps barrier-aligned at every block");
+        fold_rate<8><<<sms, 640>>>(out, cyc, nblk); if (rep) report("8: as 7, conversions and FMAs interleaved (pinned order)");
+        fold_rate<9><<<sms, 640>>>(out, cyc, nblk); if (rep) report("9: as 8 without the barrier");
         fold_rate_8w<<<sms, 384>>>(out, cyc, nblk); if (rep) report("8 warps x 64 columns, x16 pipelined, magic IADD, 2 FFMA2");
     }
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
