@@ -373,6 +373,64 @@ def test_mmq_full_size_prefill_properties(qg, O):
     assert (bits(c2) == bits(c[:, perm])).all()
 
 
+def test_baseline_config0_m1_4096x4096_q4_0_all_rows(qg, O):
+    """BASELINE configs[0], exactly: Q4_0 x Q8_1, M=1 N=4096 K=4096, every output against the reference's own CPU
+    gemm_w4a8_reference (include/gemm_reference.h:175-222, compiled in place as oracle/_ref) on operands quantized by
+    the reference's own quantizers; where oracle/_ref is absent the restated oracle (pinned against it) stands in."""
+    T, F, K = 1, 4096, 4096
+    x, w = datagen.uniform(T, F, K, seed=7)      # the reference's step tests draw uniform[-1, 1]
+    if qo.have_ref():
+        R = qo.Reference()
+        aq, wq = R.quantize_row_q8_1_ref(x), R.quantize_row_q4_0_ref(w)
+        ref = R.gemm_include(qo.Q4_0, aq, wq)          # [T, F]
+        assert (aq == O.quantize_q8_1(x)).all() and (wq == O.quantize_weight(qo.Q4_0, w, "include")).all()
+    else:
+        aq, wq = O.quantize_q8_1(x), O.quantize_weight(qo.Q4_0, w, "include")
+        ref = O.gemm(qo.Q4_0, aq, wq, layout="TF")
+    assert (host(qg.quantize_q8_1(dev(x))) == aq).all()
+    c = host(qg.gemm(dev(wq), dev(aq), F, T, K, qo.Q4_0))     # [F, T]
+    assert qg.last_path() == 0x200
+    check_c(c.T, ref, "configs[0] vs gemm_w4a8_reference")
+    s = host(qg.block_sumi(dev(wq), dev(aq), F, T, K, qo.Q4_0))
+    assert (s == O.gemm_sumi(qo.Q4_0, aq, wq)).all()
+
+
+@pytest.mark.parametrize("wt", [qo.Q4_1, qo.Q5_0, qo.Q8_0])
+def test_mmq_full_size_prefill_other_formats(qg, O, wt):
+    """BASELINE config 3's shape (M=512 N=4096 K=4096) for the formats the other full-size tests do not cover:
+    sampled rows against the oracle (bit-identical in the reference GPU kernel's operation order with
+    QGEMM_FOLD_REFSEQ), token-permutation equivariance."""
+    T, F, K = 512, 4096, 4096
+    x, w = datagen.model_like(T, F, K, seed=61 + wt)
+    dwq = {3: qg.quantize_q4_1, 6: qg.quantize_q5_0, 8: qg.quantize_q8_0}[wt](dev(w))
+    daq = qg.quantize_q8_1(dev(x))
+    aq, wq = host(daq), host(dwq)
+    c = host(qg.gemm(dwq, daq, F, T, K, wt))
+    assert qg.last_path() == 0x400
+    rows = np.r_[0:4, 1000:1004, F - 4:F]
+    check_c(c[rows], O.gemm(wt, aq, wq[rows], layout="FT"), f"prefill {qo.TYPE_NAMES[wt]} vs CPU-order oracle")
+    cr = host(qg.gemm(dwq, daq, F, T, K, wt, FOLD_REFSEQ))
+    assert (bits(cr[rows]) == bits(O.gemm(wt, aq, wq[rows], layout="FT", flags=qo.GEMM_FMA))).all()
+    perm = np.random.default_rng(2).permutation(T)
+    c2 = host(qg.gemm(dwq, dev(aq[perm]), F, T, K, wt))
+    assert (bits(c2) == bits(c[:, perm])).all()
+
+
+def test_reference_python_test_file_runs_unchanged(qg):
+    """The reference's own python/tests/test_gemm_q4_0.py, staged unmodified under baseline/_ref/ by
+    __graft_entry__.build() (git-ignored, travels to the GPU box), run with `quant_gemm` resolving to this package."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    test = os.path.join(root, "baseline", "_ref", "python", "tests", "test_gemm_q4_0.py")
+    if not os.path.exists(test):
+        pytest.skip("reference test file not staged (needs /root/reference at build time)")
+    env = dict(os.environ, PYTHONPATH=os.path.join(root, "llama.cpp-quant-gemm_b200") + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    out = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", test], capture_output=True, text=True,
+                         env=env, cwd=os.path.join(root, "baseline", "_ref", "python"), timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+
+
 def _gpu_model_like(T, F, K, seed):
     """Model-like fp32 operands generated on the device (the full-size shapes are too slow to draw on the host)."""
     g = torch.Generator(device="cuda")
