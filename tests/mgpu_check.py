@@ -27,8 +27,9 @@ import qgemm_oracle as qo  # noqa: E402
 
 def main() -> int:
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
-    dev = torch.device("cuda")
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     ctl = dist.new_group(backend="gloo")
     import quant_gemm
