@@ -553,6 +553,29 @@ static cudaError_t launch_mmq_t(const void* act, const void* wgt, float* C, int3
     return e;
 }
 
+cudaError_t launch_quantize_q8_1_tiles(const float* x, uint8_t* a8, float2* as, int T, int Tpad, int K, float coef, uint32_t flags,
+                                       cudaStream_t st);
+
+// fp32 activations straight into the tensor-core path: quantize_q8_1 writes the operand tiles itself, then the
+// native-layout GEMM -- two launches, no block_q8_1 round trip (successor of kernels/gemm/gemm_fused.cuh:76-302).
+// Returns cudaErrorNotSupported where that pairing does not apply (the caller then chains the separate kernels).
+cudaError_t launch_mmq_f32act(int wtype, const float* act_f32, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
+                              int64_t ldc_f, uint32_t flags, uint32_t qflags, void* ws, size_t ws_bytes, int num_sms, cudaStream_t st) {
+    if ((flags & QGEMM_WEIGHTS_PREPACKED) || K % 128 != 0 || !mmq_native_supported(wtype, wgt, T, F, K) || QGEMM_ENV("QGEMM_MMQ_LEGACY") ||
+        QGEMM_ENV("QGEMM_NO_FUSED_QUANT"))
+        return cudaErrorNotSupported;
+    const MmqWs L = mmq_layout(T, F, K);
+    if (ws_bytes < L.w8 || reinterpret_cast<uintptr_t>(ws) % 256 != 0) return cudaErrorNotSupported;
+    float coef = 0.f;
+    if (wtype == QGEMM_TYPE_Q4_0) coef = -8.f;
+    else if (wtype == QGEMM_TYPE_Q5_0) coef = -16.f;
+    else if (wtype == QGEMM_TYPE_Q4_1 || wtype == QGEMM_TYPE_Q5_1) coef = (flags & QGEMM_MS_EXACT) ? 1.f : 0.25f;
+    uint8_t* base = (uint8_t*)ws;
+    if (cudaError_t e = launch_quantize_q8_1_tiles(act_f32, base + L.a8, (float2*)(base + L.as), T, L.Tpad, K, coef, qflags, st)) return e;
+    return launch_mmq_native(wtype, base + L.a8, (const float2*)(base + L.as), wgt, C, nullptr, T, F, K, L.Tpad, ldc_t, ldc_f, flags, num_sms,
+                             st, nullptr);
+}
+
 size_t mmq_prepack_bytes(int wtype, int F, int K) {
     if (block_bytes(wtype) == 0 || wtype == QGEMM_TYPE_Q8_1 || F < 1 || K < 32) return 0;
     return mmq_pack_layout(F, K).total;

@@ -35,6 +35,8 @@ cudaError_t launch_mmq_prepack(int wtype, const void* wgt, void* packed, int F, 
 bool mmq_supported(int wtype, const void* act, const void* wgt, int T, int F, int K);
 size_t mmq_workspace_bytes(int wtype, int T, int F, int K);
 size_t mmq_workspace_need(int wtype, const void* wgt, int T, int F, int K, uint32_t flags);
+cudaError_t launch_mmq_f32act(int wtype, const float* act_f32, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
+                              int64_t ldc_f, uint32_t flags, uint32_t qflags, void* ws, size_t ws_bytes, int num_sms, cudaStream_t st);
 cudaError_t launch_mmq(int wtype, const void* act, const void* wgt, float* C, int32_t* sumi_out, int T, int F, int K,
                        int64_t ldc_t, int64_t ldc_f, uint32_t flags, void* ws, size_t ws_bytes, int num_sms,
                        cudaStream_t, const PeerOut* peer = nullptr);
@@ -390,6 +392,19 @@ int qgemm_gemm_f32act(int wtype, const float* act_f32, const void* weight, float
     const size_t a_q = align_up((size_t)T * (K / kQK) * kQ81Bytes, 256);
     if (K > 0 && (!workspace || workspace_bytes < a_q || !aligned(workspace, 16))) return QGEMM_E_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
+    {   // tensor-core sizes: the quantizer writes the GEMM's operand tiles directly (two launches in all)
+        const uint32_t gflags = flags & 0xffffu, path = gflags & QGEMM_PATH_MASK;
+        const bool tc = !(gflags & QGEMM_SEQUENTIAL) && (path == QGEMM_PATH_TCGEN05 || (path == QGEMM_PATH_AUTO && T >= kMmqMinTokens));
+        if (tc && K > 0 && workspace_bytes > a_q) {
+            const cudaError_t e = launch_mmq_f32act(wtype, act_f32, weight, C, T, F, K, ldc_t, ldc_f, gflags, (flags >> 16) & 0xffu,
+                                                    (char*)workspace + a_q, workspace_bytes - a_q, dev.sms, st);
+            if (e == cudaSuccess) {
+                t_last_path = QGEMM_PATH_TCGEN05;
+                return QGEMM_OK;
+            }
+            if (e != cudaErrorNotSupported) return cuda_fail(e, "gemm_f32act launch");
+        }
+    }
     if (K > 0 &&
         launch_quantize_q8_1(act_f32, workspace, (int64_t)T * (K / kQK), (flags >> 16) & 0xffu, st) != cudaSuccess)
         return QGEMM_E_CUDA;

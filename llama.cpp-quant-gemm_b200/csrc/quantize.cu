@@ -27,12 +27,24 @@ __device__ __forceinline__ int round_half_away(float v) {
 // ---------------------------------------------------------------------------
 constexpr int kQWarps = 8;
 
-template <bool kAlignedX>
+// kTiles: instead of 36-byte blocks the kernel writes what the tensor-core GEMM kernels read -- the s8 values in the
+// 128-byte-swizzled K-major operand tiles a8[K/128][Tpad][128] and (d_a, coef * s_a) in the slabs as[Tpad/128][nb][128]
+// (layout of mmq.cu's activation prepass) -- so that the fp32-activation GEMM is two launches with no q8_1 round trip
+// through HBM.  d, s and q are the same values, rounded the same way, as in the block_q8_1 the plain kernel emits.
+struct Q81Tiles {
+    uint8_t* a8;
+    float2* as;
+    int T, Tpad, nb;   // nb % 4 == 0
+    float coef;
+};
+
+template <bool kAlignedX, bool kTiles>
 __global__ void __launch_bounds__(kQWarps * 32)
-quantize_q8_1_kernel(const float* __restrict__ x, uint32_t* __restrict__ y, int64_t nblocks, uint32_t flags) {
+quantize_q8_1_kernel(const float* __restrict__ x, uint32_t* __restrict__ y, int64_t nblocks, uint32_t flags, const Q81Tiles tl) {
     __shared__ float tile[kQWarps][32][33];
     __shared__ uint32_t stage[kQWarps][32 * 9];
 
+    if constexpr (kTiles) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the GEMM behind us may set itself up
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t b0 = ((int64_t)blockIdx.x * kQWarps + warp) * 32;
     if (b0 >= nblocks) return;
@@ -84,6 +96,20 @@ quantize_q8_1_kernel(const float* __restrict__ x, uint32_t* __restrict__ y, int6
         sw[1 + w] = packed;
     }
     const float s = (flags & QGEMM_Q81_S_FROM_QSUM) ? __fmul_rn(__int2float_rn(sum_q), d) : sum;
+    if constexpr (kTiles) {
+        // lane = block g = t * nb + b; rows past T (tile padding) are quantized zeros: d = s = 0, q = 0
+        const int64_t g = b0 + lane;
+        if (lane < nvalid) {
+            const int t = (int)(g / tl.nb), b = (int)(g - (int64_t)t * tl.nb);
+            const int kc = b >> 2, c = (b & 3) * 2;
+            uint8_t* row = tl.a8 + ((size_t)kc * tl.Tpad + t) * 128;
+            *reinterpret_cast<uint4*>(row + ((c ^ (t & 7)) << 4)) = make_uint4(sw[1], sw[2], sw[3], sw[4]);
+            *reinterpret_cast<uint4*>(row + (((c + 1) ^ (t & 7)) << 4)) = make_uint4(sw[5], sw[6], sw[7], sw[8]);
+            const float dh = __half2float(__float2half_rn(d)), sh = __half2float(__float2half_rn(s));
+            tl.as[((size_t)(t >> 7) * tl.nb + b) * 128 + (t & 127)] = make_float2(dh, __fmul_rn(tl.coef, sh));
+        }
+        return;
+    }
     sw[0] = (uint32_t)__half_as_ushort(__float2half_rn(d)) | ((uint32_t)__half_as_ushort(__float2half_rn(s)) << 16);
     __syncwarp();
 
@@ -102,9 +128,45 @@ cudaError_t launch_quantize_q8_1(const float* x, void* y, int64_t nblocks, uint3
     const int64_t per_cta = (int64_t)kQWarps * 32;
     const unsigned grid = (unsigned)((nblocks + per_cta - 1) / per_cta);
     if ((reinterpret_cast<uintptr_t>(x) & 15) == 0)
-        quantize_q8_1_kernel<true><<<grid, kQWarps * 32, 0, st>>>(x, (uint32_t*)y, nblocks, flags);
+        quantize_q8_1_kernel<true, false><<<grid, kQWarps * 32, 0, st>>>(x, (uint32_t*)y, nblocks, flags, Q81Tiles{});
     else
-        quantize_q8_1_kernel<false><<<grid, kQWarps * 32, 0, st>>>(x, (uint32_t*)y, nblocks, flags);
+        quantize_q8_1_kernel<false, false><<<grid, kQWarps * 32, 0, st>>>(x, (uint32_t*)y, nblocks, flags, Q81Tiles{});
+    note_launch();
+    return cudaGetLastError();
+}
+
+// fp32 x[T][K] -> operand tiles + slabs for the tensor-core kernels (K % 128 == 0).  The source has T rows; the tiles
+// have Tpad: the kernel runs over Tpad * nb blocks and reads zeros past row T.
+__global__ void zero_pad_rows_kernel(uint8_t* a8, float2* as, int T, int Tpad, int nb) {
+    // rows [T, Tpad) of every K chunk and slab: quantized zeros
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int pad = Tpad - T;
+    if (i >= (int64_t)pad * nb) return;
+    const int t = T + (int)(i / nb), b = (int)(i % nb);
+    const int kc = b >> 2, c = (b & 3) * 2;
+    uint8_t* row = a8 + ((size_t)kc * Tpad + t) * 128;
+    *reinterpret_cast<uint4*>(row + ((c ^ (t & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(row + (((c + 1) ^ (t & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+    as[((size_t)(t >> 7) * nb + b) * 128 + (t & 127)] = make_float2(0.f, 0.f);
+}
+
+cudaError_t launch_quantize_q8_1_tiles(const float* x, uint8_t* a8, float2* as, int T, int Tpad, int K, float coef, uint32_t flags,
+                                       cudaStream_t st) {
+    const int nb = K / 32;
+    if (T < 1 || nb < 4 || (nb & 3)) return cudaErrorInvalidValue;
+    if (Tpad > T) {   // at most 127 rows: a sliver in front of the main pass (same stream, so ordered before the GEMM)
+        const int64_t n = (int64_t)(Tpad - T) * nb;
+        zero_pad_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a8, as, T, Tpad, nb);
+        note_launch();
+    }
+    const int64_t nblocks = (int64_t)T * nb;
+    const int64_t per_cta = (int64_t)kQWarps * 32;
+    const unsigned grid = (unsigned)((nblocks + per_cta - 1) / per_cta);
+    const Q81Tiles tl{a8, as, T, Tpad, nb, coef};
+    if ((reinterpret_cast<uintptr_t>(x) & 15) == 0)
+        quantize_q8_1_kernel<true, true><<<grid, kQWarps * 32, 0, st>>>(x, nullptr, nblocks, flags, tl);
+    else
+        quantize_q8_1_kernel<false, true><<<grid, kQWarps * 32, 0, st>>>(x, nullptr, nblocks, flags, tl);
     note_launch();
     return cudaGetLastError();
 }

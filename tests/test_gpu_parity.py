@@ -431,6 +431,31 @@ def test_reference_python_test_file_runs_unchanged(qg):
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
 
 
+@pytest.mark.parametrize("wt", [qo.Q4_0, qo.Q5_1, qo.Q8_0])
+@pytest.mark.parametrize("T", [256, 200])
+def test_fused_quantize_gemm_is_two_launches_and_bit_equal(qg, O, wt, T):
+    """The one-call fp32-activation GEMM at tensor-core sizes: quantize_q8_1 writes the operand tiles itself (no
+    block_q8_1 round trip), then the GEMM kernel -- two launches (three when T is not a multiple of 128: a sliver
+    zeroes the padding rows).  d, s and q must be the values of quantize_row_q8_1_ref: the result equals
+    quantize + GEMM bit for bit for every quantizer flavour, and the oracle's on sampled rows."""
+    F, K = 384, 1024
+    x, w = datagen.model_like(T, F, K, seed=900 + wt + T)
+    x[3, 64:96] = 0.0                      # an all-zero block (d = 0)
+    x[5, :32] = np.float32(0.5) * np.arange(-16, 16, dtype=np.float32)   # exact .5 ties after scaling
+    wq = O.quantize_weight(wt, w)
+    dx, dwq = dev(x), dev(wq)
+    for qf in (0, qo.Q81_ROUND_EVEN, qo.Q81_S_FROM_QSUM | qo.Q81_CLAMP127):
+        qg.reset_launch_count()
+        c1 = qg.gemm_w4a8(dwq, dx, F, T, K, wtype=wt, q81_flags=qf)
+        assert qg.last_path() == 0x400
+        assert qg.launch_count() == (2 if T % 128 == 0 else 3)
+        c2 = qg.gemm(dwq, qg.quantize_q8_1(dx, qf), F, T, K, wt)
+        assert torch.equal(c1, c2), f"flags {qf}"
+    aq = O.quantize_q8_1(x)
+    rows = np.r_[0:8, F - 8:F]
+    check_c(host(qg.gemm_w4a8(dwq, dx, F, T, K, wtype=wt))[rows], O.gemm(wt, aq, wq[rows], layout="FT"), "fused quantize + GEMM vs oracle")
+
+
 def _gpu_model_like(T, F, K, seed):
     """Model-like fp32 operands generated on the device (the full-size shapes are too slow to draw on the host)."""
     g = torch.Generator(device="cuda")
