@@ -214,6 +214,19 @@ QGEMM_API int qgemm_gemm_f32act(int wtype, const float *act_f32, const void *wei
                       size_t workspace_bytes, void *stream);
 
 /*
+ * W4A16 / W8A16: fp32 activations act_f32[T][K] against Q4_0 / Q8_0 weights with NO activation quantization,
+ *     C[t*ldc_t + f*ldc_f] = sum_k act[t][k] * d_w * (q_w - 8)        (q8_0: d_w * q_w)
+ * every product and sum in fp32.  Replaces gemm_w4a16_naive / gemm_w8a16_naive (include/gemm_cuda_naive.cuh:66-143,
+ * 267-283; CPU: gemm_w4a16_reference / gemm_w8a16_reference, include/gemm_reference.h:73-147) and the python
+ * extension's gemm_q4_0_fp32 (python/quant_gemm/csrc/gemm_ops.cu:271-463).  T <= 8: weight-streaming kernel;
+ * larger T: register-tiled fp32 GEMM with in-kernel dequantization; both sum K in a parallel order (<= 1e-5 of
+ * max|C| from the reference).  QGEMM_SEQUENTIAL: one thread per output in the reference kernel's order and FMA
+ * contraction, bit-identical to it; also taken for K % 64 != 0 or act_f32 not 16-byte aligned.  No workspace.
+ */
+QGEMM_API int qgemm_gemm_a16(int wtype, const float *act_f32, const void *weight, float *C, int T, int F, int K,
+                             int64_t ldc_t, int64_t ldc_f, uint32_t flags, void *stream);
+
+/*
  * Test hook for the bit-exactness contract: sumi[(t*F + f)*(K/32) + b] =
  * the int32 block dot product exactly as the selected path computes it
  * (QGEMM_PATH_* in flags picks whose integers are dumped).

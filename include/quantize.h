@@ -15,13 +15,13 @@
 #include "quant_types.h"
 
 inline void quantize_q4_0_cuda(const float* x, block_q4_0* y, int64_t k, cudaStream_t stream = 0) {
-    (void)qgemm_quantize_weight(QGEMM_TYPE_Q4_0, x, y, 1, k, QGEMM_Q81_ROUND_EVEN, (void*)stream);
+    qgemm_dropin_status(qgemm_quantize_weight(QGEMM_TYPE_Q4_0, x, y, 1, k, QGEMM_Q81_ROUND_EVEN, (void*)stream), "quantize_q4_0_cuda");
 }
 inline void quantize_q8_0_cuda(const float* x, block_q8_0* y, int64_t k, cudaStream_t stream = 0) {
-    (void)qgemm_quantize_weight(QGEMM_TYPE_Q8_0, x, y, 1, k, QGEMM_Q81_ROUND_EVEN, (void*)stream);
+    qgemm_dropin_status(qgemm_quantize_weight(QGEMM_TYPE_Q8_0, x, y, 1, k, QGEMM_Q81_ROUND_EVEN, (void*)stream), "quantize_q8_0_cuda");
 }
 inline void quantize_q8_1_cuda(const float* x, block_q8_1* y, int64_t k, cudaStream_t stream = 0) {
-    (void)qgemm_quantize_q8_1(x, y, 1, k, QGEMM_Q81_ROUND_EVEN, (void*)stream);
+    qgemm_dropin_status(qgemm_quantize_q8_1(x, y, 1, k, QGEMM_Q81_ROUND_EVEN, (void*)stream), "quantize_q8_1_cuda");
 }
 
 #endif /* QUANTIZE_H */

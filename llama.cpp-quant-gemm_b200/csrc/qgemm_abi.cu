@@ -32,6 +32,11 @@ cudaError_t launch_gemv_mma(int wtype, const void* act, const void* wgt, float* 
                             int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t, const PeerOut* peer = nullptr);
 size_t mmq_prepack_bytes(int wtype, int F, int K);
 cudaError_t launch_mmq_prepack(int wtype, const void* wgt, void* packed, int F, int K, cudaStream_t);
+bool f32act_supported(int wtype, const void* act, const void* wgt, int K);
+cudaError_t launch_gemm_f32act_dequant(int wtype, const float* act, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
+                                       int64_t ldc_f, int num_sms, cudaStream_t st);
+cudaError_t launch_gemm_f32act_sequential(int wtype, const float* act, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
+                                          int64_t ldc_f, cudaStream_t st);
 bool mmq_supported(int wtype, const void* act, const void* wgt, int T, int F, int K);
 size_t mmq_workspace_bytes(int wtype, int T, int F, int K);
 size_t mmq_workspace_need(int wtype, const void* wgt, int T, int F, int K, uint32_t flags);
@@ -271,8 +276,8 @@ int qgemm_quantize_q8_1(const float* x, void* y, int64_t rows, int64_t K, uint32
     if (!aligned(x, 4) || !aligned(y, 4)) return QGEMM_E_ALIGN;
     DeviceInfo dev;
     if (int rc = device_check(&dev)) return rc;
-    return launch_quantize_q8_1(x, y, rows * (K / kQK), flags, (cudaStream_t)stream) == cudaSuccess ? QGEMM_OK
-                                                                                                   : QGEMM_E_CUDA;
+    const cudaError_t e = launch_quantize_q8_1(x, y, rows * (K / kQK), flags, (cudaStream_t)stream);
+    return e == cudaSuccess ? QGEMM_OK : cuda_fail(e, "quantize_q8_1 launch");
 }
 
 int qgemm_quantize_weight(int wtype, const float* x, void* y, int64_t rows, int64_t K, uint32_t flags, void* stream) {
@@ -282,9 +287,8 @@ int qgemm_quantize_weight(int wtype, const float* x, void* y, int64_t rows, int6
     if (!aligned(x, 4) || !aligned(y, 2)) return QGEMM_E_ALIGN;
     DeviceInfo dev;
     if (int rc = device_check(&dev)) return rc;
-    return launch_quantize_weight(wtype, x, y, rows * (K / kQK), flags, (cudaStream_t)stream) == cudaSuccess
-               ? QGEMM_OK
-               : QGEMM_E_CUDA;
+    const cudaError_t e = launch_quantize_weight(wtype, x, y, rows * (K / kQK), flags, (cudaStream_t)stream);
+    return e == cudaSuccess ? QGEMM_OK : cuda_fail(e, "quantize_weight launch");
 }
 
 int qgemm_dequantize(int type, const void* x, float* y, int64_t rows, int64_t K, void* stream) {
@@ -295,8 +299,8 @@ int qgemm_dequantize(int type, const void* x, float* y, int64_t rows, int64_t K,
     if (!aligned(x, 2) || !aligned(y, 16)) return QGEMM_E_ALIGN;
     DeviceInfo dev;
     if (int rc = device_check(&dev)) return rc;
-    return launch_dequantize(type, x, y, rows * (K / kQK), (cudaStream_t)stream) == cudaSuccess ? QGEMM_OK
-                                                                                              : QGEMM_E_CUDA;
+    const cudaError_t e = launch_dequantize(type, x, y, rows * (K / kQK), (cudaStream_t)stream);
+    return e == cudaSuccess ? QGEMM_OK : cuda_fail(e, "dequantize launch");
 }
 
 size_t qgemm_workspace_bytes(int wtype, int T, int F, int K, uint32_t flags) {
@@ -412,6 +416,32 @@ int qgemm_gemm_f32act(int wtype, const float* act_f32, const void* weight, float
                     workspace_bytes - a_q, st, dev);
 }
 
+int qgemm_gemm_a16(int wtype, const float* act_f32, const void* weight, float* C, int T, int F, int K, int64_t ldc_t,
+                   int64_t ldc_f, uint32_t flags, void* stream) {
+    if ((wtype != QGEMM_TYPE_Q4_0 && wtype != QGEMM_TYPE_Q8_0) || T < 0 || F < 0 || K < 0 || (K % kQK) != 0) return QGEMM_E_BADARG;
+    if (T == 0 || F == 0) return QGEMM_OK;
+    if (!act_f32 || !weight || !C) return QGEMM_E_BADARG;
+    if (!aligned(act_f32, 4) || !aligned(weight, 2) || !aligned(C, 4)) return QGEMM_E_ALIGN;
+    DeviceInfo dev;
+    if (int rc = device_check(&dev)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (K == 0) {
+        const int64_t n = (int64_t)T * F;
+        fill_zero_strided<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(C, T, F, ldc_t, ldc_f);
+        note_launch();
+        return cudaGetLastError() == cudaSuccess ? QGEMM_OK : cuda_fail(cudaGetLastError(), "gemm_a16 fill");
+    }
+    cudaError_t e;
+    if (!(flags & QGEMM_SEQUENTIAL) && f32act_supported(wtype, act_f32, weight, K)) {
+        e = launch_gemm_f32act_dequant(wtype, act_f32, weight, C, T, F, K, ldc_t, ldc_f, dev.sms, st);
+        t_last_path = T <= 8 ? QGEMM_PATH_GEMV : QGEMM_PATH_MMA;
+    } else {
+        e = launch_gemm_f32act_sequential(wtype, act_f32, weight, C, T, F, K, ldc_t, ldc_f, st);
+        t_last_path = QGEMM_PATH_GENERIC;
+    }
+    return e == cudaSuccess ? QGEMM_OK : cuda_fail(e, "gemm_a16 launch");
+}
+
 int qgemm_sumi(int wtype, const void* act_q8_1, const void* weight, int32_t* sumi, int T, int F, int K, uint32_t flags,
                void* workspace, size_t workspace_bytes, void* stream) {
     if (int rc = check_gemm_args(wtype, act_q8_1, weight, sumi, T, F, K)) return rc;
@@ -429,7 +459,7 @@ int qgemm_sumi(int wtype, const void* act_q8_1, const void* weight, int32_t* sum
     } else {
         e = launch_sumi_generic(wtype, act_q8_1, weight, sumi, T, F, K, st);
     }
-    return e == cudaSuccess ? QGEMM_OK : QGEMM_E_CUDA;
+    return e == cudaSuccess ? QGEMM_OK : cuda_fail(e, "sumi launch");
 }
 
 static int make_peer_out(const qgemm_peers* peers, PeerOut* po) {

@@ -271,6 +271,34 @@ def gemm_w4a8(weight_q: torch.Tensor, activation: torch.Tensor, M: int, N: int, 
     return out
 
 
+def gemm_a16(weight_q: torch.Tensor, activation: torch.Tensor, M: int, N: int, K: int, wtype: int = TYPE_Q4_0,
+             flags: int = 0) -> torch.Tensor:
+    """fp32 activations [M tokens, K] against Q4_0 / Q8_0 weights [N rows, K/32, bytes] with NO activation quantization
+    -> [M, N] (the include/ convention, like gemm_w4a16_naive and the python extension's gemm_q4_0_fp32).
+    flags=GEMM_SEQUENTIAL reproduces the reference GPU kernel bit for bit."""
+    _check(weight_q.is_cuda and activation.is_cuda, "Inputs must be CUDA tensors")
+    _check(weight_q.dtype == torch.uint8, "Weight must be uint8")
+    _check(activation.dtype == torch.float32, "Activation must be float32")
+    _check(wtype in (TYPE_Q4_0, TYPE_Q8_0), "W4A16 / W8A16 exist for Q4_0 and Q8_0 weights")
+    _check(K % 32 == 0, f"K must be divisible by 32, got {K}")
+    _check(weight_q.numel() == N * (K // 32) * BLOCK_BYTES[wtype], "Weight shape mismatch")
+    _check(activation.numel() == M * K, "Activation shape mismatch")
+    weight_q = weight_q.contiguous()
+    activation = activation.contiguous()
+    out = torch.empty((M, N), dtype=torch.float32, device=weight_q.device)
+    with torch.cuda.device(weight_q.device):
+        rc = _lib.lib().qgemm_gemm_a16(wtype, activation.data_ptr(), weight_q.data_ptr(), out.data_ptr(), M, N, K, N, 1, flags,
+                                       _stream(weight_q))
+    _lib.raise_on_error(rc, "gemm_a16")
+    return out
+
+
+def gemm_q4_0_fp32(weight_q: torch.Tensor, activation: torch.Tensor, M: int, N: int, K: int) -> torch.Tensor:
+    """Q4_0 weights [N, K/32, 18] x fp32 activations [M, K] -> [M, N]: the entry the reference's extension implements
+    (python/quant_gemm/csrc/gemm_ops.cu:271-463, gemm_q4_0_fp32_cuda) but never binds."""
+    return gemm_a16(weight_q, activation, M, N, K, TYPE_Q4_0)
+
+
 def block_sumi(weight_q: torch.Tensor, activation_q: torch.Tensor, M: int, N: int, K: int, wtype: int,
                flags: int = 0) -> torch.Tensor:
     """Test hook: int32 sumi[N tokens, M rows, K/32] exactly as the selected path computes it."""

@@ -4,7 +4,8 @@
 //
 //   dropin_check <dir>    reads  <dir>/x.f32 [T*K], <dir>/w_q4_0.bin, <dir>/w_q5_1.bin, <dir>/w_q8_0.bin, <dir>/dims.txt
 //                         writes <dir>/a_q8_1.bin, c_inc_q4_0.f32 [T,F], c_inc_q8_0.f32 [T,F],
-//                                c_ggml_q4_0.f32 [F,T], c_ggml_q5_1.f32 [F,T], c_tile2d.f32 [F,T], c_big.f32 [F,T]
+//                                c_ggml_q4_0.f32 [F,T], c_ggml_q5_1.f32 [F,T], c_tile2d.f32 [F,T], c_big.f32 [F,T],
+//                                c_w4a16.f32 / c_w8a16.f32 / c_adapter16.f32 / c_hook16.f32 [T,F] (fp32 activations), c_hook.f32 [T,F]
 #include <cstdio>
 #include <string>
 #include <vector>
@@ -20,9 +21,11 @@
 #include "kernels/gemm/gemm_async_copy.cuh"
 #include "kernels/gemm/gemm_vectorized.cuh"
 
-// a stand-in for ggml.h's tensor (only the fields the adapter touches)
-struct ggml_tensor { int type; int64_t ne[4]; void* data; };
+// a stand-in for ggml.h (only what the adapter touches): the complete tensor type + the macro that says it is there
+#define GGML_MAX_DIMS 4
+struct ggml_tensor { int type; int64_t ne[GGML_MAX_DIMS]; void* data; };
 #include "include/llama_adapter.h"
+#include "compat/ggml_cuda_mul_mat.cuh"
 
 static std::vector<char> slurp(const std::string& p) {
     FILE* f = fopen(p.c_str(), "rb");
@@ -76,8 +79,27 @@ int main(int argc, char** argv) {
 
     // ggml_tensor adapter: activation [K, M], weights [K, N], output [N, M]
     ggml_tensor ta{QUANT_TYPE_Q8_1, {K, T, 1, 1}, a}, tw{QUANT_TYPE_Q4_0, {K, F, 1, 1}, w4}, to{QUANT_TYPE_F32, {F, T, 1, 1}, c};
-    if (gemm_w4a8_from_ggml(&ta, &tw, &to, "dp4a", st) != 0) return 4;
+    gemm_w4a8_from_ggml(&ta, &tw, &to, "dp4a");                                   // the reference's declared signature
+    if (qgemm_dropin_last_status() != 0) return 4;
     fetch("c_adapter.f32");
+    int dm, dn, dk;
+    extract_dims_from_tensor(&ta, &tw, &dm, &dn, &dk);
+    if (dm != T || dn != F || dk != K || !validate_tensor_types(&ta, &tw, &to, QUANT_TYPE_Q8_1, QUANT_TYPE_Q4_0, QUANT_TYPE_F32)) return 6;
+    ggml_tensor bad{QUANT_TYPE_Q4_0, {K, T, 1, 1}, a};                           // wrong activation type: reported, not silently dropped
+    gemm_w4a8_from_ggml(&bad, &tw, &to);
+    if (qgemm_dropin_last_status() != QGEMM_E_BADARG) return 7;
+
+    // fp32 activations, no quantization: W4A16 / W8A16 launchers, adapter and the mul_mat-shaped hooks
+    gemm_w4a16_naive(x, w4, c, T, F, K, st);  fetch("c_w4a16.f32");
+    gemm_w8a16_naive(x, w8, c, T, F, K, st);  fetch("c_w8a16.f32");
+    ggml_tensor tx{QUANT_TYPE_F32, {K, T, 1, 1}, x};
+    gemm_w4a16_from_ggml(&tx, &tw, &to);
+    if (qgemm_dropin_last_status() != 0) return 8;
+    fetch("c_adapter16.f32");
+    if (qgemm_ggml_cuda_op_mul_mat_f32act(QUANT_TYPE_Q4_0, (const char*)w4, x, c, K, 0, F, T, F, st) != 0) return 9;
+    fetch("c_hook16.f32");
+    if (qgemm_ggml_cuda_op_mul_mat_q(QUANT_TYPE_Q4_0, (const char*)w4, (const char*)a, c, K, 0, F, T, K, F, st) != 0) return 10;
+    fetch("c_hook.f32");
 
     // the unchanged launcher reaches the tensor-core path on its own (scratch from the stream's pool) ...
     printf("launcher path 0x%x\n", qgemm_last_path());

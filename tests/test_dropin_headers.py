@@ -34,11 +34,11 @@ def test_dropin_program_builds_and_static_checks_pass():
 def test_reference_entry_point_names_are_all_present():
     """Every hot-path launcher name of the reference's headers exists in ours."""
     names = {
-        "include/gemm_cuda_naive.cuh": ["gemm_w4a8_naive", "gemm_w8a8_naive"],
+        "include/gemm_cuda_naive.cuh": ["gemm_w4a8_naive", "gemm_w8a8_naive", "gemm_w4a16_naive", "gemm_w8a16_naive"],
         "include/gemm_cuda_tiled.cuh": ["gemm_w4a8_tiled"],
         "include/gemm_cuda_dp4a.cuh": ["gemm_w4a8_dp4a", "gemm_w8a8_dp4a", "gemm_w4a8_tiled_dp4a", "gemm_w4a8_vectorized_dp4a"],
         "include/quantize.h": ["quantize_q4_0_cuda", "quantize_q8_0_cuda", "quantize_q8_1_cuda"],
-        "include/llama_adapter.h": ["gemm_w4a8_from_ggml", "validate_tensor_types", "extract_dims_from_tensor"],
+        "include/llama_adapter.h": ["gemm_w4a8_from_ggml", "gemm_w4a16_from_ggml", "validate_tensor_types", "extract_dims_from_tensor"],
         "kernels/gemm/gemm_quant_formats.cuh": ["gemm_q4_0_q8_1", "gemm_q4_1_q8_1", "gemm_q5_0_q8_1", "gemm_q5_1_q8_1", "gemm_q8_0_q8_1"],
         "kernels/gemm/gemm_warp_optimized.cuh": ["gemm_q4_0_q8_1_warp", "gemm_q4_0_q8_1_warp_v2", "gemm_q4_0_q8_1_warp_prefetch",
                                                  "gemm_q4_0_q8_1_warp_multirow", "gemm_q4_0_q8_1_warp_multirow8", "gemm_q4_0_q8_1_smem",
@@ -78,6 +78,12 @@ def test_dropin_program_matches_oracle(tmp_path):
     def load(name, shape):
         return np.fromfile(tmp_path / name, dtype=np.float32).reshape(shape)
 
+    # fp32-activation entries against the oracle's restatement of gemm_w4a16_reference / gemm_w8a16_reference
+    for name, wt, key in [("c_w4a16.f32", qo.Q4_0, "q4_0"), ("c_w8a16.f32", qo.Q8_0, "q8_0"), ("c_adapter16.f32", qo.Q4_0, "q4_0"),
+                          ("c_hook16.f32", qo.Q4_0, "q4_0")]:
+        r16 = O.gemm_f32act_dequant(wt, x, wq[key], layout="TF")
+        assert qo.max_norm_err(load(name, (T, F)), r16) <= 1e-5, name
+    assert qo.max_norm_err(load("c_hook.f32", (T, F)).T, ref["q4_0"]) <= 1e-5
     for name, key, transposed in [("c_inc_q4_0.f32", "q4_0", True), ("c_inc_q4_0_b.f32", "q4_0", True),
                                   ("c_inc_q8_0.f32", "q8_0", True), ("c_ggml_q4_0.f32", "q4_0", False),
                                   ("c_ggml_q5_1.f32", "q5_1", False), ("c_tile2d.f32", "q4_0", False),

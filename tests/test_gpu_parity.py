@@ -456,6 +456,46 @@ def test_fused_quantize_gemm_is_two_launches_and_bit_equal(qg, O, wt, T):
     check_c(host(qg.gemm_w4a8(dwq, dx, F, T, K, wtype=wt))[rows], O.gemm(wt, aq, wq[rows], layout="FT"), "fused quantize + GEMM vs oracle")
 
 
+# ------------------------------------------------------------------------------------------
+# W4A16 / W8A16: fp32 activations, no activation quantization (qgemm_gemm_a16)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("wt", [qo.Q4_0, qo.Q8_0])
+@pytest.mark.parametrize("T,F,K", [(1, 300, 4096), (3, 129, 1024), (8, 64, 11008), (9, 70, 256), (100, 130, 1024), (64, 64, 96)])
+def test_gemm_a16_vs_oracle_and_reference_gpu(qg, O, wt, T, F, K):
+    """Against the oracle's restatement of gemm_w4a16_reference / gemm_w8a16_reference (include/gemm_reference.h:73-147,
+    pinned bit for bit against the reference in test_oracle_golden.py): <= 1e-5 on the fast kernels; the sequential
+    kernel is bit-identical to the FMA-order result = what nvcc builds from gemm_w4a16_naive_kernel, and to that
+    kernel itself run on this device when oracle/_ref is present."""
+    x, w = datagen.model_like(T, F, K, seed=K + T)
+    wq = O.quantize_weight(wt, w, "include")
+    ref = O.gemm_f32act_dequant(wt, x, wq, layout="TF")
+    c = host(qg.gemm_a16(dev(wq), dev(x), T, F, K, wt))
+    check_c(c, ref, f"a16 {qo.TYPE_NAMES[wt]} {T}x{F}x{K}")
+    cs = host(qg.gemm_a16(dev(wq), dev(x), T, F, K, wt, qg.GEMM_SEQUENTIAL))
+    assert (bits(cs) == bits(O.gemm_f32act_dequant(wt, x, wq, layout="TF", flags=qo.GEMM_FMA))).all()
+    if qo.have_ref():
+        R = qo.Reference()
+        fn = getattr(R.lib, "ref_gpu_gemm_w4a16_naive" if wt == qo.Q4_0 else "ref_gpu_gemm_w8a16_naive", None)
+        if fn is not None:
+            r = torch.empty((T, F), device="cuda")
+            dx, dw = dev(x), dev(wq)
+            torch.cuda.synchronize()
+            fn(dx.data_ptr(), dw.data_ptr(), r.data_ptr(), T, F, K, None)
+            assert (bits(host(r)) == bits(cs)).all()
+
+
+def test_gemm_q4_0_fp32_python_entry(qg, O):
+    """python gemm_q4_0_fp32(weight_q [N,K/32,18], activation [M,K]) -> [M,N] (gemm_ops.cu:431-463)."""
+    M, N, K = 5, 96, 512
+    x, w = datagen.uniform(M, N, K, seed=3)
+    wq = O.quantize_weight(qo.Q4_0, w)
+    out = qg.gemm_q4_0_fp32(dev(wq), dev(x), M, N, K)
+    assert out.shape == (M, N) and out.dtype == torch.float32
+    check_c(host(out), O.gemm_f32act_dequant(qo.Q4_0, x, wq, layout="TF"), "gemm_q4_0_fp32")
+    with pytest.raises(RuntimeError):
+        qg.gemm_q4_0_fp32(dev(wq), dev(x), M, N, K + 32)
+
+
 def _gpu_model_like(T, F, K, seed):
     """Model-like fp32 operands generated on the device (the full-size shapes are too slow to draw on the host)."""
     g = torch.Generator(device="cuda")
