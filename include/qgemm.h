@@ -156,6 +156,11 @@ QGEMM_API int qgemm_dequantize(int type, const void *x, float *y, int64_t rows, 
  * workspace: qgemm_workspace_bytes() bytes of device memory, 256-byte aligned
  * (may be NULL when that returns 0).  Alignment: act 4 bytes, weight 2 bytes, C 4 bytes
  * (the reference's requirement); rows that are 16-byte aligned take the fast paths.
+ * A call of tensor-core size (T >= 96) that brings no scratch -- no workspace, none registered with
+ * qgemm_set_default_workspace(), no QGEMM_STREAM_ALLOC -- returns QGEMM_E_WORKSPACE instead of running on the
+ * weight-streaming passes at a fraction of the speed; QGEMM_PATH_MMA requests those passes explicitly.
+ * With K % 256 == 0 the scratch holds only the repacked activations (T * K * 1.0625 bytes): the weights are read in
+ * their native layout.
  */
 QGEMM_API size_t qgemm_workspace_bytes(int wtype, int T, int F, int K, uint32_t flags);
 

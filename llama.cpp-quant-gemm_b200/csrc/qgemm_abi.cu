@@ -207,7 +207,11 @@ static int run_gemm(int wtype, const void* act, const void* wgt, float* C, int T
         path = QGEMM_PATH_TCGEN05;
     }
     if (path == QGEMM_PATH_AUTO) {
-        if (T >= kMmqMinTokens && mmq_supported(wtype, act, wgt, T, F, K) && ws && ws_bytes >= mmq_workspace_need(wtype, wgt, T, F, K, flags))
+        const bool tc_size = T >= kMmqMinTokens && mmq_supported(wtype, act, wgt, T, F, K);
+        // a prefill-sized call without scratch would fall to the weight-streaming passes at a fraction of the speed:
+        // say so instead of doing it silently (QGEMM_PATH_MMA asks for that path explicitly, QGEMM_STREAM_ALLOC lends scratch)
+        if (tc_size && (!ws || ws_bytes < mmq_workspace_need(wtype, wgt, T, F, K, flags))) return QGEMM_E_WORKSPACE;
+        if (tc_size)
             path = QGEMM_PATH_TCGEN05;
         else if (T >= (K > 8192 ? kMmaMinTokens + 1 : kMmaMinTokens) && gemv_mma_supported(wtype, act, wgt, T, F, K))
             path = QGEMM_PATH_MMA;
@@ -344,7 +348,7 @@ int qgemm_gemm_group(int wtype, const void* act_q8_1, int nmat, const void* cons
     for (int m = 0; m < nmat; m++) fast = fast && gemv_supported(wtype, act_q8_1, weights[m], Fs[m], K);
     if (!fast || T > 8) {  // same results, one launch per matrix
         for (int m = 0; m < nmat; m++)
-            if (int rc = run_gemm(wtype, act_q8_1, weights[m], Cs[m], T, Fs[m], K, ldc_t, ldc_f, flags, nullptr, 0, st, dev))
+            if (int rc = run_gemm(wtype, act_q8_1, weights[m], Cs[m], T, Fs[m], K, ldc_t, ldc_f, flags | QGEMM_STREAM_ALLOC, nullptr, 0, st, dev))
                 return rc;
         return QGEMM_OK;
     }

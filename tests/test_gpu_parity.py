@@ -346,12 +346,16 @@ def test_mmq_fuzz_ms_exact_and_layouts(qg, O, wt):
     assert L.qgemm_gemm(wt, da.data_ptr(), dw.data_ptr(), out.data_ptr(), T, F, nb * 32, F, 1, 0, ws.data_ptr(), nws,
                         torch.cuda.current_stream().cuda_stream) == 0
     assert (bits(host(out).T) == bits(c)).all()
-    # without a workspace AUTO must still answer (weight-streaming path), and a forced path must say so
-    assert L.qgemm_gemm(wt, da.data_ptr(), dw.data_ptr(), out.data_ptr(), T, F, nb * 32, F, 1, 0, None, 0,
-                        torch.cuda.current_stream().cuda_stream) == 0
-    check_c(host(out).T, c, "auto without workspace")
-    assert L.qgemm_gemm(wt, da.data_ptr(), dw.data_ptr(), out.data_ptr(), T, F, nb * 32, F, 1, 0x400, None, 0,
-                        torch.cuda.current_stream().cuda_stream) == -5
+    # a prefill-sized call without scratch is refused (QGEMM_E_WORKSPACE) rather than demoted silently; the streaming
+    # path remains available on request, and QGEMM_STREAM_ALLOC lends the scratch
+    st = torch.cuda.current_stream().cuda_stream
+    assert L.qgemm_gemm(wt, da.data_ptr(), dw.data_ptr(), out.data_ptr(), T, F, nb * 32, F, 1, 0, None, 0, st) == -5
+    assert L.qgemm_gemm(wt, da.data_ptr(), dw.data_ptr(), out.data_ptr(), T, F, nb * 32, F, 1, 0x400, None, 0, st) == -5
+    assert L.qgemm_gemm(wt, da.data_ptr(), dw.data_ptr(), out.data_ptr(), T, F, nb * 32, F, 1, 0x300, None, 0, st) == 0
+    check_c(host(out).T, c, "streaming path without workspace")
+    assert L.qgemm_gemm(wt, da.data_ptr(), dw.data_ptr(), out.data_ptr(), T, F, nb * 32, F, 1, 0x80, None, 0, st) == 0
+    assert qg.last_path() == 0x400
+    check_c(host(out).T, c, "auto with stream-pool scratch")
 
 
 def test_mmq_full_size_prefill_properties(qg, O):
