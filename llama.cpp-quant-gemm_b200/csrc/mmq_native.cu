@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int mt = tile % p.tiles_m;
                 for (int kc = 0; kc < nkc; kc++) {
-                    PROF_WAIT(pf_wait, ptx::mbar_wait_backoff(&empty[s], ph ^ 1));
+                    PROF_WAIT(pf_wait, ptx::mbar_wait_backoff_guarded(&empty[s], ph ^ 1));
                     uint8_t* st = stages + s * kStageBytes;
                     ptx::mbar_arrive_expect_tx(&full[s], kBM * kKC + kBPS * kBM * 8);
                     ptx::bulk_g2s(st + kStageA, p.a8 + ((size_t)kc * p.Tpad + (size_t)mt * kBM) * kKC, kBM * kKC, &full[s]);
@@ -235,13 +235,13 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
         PROF_DECL;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             for (int kc = 0; kc < nkc; kc++) {
-                PROF_WAIT(pf_wait, ptx::mbar_wait(&full[s], ph));
+                PROF_WAIT(pf_wait, ptx::mbar_wait_guarded(&full[s], ph));
                 t5::fence_after();
                 const uint64_t adesc = t5::smem_desc(ptx::smem_u32(stages + s * kStageBytes + kStageA));
                 const uint64_t bdesc = t5::smem_desc(ptx::smem_u32(stages + s * kStageBytes + kStageW));
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
-                    PROF_WAIT(pf_wait2, ptx::mbar_wait(&tempty[h], tph ^ 1));
+                    PROF_WAIT(pf_wait2, ptx::mbar_wait_guarded(&tempty[h], tph ^ 1));
                     t5::fence_after();
                     if (lane == 0) {
                         // one instruction = one quantization block (32 bytes of K = +2 in the >>4 address field)
@@ -284,11 +284,11 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
         uint32_t ph = 0, rph = 0;
         PROF_DECL;
         for (int q = 0; q < total; q++) {
-            PROF_WAIT(pf_wait, ptx::mbar_wait(&rawfull[r], rph));
+            PROF_WAIT(pf_wait, ptx::mbar_wait_guarded(&rawfull[r], rph));
             const uint8_t* rslot = raw_ring + r * raw_stage_bytes<WT>();
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                PROF_WAIT(pf_wait2, ptx::mbar_wait(&empty[s], ph ^ 1));
+                PROF_WAIT(pf_wait2, ptx::mbar_wait_guarded(&empty[s], ph ^ 1));
 #pragma unroll
                 for (int i = 0; i < kRowsPerThread; i++) {
                     const int row = u + i * kUT;
@@ -326,12 +326,12 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
             for (int i = 0; i < kEpiCols / 2; i++) acc[i] = 0ull;
 #pragma unroll 1
             for (int kc = 0; kc < nkc; kc++) {
-                PROF_WAIT(pf_wait, ptx::mbar_wait(&full[s], ph));  // scale slabs of this stage are visible
+                PROF_WAIT(pf_wait, ptx::mbar_wait_guarded(&full[s], ph));  // scale slabs of this stage are visible
                 const uint8_t* st = stages + s * kStageBytes;
 #pragma unroll 1
                 for (int h = 0; h < 2; h++) {   // one TMEM half = two blocks per iteration; not unrolled further so that the
                                                 // accumulators keep their registers
-                    PROF_WAIT(pf_wait2, ptx::mbar_wait(&tfull[h], tph));
+                    PROF_WAIT(pf_wait2, ptx::mbar_wait_guarded(&tfull[h], tph));
                     t5::fence_after();
 #pragma unroll
                     for (int jj = 0; jj < 2; jj++) {

@@ -34,22 +34,35 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// A wait that would never end (a protocol bug, a lost copy) must not hang the device: after ~2 s of polling the
-// thread reports which barrier it was stuck on and traps, which fails the launch with a CUDA error instead.
+// A wait that would never end (a protocol bug, a lost copy) must not hang the device: after a bounded number of polls
+// the thread traps, which fails the launch with a CUDA error instead.  -DQGEMM_MBAR_DEBUG also prints which barrier
+// it was stuck on (the printf call costs every kernel a stack frame, so it is off in the shipped build).
+#ifdef QGEMM_MBAR_DEBUG
 static __device__ __noinline__ void mbar_timeout(uint64_t* bar, uint32_t parity) {
     printf("qgemm: mbarrier wait timed out: block %d thread %d barrier smem+0x%x parity %u\n", (int)blockIdx.x, (int)threadIdx.x,
            smem_u32(bar), parity);
     __trap();
 }
-// polls before giving up: try_wait itself suspends the thread for a hardware-defined slice, so this is seconds
-constexpr uint32_t kMbarTimeoutPolls = 1u << 26;
+#else
+__device__ __forceinline__ void mbar_timeout(uint64_t*, uint32_t) { asm volatile("trap;"); }
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+// for single-thread role warps that share a scheduler with busy math warps: sleep between polls
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(32);
+}
+// Guarded forms (the prefill kernel with its five barrier rings uses these): polls before giving up -- try_wait itself
+// suspends the thread for a hardware-defined slice, so this is seconds.  The decode kernels keep the bare loops: the
+// poll counter cost them 3 % on the decode stack (A/B on one box).
+constexpr uint32_t kMbarTimeoutPolls = 1u << 26;
+__device__ __forceinline__ void mbar_wait_guarded(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     for (uint32_t n = 0; !mbar_try_wait(bar, parity); n++)
         if (n > kMbarTimeoutPolls) mbar_timeout(bar, parity);
 }
-// for single-thread role warps that share a scheduler with busy math warps: sleep between polls
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_backoff_guarded(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     for (uint32_t n = 0; !mbar_try_wait(bar, parity); n++) {
         __nanosleep(32);
