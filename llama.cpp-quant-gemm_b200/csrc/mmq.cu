@@ -137,9 +137,11 @@ __device__ __forceinline__ void repack_act_body(int64_t gid, const uint8_t* __re
 }
 __global__ void __launch_bounds__(256)
 mmq_repack_act_kernel(const uint8_t* __restrict__ act, uint8_t* __restrict__ a8, float2* __restrict__ as, int T,
-                      int Tpad, int nb, int nbp, float coef) {
+                      int Tpad, int nb, int nbp, float coef, unsigned* zero = nullptr, int nzero = 0) {
     ptx::griddep_launch_dependents();   // the GEMM kernel behind this one may set itself up while we run
-    repack_act_body((int64_t)blockIdx.x * blockDim.x + threadIdx.x, act, a8, as, T, Tpad, nb, nbp, coef);
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < nzero) zero[gid] = 0u;    // split-K arrival counters of the GEMM behind us
+    repack_act_body(gid, act, a8, as, T, Tpad, nb, nbp, coef);
 }
 
 // ---------------------------------------------------------------------------
@@ -457,6 +459,10 @@ bool mmq_supported(int wtype, const void* act, const void* wgt, int T, int F, in
 }
 
 bool mmq_native_supported(int wtype, const void* wgt, int T, int F, int K);
+size_t mmq_native_split_bytes(int T, int F, int K, uint32_t flags, int num_sms);
+unsigned* mmq_native_split_counters(int T, int F, int K, uint32_t flags, int num_sms, void* split_ws, size_t split_ws_bytes, bool dump,
+                                    const PeerOut* peer, int* count);
+constexpr int kSplitPlanSms = 148;   // workspace sizing happens without a device: plan for a full B200
 
 // Scratch of the tensor-core path.  Shapes the native-layout kernel takes (K % 256 == 0) need the repacked activations
 // only; the prepass kernel also keeps the unpacked weights there.  The pointer-free form (qgemm_workspace_bytes) assumes
@@ -464,22 +470,25 @@ bool mmq_native_supported(int wtype, const void* wgt, int T, int F, int K);
 size_t mmq_workspace_bytes(int wtype, int T, int F, int K) {
     if (T < 1 || F < 1 || K < 32) return 0;
     const MmqWs L = mmq_layout(T, F, K);
-    return mmq_native_supported(wtype, nullptr, T, F, K) ? L.w8 : L.total;
+    // the split-K scratch of small-T calls is sized for the default flags (FOLD_REFSEQ needs none)
+    return mmq_native_supported(wtype, nullptr, T, F, K) ? L.w8 + mmq_native_split_bytes(T, F, K, 0, kSplitPlanSms) : L.total;
 }
 size_t mmq_workspace_need(int wtype, const void* wgt, int T, int F, int K, uint32_t flags) {
     if (T < 1 || F < 1 || K < 32) return 0;
     const MmqWs L = mmq_layout(T, F, K);
-    if ((flags & QGEMM_WEIGHTS_PREPACKED) || (mmq_native_supported(wtype, wgt, T, F, K) && !QGEMM_ENV("QGEMM_MMQ_LEGACY"))) return L.w8;
+    if (flags & QGEMM_WEIGHTS_PREPACKED) return L.w8;
+    // split-K scratch is optional: a call that brings only the activation part runs unsplit
+    if (mmq_native_supported(wtype, wgt, T, F, K) && !QGEMM_ENV("QGEMM_MMQ_LEGACY")) return L.w8;
     return L.total;
 }
 
 cudaError_t launch_mmq_native(int wtype, const uint8_t* a8, const float2* as, const void* wgt, float* C, int32_t* sumi, int T,
                               int F, int K, int Tpad, int64_t ldc_t, int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t st,
-                              const PeerOut* peer);
+                              const PeerOut* peer, void* split_ws, size_t split_ws_bytes);
 
 template <int WT>
 static cudaError_t launch_mmq_t(const void* act, const void* wgt, float* C, int32_t* sumi, int T, int F, int K,
-                                int64_t ldc_t, int64_t ldc_f, uint32_t flags, void* ws, int num_sms, cudaStream_t st,
+                                int64_t ldc_t, int64_t ldc_f, uint32_t flags, void* ws, size_t ws_bytes, int num_sms, cudaStream_t st,
                                 const PeerOut* peer) {
     const MmqWs L = mmq_layout(T, F, K);
     const int nb = K / 32, nbp = L.nkc * kBlocksPerStage;
@@ -494,12 +503,15 @@ static cudaError_t launch_mmq_t(const void* act, const void* wgt, float* C, int3
     const unsigned act_blocks = (unsigned)(((int64_t)L.Tpad * nbp + 255) / 256);
     if (!(flags & QGEMM_WEIGHTS_PREPACKED) && mmq_native_supported(WT, wgt, T, F, K) && !QGEMM_ENV("QGEMM_MMQ_LEGACY")) {
         // native blocks are unpacked inside the kernel (mmq_native.cu): only the activations are repacked per call
+        int ncount = 0;
+        unsigned* counters = mmq_native_split_counters(T, F, K, flags, num_sms, ws_bytes > L.w8 ? base + L.w8 : nullptr,
+                                                       ws_bytes > L.w8 ? ws_bytes - L.w8 : 0, sumi != nullptr, peer, &ncount);
         mmq_repack_act_kernel<<<act_blocks, 256, 0, st>>>((const uint8_t*)act, base + L.a8, (float2*)(base + L.as), T, L.Tpad,
-                                                          nb, nbp, coef);
+                                                          nb, nbp, coef, counters, ncount);
         note_launch();
         if (cudaError_t e = cudaGetLastError()) return e;
         return launch_mmq_native(WT, base + L.a8, (const float2*)(base + L.as), wgt, C, sumi, T, F, K, L.Tpad, ldc_t, ldc_f, flags,
-                                 num_sms, st, peer);
+                                 num_sms, st, peer, ws_bytes > L.w8 ? base + L.w8 : nullptr, ws_bytes > L.w8 ? ws_bytes - L.w8 : 0);
     }
     if (flags & QGEMM_WEIGHTS_PREPACKED) {  // `wgt` is a qgemm_prepack_weights() buffer: nothing to unpack
         const MmqPack P = mmq_pack_layout(F, K);
@@ -554,7 +566,7 @@ static cudaError_t launch_mmq_t(const void* act, const void* wgt, float* C, int3
 }
 
 cudaError_t launch_quantize_q8_1_tiles(const float* x, uint8_t* a8, float2* as, int T, int Tpad, int K, float coef, uint32_t flags,
-                                       cudaStream_t st);
+                                       cudaStream_t st, unsigned* zero, int nzero);
 
 // fp32 activations straight into the tensor-core path: quantize_q8_1 writes the operand tiles itself, then the
 // native-layout GEMM -- two launches, no block_q8_1 round trip (successor of kernels/gemm/gemm_fused.cuh:76-302).
@@ -571,9 +583,13 @@ cudaError_t launch_mmq_f32act(int wtype, const float* act_f32, const void* wgt, 
     else if (wtype == QGEMM_TYPE_Q5_0) coef = -16.f;
     else if (wtype == QGEMM_TYPE_Q4_1 || wtype == QGEMM_TYPE_Q5_1) coef = (flags & QGEMM_MS_EXACT) ? 1.f : 0.25f;
     uint8_t* base = (uint8_t*)ws;
-    if (cudaError_t e = launch_quantize_q8_1_tiles(act_f32, base + L.a8, (float2*)(base + L.as), T, L.Tpad, K, coef, qflags, st)) return e;
+    int ncount = 0;
+    unsigned* counters = mmq_native_split_counters(T, F, K, flags, num_sms, ws_bytes > L.w8 ? base + L.w8 : nullptr,
+                                                   ws_bytes > L.w8 ? ws_bytes - L.w8 : 0, false, nullptr, &ncount);
+    if (cudaError_t e = launch_quantize_q8_1_tiles(act_f32, base + L.a8, (float2*)(base + L.as), T, L.Tpad, K, coef, qflags, st, counters, ncount))
+        return e;
     return launch_mmq_native(wtype, base + L.a8, (const float2*)(base + L.as), wgt, C, nullptr, T, F, K, L.Tpad, ldc_t, ldc_f, flags, num_sms,
-                             st, nullptr);
+                             st, nullptr, ws_bytes > L.w8 ? base + L.w8 : nullptr, ws_bytes > L.w8 ? ws_bytes - L.w8 : 0);
 }
 
 size_t mmq_prepack_bytes(int wtype, int F, int K) {
@@ -608,11 +624,11 @@ cudaError_t launch_mmq(int wtype, const void* act, const void* wgt, float* C, in
     if (ws_bytes < mmq_workspace_need(wtype, wgt, T, F, K, flags) || reinterpret_cast<uintptr_t>(ws) % 256 != 0)
         return cudaErrorInvalidValue;
     switch (wtype) {
-    case QGEMM_TYPE_Q4_0: return launch_mmq_t<QGEMM_TYPE_Q4_0>(act, wgt, C, sumi_out, T, F, K, ldc_t, ldc_f, flags, ws, num_sms, st, peer);
-    case QGEMM_TYPE_Q4_1: return launch_mmq_t<QGEMM_TYPE_Q4_1>(act, wgt, C, sumi_out, T, F, K, ldc_t, ldc_f, flags, ws, num_sms, st, peer);
-    case QGEMM_TYPE_Q5_0: return launch_mmq_t<QGEMM_TYPE_Q5_0>(act, wgt, C, sumi_out, T, F, K, ldc_t, ldc_f, flags, ws, num_sms, st, peer);
-    case QGEMM_TYPE_Q5_1: return launch_mmq_t<QGEMM_TYPE_Q5_1>(act, wgt, C, sumi_out, T, F, K, ldc_t, ldc_f, flags, ws, num_sms, st, peer);
-    case QGEMM_TYPE_Q8_0: return launch_mmq_t<QGEMM_TYPE_Q8_0>(act, wgt, C, sumi_out, T, F, K, ldc_t, ldc_f, flags, ws, num_sms, st, peer);
+    case QGEMM_TYPE_Q4_0: return launch_mmq_t<QGEMM_TYPE_Q4_0>(act, wgt, C, sumi_out, T, F, K, ldc_t, ldc_f, flags, ws, ws_bytes, num_sms, st, peer);
+    case QGEMM_TYPE_Q4_1: return launch_mmq_t<QGEMM_TYPE_Q4_1>(act, wgt, C, sumi_out, T, F, K, ldc_t, ldc_f, flags, ws, ws_bytes, num_sms, st, peer);
+    case QGEMM_TYPE_Q5_0: return launch_mmq_t<QGEMM_TYPE_Q5_0>(act, wgt, C, sumi_out, T, F, K, ldc_t, ldc_f, flags, ws, ws_bytes, num_sms, st, peer);
+    case QGEMM_TYPE_Q5_1: return launch_mmq_t<QGEMM_TYPE_Q5_1>(act, wgt, C, sumi_out, T, F, K, ldc_t, ldc_f, flags, ws, ws_bytes, num_sms, st, peer);
+    case QGEMM_TYPE_Q8_0: return launch_mmq_t<QGEMM_TYPE_Q8_0>(act, wgt, C, sumi_out, T, F, K, ldc_t, ldc_f, flags, ws, ws_bytes, num_sms, st, peer);
     default: return cudaErrorInvalidValue;
     }
 }

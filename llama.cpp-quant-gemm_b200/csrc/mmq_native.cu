@@ -76,6 +76,9 @@ struct Params {
     int T, F, nb, nkc, Tpad;
     int64_t ldc_t, ldc_f;
     int tiles_m, tiles_n;
+    int ksplit;            // K is cut into ksplit equal ranges of whole raw stages; work unit = (tile, range)
+    float* partial;        // ksplit > 1: [tile][range][128 tokens][128 rows] partial sums
+    unsigned* tile_count;  //             arrivals per tile (returns to zero)
     int stages, raw_stages;
     int dbg;
     PeerOut peer;
@@ -175,6 +178,7 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
     uint64_t* tfull = rawfull + kMaxRaw;                      // [2]          MMA commit per TMEM half
     uint64_t* tempty = tfull + 2;                             // [2]          16 epilogue warps
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    volatile int* split_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
     uint8_t* stages = smem + kBarBytes;
     uint8_t* raw_ring = stages + nstages * kStageBytes;
     float* out_tile = reinterpret_cast<float*>(raw_ring + nraw * raw_stage_bytes<WT>());   // [kBN][kBM], only with p.tma_out
@@ -183,6 +187,11 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
     const int nkc = p.nkc;
     const int nbp = nkc * kBPS;
     const int ntiles = p.tiles_m * p.tiles_n;
+    // Work units: every tile once per K range.  With few tiles (T <= 256 at Llama widths) the K loop is split so that the
+    // whole chip works on the call; the ranges of a tile are added in FIXED order by whichever CTA finishes last.
+    const int ksplit = p.ksplit;
+    const int nkc_u = nkc / ksplit;             // operand stages per unit (even: whole raw stages)
+    const int units = ntiles * ksplit;          // unit u = (tile u % ntiles, range u / ntiles)
 
     if (threadIdx.x == kWarpProd * 32) {
         for (int s = 0; s < kMaxStages; s++) {
@@ -210,9 +219,10 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
             int s = 0;
             uint32_t ph = 0;
             PROF_DECL;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int tile = u % ntiles, kc0 = (u / ntiles) * nkc_u;
                 const int mt = tile % p.tiles_m;
-                for (int kc = 0; kc < nkc; kc++) {
+                for (int kc = kc0; kc < kc0 + nkc_u; kc++) {
                     PROF_WAIT(pf_wait, ptx::mbar_wait_backoff_guarded(&empty[s], ph ^ 1));
                     uint8_t* st = stages + s * kStageBytes;
                     ptx::mbar_arrive_expect_tx(&full[s], kBM * kKC + kBPS * kBM * 8);
@@ -233,8 +243,8 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
         int s = 0;
         uint32_t ph = 0, tph = 0;
         PROF_DECL;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            for (int kc = 0; kc < nkc; kc++) {
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            for (int kc = 0; kc < nkc_u; kc++) {
                 PROF_WAIT(pf_wait, ptx::mbar_wait_guarded(&full[s], ph));
                 t5::fence_after();
                 const uint64_t adesc = t5::smem_desc(ptx::smem_u32(stages + s * kStageBytes + kStageA));
@@ -265,17 +275,18 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
         const int u = threadIdx.x - kWarpUnpack * 32;   // this thread owns weight rows u, u + 64 of the tile
         constexpr int kRow = raw_row_bytes<WT>();
         constexpr int kHalf = kBPS * Fmt<WT>::bytes;
-        const int nrs = nkc >> 1;                         // raw stages per tile
-        const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-        const int total = my_tiles * nrs;                 // raw stages of this CTA, tiles back to back
-        // issue side: (tile, rs) of the next raw stage to request, and the slot it goes to
-        int itile = blockIdx.x, irs = 0, islot = 0, issued = 0;
+        const int nrs = nkc_u >> 1;                       // raw stages per unit
+        const int my_units = (units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int total = my_units * nrs;                 // raw stages of this CTA, units back to back
+        // issue side: (unit, rs) of the next raw stage to request, and the slot it goes to
+        int iunit = blockIdx.x, irs = 0, islot = 0, issued = 0;
         auto issue = [&]() {   // one 2-D tensor load: the next 8 raw blocks of the tile's 128 rows (rows >= F arrive as zeros)
             if (u == 0) {
+                const int itile = iunit % ntiles, rs0 = (iunit / ntiles) * nrs;
                 ptx::mbar_arrive_expect_tx(&rawfull[islot], (uint32_t)raw_stage_bytes<WT>());
-                tma_load_2d(raw_ring + islot * raw_stage_bytes<WT>(), &wmap, irs * (kRow / 2), (itile / p.tiles_m) * kBN, &rawfull[islot]);
+                tma_load_2d(raw_ring + islot * raw_stage_bytes<WT>(), &wmap, (rs0 + irs) * (kRow / 2), (itile / p.tiles_m) * kBN, &rawfull[islot]);
             }
-            if (++irs == nrs) { irs = 0; itile += gridDim.x; }
+            if (++irs == nrs) { irs = 0; iunit += gridDim.x; }
             if (++islot == nraw) islot = 0;
             issued++;
         };
@@ -319,13 +330,14 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
         int s = 0;
         uint32_t ph = 0, tph = 0;
         PROF_DECL;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int tile = u % ntiles, ks = u / ntiles, kc0 = ks * nkc_u;
             const int mt = tile % p.tiles_m, nt = tile / p.tiles_m;
             uint64_t acc[kEpiCols / 2];  // fp32 accumulators as packed pairs (columns 2i, 2i+1)
 #pragma unroll
             for (int i = 0; i < kEpiCols / 2; i++) acc[i] = 0ull;
 #pragma unroll 1
-            for (int kc = 0; kc < nkc; kc++) {
+            for (int kc = kc0; kc < kc0 + nkc_u; kc++) {
                 PROF_WAIT(pf_wait, ptx::mbar_wait_guarded(&full[s], ph));  // scale slabs of this stage are visible
                 const uint8_t* st = stages + s * kStageBytes;
 #pragma unroll 1
@@ -375,6 +387,43 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
                 if (++s == nstages) { s = 0; ph ^= 1; }
             }
             if constexpr (!kDump) {
+                if (ksplit > 1) {
+                    // this unit's partial tile -> scratch; the CTA that completes the tile adds the ranges in order
+                    // 0 .. ksplit-1 (a fixed association, whatever the arrival order) and stores C
+                    float* part = p.partial + ((size_t)tile * ksplit + ks) * (kBM * kBN) + (size_t)row * kBN + cgrp * kEpiCols;
+#pragma unroll
+                    for (int i = 0; i < kEpiCols / 4; i++) {
+                        float4 v;
+                        unpk(acc[2 * i], v.x, v.y);
+                        unpk(acc[2 * i + 1], v.z, v.w);
+                        __stcg(reinterpret_cast<float4*>(part) + i, v);
+                    }
+                    __threadfence();
+                    ptx::bar_sync(3, kEpiWarps * 32);
+                    if (threadIdx.x == 0) {
+                        const unsigned prev = atomicAdd(p.tile_count + tile, 1u);
+                        const int last = (prev == (unsigned)ksplit - 1u);
+                        if (last) p.tile_count[tile] = 0u;       // ready for the next call
+                        *split_flag = last;
+                    }
+                    ptx::bar_sync(3, kEpiWarps * 32);
+                    const bool last = *split_flag != 0;
+                    ptx::bar_sync(3, kEpiWarps * 32);            // the flag may be rewritten by the next unit
+                    if (!last) continue;
+                    __threadfence();
+                    const float* p0 = p.partial + (size_t)tile * ksplit * (kBM * kBN) + (size_t)row * kBN + cgrp * kEpiCols;
+#pragma unroll
+                    for (int i = 0; i < kEpiCols / 4; i++) {
+                        float4 sum = __ldcg(reinterpret_cast<const float4*>(p0) + i);
+                        for (int q = 1; q < ksplit; q++) {
+                            const float4 v = __ldcg(reinterpret_cast<const float4*>(p0 + (size_t)q * (kBM * kBN)) + i);
+                            sum.x = __fadd_rn(sum.x, v.x); sum.y = __fadd_rn(sum.y, v.y);
+                            sum.z = __fadd_rn(sum.z, v.z); sum.w = __fadd_rn(sum.w, v.w);
+                        }
+                        acc[2 * i] = pk(sum.x, sum.y);
+                        acc[2 * i + 1] = pk(sum.z, sum.w);
+                    }
+                }
                 const int t = mt * kBM + row;
                 if (p.tma_out) {
                     // Fused all-gather, bulk variant (see mmq.cu): the tile is staged as [f][t] and carried to every rank's
@@ -495,7 +544,7 @@ static cudaError_t launch_t(Params p, const void* wgt, bool refseq, int num_sms,
     if (cudaError_t e = smem_optin(fn, smem)) return e;
     const int ntiles = p.tiles_m * p.tiles_n;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(min(ntiles, num_sms));
+    cfg.gridDim = dim3(min(ntiles * p.ksplit, num_sms));
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -519,16 +568,64 @@ bool mmq_native_supported(int wtype, const void* wgt, int T, int F, int K) {
     return reinterpret_cast<uintptr_t>(wgt) % 16 == 0 && nat::encode_tiled_fn() != nullptr;   // nullptr counts as aligned
 }
 
-// a8 / as: the activation prepass of mmq.cu (Tpad tokens, nkc operand stages)
+// Split-K factor for a call: 1 when the tiles alone fill the chip (or the caller wants the reference's summation order);
+// otherwise the largest number of equal K ranges (whole raw stages each, at least four operand stages) that still fits
+// ONE wave of work units.  Measured on 4096-wide weights, K = 4096: T = 128 (32 tiles) 62 -> 40 us with 4 ranges,
+// T = 256 (64 tiles) 64.5 -> 48 us with 2; splitting into more than one wave was slower than not splitting (T = 384:
+// 85 vs 64.5 us), every unit paying its own pipeline fill and reduction.
+int mmq_native_ksplit(int T, int F, int K, uint32_t flags, int num_sms) {
+    if ((flags & QGEMM_FOLD_REFSEQ) || QGEMM_ENV("QGEMM_MMQ_NO_SPLITK")) return 1;
+    const int tiles = ((T + nat::kBM - 1) / nat::kBM) * ((F + nat::kBN - 1) / nat::kBN), nkc = K / nat::kKC;
+    int best = 1;
+    for (int s : {2, 3, 4, 6, 8}) {
+        if (nkc % (2 * s) != 0 || nkc / s < 4 || tiles * s > num_sms) continue;
+        best = s;
+    }
+    return best;
+}
+size_t mmq_native_split_bytes(int T, int F, int K, uint32_t flags, int num_sms) {
+    const int s = mmq_native_ksplit(T, F, K, flags, num_sms);
+    if (s == 1) return 0;
+    const size_t tiles = (size_t)((T + nat::kBM - 1) / nat::kBM) * ((F + nat::kBN - 1) / nat::kBN);
+    return tiles * s * nat::kBM * nat::kBN * sizeof(float) + (tiles * sizeof(unsigned) + 255) / 256 * 256;
+}
+
+// Where the arrival counters of a split-K call live inside its scratch (nullptr / 0: the call runs unsplit).  They must be
+// zero when the GEMM kernel starts: the activation prepass in front of it clears them (a memset node between the two
+// kernels would break their programmatic dependency and cost ~15 us).
+unsigned* mmq_native_split_counters(int T, int F, int K, uint32_t flags, int num_sms, void* split_ws, size_t split_ws_bytes, bool dump,
+                                    const PeerOut* peer, int* count) {
+    *count = 0;
+    if (dump || (peer && peer->world > 1)) return nullptr;
+    const int ks = mmq_native_ksplit(T, F, K, flags, num_sms);
+    if (ks == 1 || !split_ws || split_ws_bytes < mmq_native_split_bytes(T, F, K, flags, num_sms) || reinterpret_cast<uintptr_t>(split_ws) % 16 != 0)
+        return nullptr;
+    const size_t tiles = (size_t)((T + nat::kBM - 1) / nat::kBM) * ((F + nat::kBN - 1) / nat::kBN);
+    *count = (int)tiles;
+    return (unsigned*)((char*)split_ws + tiles * ks * nat::kBM * nat::kBN * sizeof(float));
+}
+
+// a8 / as: the activation prepass of mmq.cu (Tpad tokens, nkc operand stages); split_ws: mmq_native_split_bytes() bytes whose
+// counters (mmq_native_split_counters) the caller has cleared on this stream
 cudaError_t launch_mmq_native(int wtype, const uint8_t* a8, const float2* as, const void* wgt, float* C, int32_t* sumi, int T,
                               int F, int K, int Tpad, int64_t ldc_t, int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t st,
-                              const PeerOut* peer) {
+                              const PeerOut* peer, void* split_ws, size_t split_ws_bytes) {
     nat::Params p;
     p.a8 = a8; p.as = as; p.C = C; p.sumi = sumi;
     p.T = T; p.F = F; p.nb = K / 32; p.nkc = K / nat::kKC; p.Tpad = Tpad;
     p.ldc_t = ldc_t; p.ldc_f = ldc_f;
     p.tiles_m = Tpad / nat::kBM; p.tiles_n = (F + nat::kBN - 1) / nat::kBN;
     p.stages = 0; p.raw_stages = 0;
+    p.ksplit = 1; p.partial = nullptr; p.tile_count = nullptr;
+    {
+        int ncount = 0;
+        unsigned* counters = mmq_native_split_counters(T, F, K, flags, num_sms, split_ws, split_ws_bytes, sumi != nullptr, peer, &ncount);
+        if (counters) {
+            p.ksplit = mmq_native_ksplit(T, F, K, flags, num_sms);
+            p.partial = (float*)split_ws;
+            p.tile_count = counters;
+        }
+    }
     const bool refseq = (flags & QGEMM_FOLD_REFSEQ) != 0;
     p.dbg = QGEMM_ENV("QGEMM_MMQ_DBG") ? atoi(QGEMM_ENV("QGEMM_MMQ_DBG")) : 0;
     p.peer = peer ? *peer : PeerOut{};

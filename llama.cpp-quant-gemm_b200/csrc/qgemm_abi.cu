@@ -1,5 +1,6 @@
 // qgemm_abi.cu -- the extern "C" surface of libqgemm_sm100.so (include/qgemm.h):
 // argument validation, device check, path selection, launch bookkeeping.
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -189,7 +190,8 @@ static int run_gemm(int wtype, const void* act, const void* wgt, float* C, int T
     void* pool_ws = nullptr;
     if (!ws && (flags & QGEMM_STREAM_ALLOC) && (path == QGEMM_PATH_TCGEN05 || (path == QGEMM_PATH_AUTO && T >= kMmqMinTokens)) &&
         mmq_supported(wtype, act, wgt, T, F, K)) {
-        const size_t need = align_up(mmq_workspace_need(wtype, wgt, T, F, K, flags), 256);
+        // what the call needs, or what it can use (the split-K scratch of small-T calls), whichever is larger
+        const size_t need = align_up(std::max(mmq_workspace_need(wtype, wgt, T, F, K, flags), mmq_workspace_bytes(wtype, T, F, K)), 256);
         if (scratch_alloc(&pool_ws, need, st) == cudaSuccess) {
             ws = pool_ws;
             ws_bytes = need;

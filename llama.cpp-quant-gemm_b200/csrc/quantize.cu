@@ -36,6 +36,8 @@ struct Q81Tiles {
     float2* as;
     int T, Tpad, nb;   // nb % 4 == 0
     float coef;
+    unsigned* zero;    // split-K arrival counters of the GEMM behind this kernel: cleared here
+    int nzero;
 };
 
 template <bool kAlignedX, bool kTiles>
@@ -44,7 +46,11 @@ quantize_q8_1_kernel(const float* __restrict__ x, uint32_t* __restrict__ y, int6
     __shared__ float tile[kQWarps][32][33];
     __shared__ uint32_t stage[kQWarps][32 * 9];
 
-    if constexpr (kTiles) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the GEMM behind us may set itself up
+    if constexpr (kTiles) {
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the GEMM behind us may set itself up
+        const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (gid < tl.nzero) tl.zero[gid] = 0u;
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t b0 = ((int64_t)blockIdx.x * kQWarps + warp) * 32;
     if (b0 >= nblocks) return;
@@ -151,7 +157,7 @@ __global__ void zero_pad_rows_kernel(uint8_t* a8, float2* as, int T, int Tpad, i
 }
 
 cudaError_t launch_quantize_q8_1_tiles(const float* x, uint8_t* a8, float2* as, int T, int Tpad, int K, float coef, uint32_t flags,
-                                       cudaStream_t st) {
+                                       cudaStream_t st, unsigned* zero, int nzero) {
     const int nb = K / 32;
     if (T < 1 || nb < 4 || (nb & 3)) return cudaErrorInvalidValue;
     if (Tpad > T) {   // at most 127 rows: a sliver in front of the main pass (same stream, so ordered before the GEMM)
@@ -162,7 +168,7 @@ cudaError_t launch_quantize_q8_1_tiles(const float* x, uint8_t* a8, float2* as, 
     const int64_t nblocks = (int64_t)T * nb;
     const int64_t per_cta = (int64_t)kQWarps * 32;
     const unsigned grid = (unsigned)((nblocks + per_cta - 1) / per_cta);
-    const Q81Tiles tl{a8, as, T, Tpad, nb, coef};
+    const Q81Tiles tl{a8, as, T, Tpad, nb, coef, zero, nzero};
     if ((reinterpret_cast<uintptr_t>(x) & 15) == 0)
         quantize_q8_1_kernel<true, true><<<grid, kQWarps * 32, 0, st>>>(x, nullptr, nblocks, flags, tl);
     else

@@ -659,13 +659,14 @@ def test_peer_store_protocol_single_gpu(qg, O, wt, T):
     assert L.qgemm_gemm_peers(wt, da.data_ptr(), dw.data_ptr(), ps, 64, F, K, 1, 64, 0, st) == -5
 
 
-@pytest.mark.parametrize("wt,T", [(qo.Q4_0, 200), (qo.Q5_1, 130), (qo.Q8_0, 96)])
-def test_peer_store_protocol_prefill_single_gpu(qg, O, wt, T):
+@pytest.mark.parametrize("wt,T,K", [(qo.Q4_0, 200, 1056), (qo.Q5_1, 130, 1056), (qo.Q8_0, 96, 1056), (qo.Q4_0, 256, 1024),
+                                    (qo.Q5_1, 130, 2048)])
+def test_peer_store_protocol_prefill_single_gpu(qg, O, wt, T, K):
     """Same stand-in as above for the tcgen05 epilogue: the tile goes to both 'ranks' and is bit-identical
     to the plain tensor-core call; launch 1 of each step waits for launch 0 through the wait kernel."""
     from quant_gemm import _lib
     L = _lib.lib()
-    F, K, world, steps = 300, 1056, 2, 3
+    F, world, steps = 300, 2, 3   # K = 1056: the prepass kernel; K % 256 == 0: the native-layout kernel
     x, w = datagen.model_like(T, F, K, seed=170 + wt)
     aq, wq = O.quantize_q8_1(x), O.quantize_weight(wt, w)
     da, dw = dev(aq), dev(wq)
@@ -694,7 +695,11 @@ def test_peer_store_protocol_prefill_single_gpu(qg, O, wt, T):
     check_c(plain, O.gemm(wt, aq, wq, layout="FT"), "tcgen05 vs oracle")
     for b in bufs:
         for li in range(2):
-            assert (bits(host(b[li])) == bits(plain)).all()
+            if K % 256:
+                assert (bits(host(b[li])) == bits(plain)).all()
+            else:   # the plain call may split K over the idle SMs (another summation order); peer launches never do
+                check_c(host(b[li]), plain, "peer stores vs the plain call")
+                assert (bits(host(b[li])) == bits(host(bufs[0][0]))).all()
     assert int(flag[0]) == steps * 2 * world and int(done[0]) == 0 and int(step[0]) == steps
 
 
@@ -728,7 +733,10 @@ def test_peer_multicast_destination_single_gpu(qg, O, wt, T):
         assert L.qgemm_peer_wait(ps, st) == 0
         assert L.qgemm_peer_step_advance(step.data_ptr(), st) == 0
     plain = host(qg.gemm(dw, da, F, T, K, wt, flags=path))
-    assert (bits(host(mc)) == bits(plain)).all()
+    if T <= 8:
+        assert (bits(host(mc)) == bits(plain)).all()
+    else:   # the plain tensor-core call may split K over the idle SMs (another summation order); peer launches never do
+        check_c(host(mc), plain, "multicast destination vs the plain call")
     check_c(host(mc), O.gemm(wt, aq, wq, layout="FT"), "multicast destination vs oracle")
     for b in bufs:
         assert (host(b) == -2.0).all()
