@@ -265,6 +265,30 @@ def sharded_c5(torch, dist, quant_gemm, dev, world, rank, ctl, reps=3):
     return res
 
 
+def add_c5_efficiency(res, world):
+    """Strong-scaling efficiency of the sharded shape against the single-GPU time of the same build (committed by the
+    N=1 run of this round, profiles/r02_bench_n1.json); the N=1 run records its own time as the reference."""
+    ref_ms = None
+    p = os.path.join(ROOT, "profiles", "r02_bench_n1.json")
+    if os.path.exists(p):
+        try:
+            ref_ms = json.load(open(p))["extra"]["sharded_c5"]["compute_only"]["ms"]
+        except (KeyError, ValueError):
+            ref_ms = None
+    if world == 1:
+        res["single_gpu_ms"] = res["compute_only"]["ms"]
+        return
+    if ref_ms is None:
+        return
+    res["single_gpu_ms"] = ref_ms
+    res["single_gpu_source"] = "profiles/r02_bench_n1.json"
+    for k in ("compute_only", "nccl_all_gather", "fused_peer_stores", "fused_peer_stores_unicast"):
+        if k in res and isinstance(res[k], dict) and "ms" in res[k]:
+            res[k]["speedup_vs_1gpu"] = ref_ms / res[k]["ms"]
+            res[k]["efficiency"] = ref_ms / res[k]["ms"] / world
+    res["baseline_it_beats"] = "nccl_all_gather (local GEMM, then ncclAllGather of C in place)"
+
+
 def workload_config(n_gpus, tp=1):
     if n_gpus == 1:
         par = "1 GPU"
@@ -533,7 +557,15 @@ def main():
         r = bench_detail.time_prefill(torch, quant_gemm, WTYPE, 512, 4096, 4096, reps=5)
         extra = {"prefill_q4_0_M512_N4096_K4096": {"us": r["us"], "tops": r["tops"], "path": r["path"],
                                                    "frac_of_nominal_int8_4500_tops": r["tops"] / 4500.0,
-                                                   "note": "whole qgemm_gemm call incl. operand prepass, L2 flushed between reps"}}
+                                                   "note": "BASELINE configs[2]; whole qgemm_gemm call incl. the activation prepass "
+                                                           "(weights are unpacked inside the kernel), L2 flushed between reps"}}
+        r = bench_detail.time_prefill(torch, quant_gemm, 7, 2048, 14336, 4096, reps=3, fused_f32=True)
+        extra["prefill_q5_1_M2048_N14336_K4096_incl_quantize"] = {
+            "us": r["us"], "tops": r["tops"], "path": r["path"], "frac_of_nominal_int8_4500_tops": r["tops"] / 4500.0,
+            "note": "BASELINE configs[3]; fp32 activations in, quantize_q8_1 inside the call (two launches), L2 flushed between reps"}
+        extra["prefill_ceiling_note"] = ("the per-block scale fold runs on the CUDA cores: one I2FP + two packed FMAs per output pair and "
+                                         "quantization block; profiles/microbench/epi_probe.cu measures 469 cycles per 128x128 block for "
+                                         "that sequence alone (13.6 % of the int8 MMA rate), profiles/r02_prefill_knockouts.md")
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -574,6 +606,7 @@ def main():
         wd.start()
         try:
             extra["sharded_c5"] = sharded_c5(torch, dist, quant_gemm, dev, world, rank, ctl)
+            add_c5_efficiency(extra["sharded_c5"], world)
         except Exception as ex:  # noqa: BLE001 -- reported, the headline stands
             extra["sharded_c5"] = {"error": repr(ex)[:300]}
         wd.cancel()

@@ -110,13 +110,87 @@ def time_prefill(torch, quant_gemm, wtype, T, F, K, flags=0, reps=5, fused_f32=F
             "path": hex(quant_gemm.last_path())}
 
 
+def time_reference_gpu(torch, wtype, T, F, K, reps=3):
+    """The reference's own GPU kernels (oracle/_ref, compiled in place from /root/reference for sm_100a) on the same
+    device and the same shapes, as a reported column: gemm_q4_0_q8_1_tile2d (its best decode-style kernel),
+    gemm_w4a8_tiled_dp4a (include/) and gemm_quant_kernel (kernels/gemm, one thread per output).  Q4_0 only, like those
+    kernels.  Returns {} when oracle/_ref is absent."""
+    import qgemm_oracle as qo
+    if not qo.have_ref() or wtype != 2:
+        return {}
+    R = qo.Reference()
+    dev = torch.device("cuda")
+    w = make_weights(torch, wtype, F, K, 1, dev)[0]
+    import quant_gemm
+    aq = quant_gemm.quantize_q8_1(torch.randn((T, K), device=dev))
+    out = torch.empty((F, T), device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    res = {}
+    L = R.lib
+    cands = {
+        "ref_tile2d_us": lambda: L.ref_gpu_gemm_q4_0_tile2d(w.data_ptr(), aq.data_ptr(), out.data_ptr(), F, T, K, None),
+        "ref_tiled_dp4a_us": lambda: L.ref_gpu_gemm_w4a8_tiled_dp4a(aq.data_ptr(), w.data_ptr(), out.data_ptr(), T, F, K, None),
+        "ref_quant_kernel_us": lambda: L.ref_gpu_gemm_quant(wtype, w.data_ptr(), aq.data_ptr(), out.data_ptr(), F, T, K, None),
+    }
+    for name, fn in cands.items():
+        if name == "ref_tile2d_us" and T > 64:
+            continue   # a decode-style kernel: minutes at prefill sizes
+        torch.cuda.synchronize()
+        fn()
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) * 1e3)
+        res[name] = best
+    return res
+
+
+def run_vs_reference(out_path):
+    """BASELINE configs 1-3 shapes: ours next to the reference's GPU kernels on the same B200 (L2 flushed before every call)."""
+    import torch
+    import quant_gemm
+    rows = []
+    for (T, F, K) in [(1, 4096, 4096), (1, 11008, 4096), (8, 11008, 4096), (512, 4096, 4096)]:
+        dev = torch.device("cuda")
+        w = make_weights(torch, 2, F, K, 1, dev)[0]
+        aq = quant_gemm.quantize_q8_1(torch.randn((T, K), device=dev))
+        out = torch.empty((F, T), device=dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        quant_gemm.gemm(w, aq, F, T, K, 2, 0x10, out=out)
+        best = 1e30
+        for _ in range(5):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            quant_gemm.gemm(w, aq, F, T, K, 2, 0x10, out=out)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) * 1e3)
+        r = {"type": "q4_0", "T": T, "F": F, "K": K, "ours_us_cold_l2": best, "path": hex(quant_gemm.last_path())}
+        r.update(time_reference_gpu(torch, 2, T, F, K))
+        for k in list(r):
+            if k.startswith("ref_") and k.endswith("_us"):
+                r[k.replace("_us", "_speedup")] = r[k] / best
+        rows.append(r)
+        print(json.dumps(r), flush=True)
+    with open(out_path, "w") as f:
+        json.dump({"note": "single cold-L2 calls (CUDA events around one call, L2 flushed before it): launch latency included on both sides",
+                   "rows": rows}, f, indent=1)
+
+
 def run_prefill(out_path):
     import torch
     import quant_gemm
     rows = []
     for (wt, T, F, K, fused) in [(2, 512, 4096, 4096, False), (2, 2048, 4096, 4096, False), (7, 2048, 14336, 4096, True),
                                  (2, 4096, 28672, 8192, False), (8, 512, 4096, 4096, False), (2, 128, 4096, 4096, False),
-                                 (2, 64, 4096, 4096, False)]:
+                                 (2, 256, 4096, 4096, False), (3, 512, 4096, 4096, False), (6, 512, 4096, 4096, False)]:
         r = time_prefill(torch, quant_gemm, wt, T, F, K, fused_f32=fused)
         rows.append(r)
         print(json.dumps(r), flush=True)
@@ -158,8 +232,11 @@ if __name__ == "__main__":
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--flags", type=lambda v: int(v, 0), default=0x10)
     ap.add_argument("--prefill", action="store_true")
+    ap.add_argument("--vs-reference", action="store_true")
     a = ap.parse_args()
-    if a.prefill:
+    if a.vs_reference:
+        run_vs_reference(a.out)
+    elif a.prefill:
         run_prefill(a.out)
     else:
         run(a.out, a.quick, a.flags)
