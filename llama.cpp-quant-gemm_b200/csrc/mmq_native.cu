@@ -76,9 +76,10 @@ struct Params {
     int T, F, nb, nkc, Tpad;
     int64_t ldc_t, ldc_f;
     int tiles_m, tiles_n;
-    int ksplit;            // K is cut into ksplit equal ranges of whole raw stages; work unit = (tile, range)
-    float* partial;        // ksplit > 1: [tile][range][128 tokens][128 rows] partial sums
-    unsigned* tile_count;  //             arrivals per tile (returns to zero)
+    int nfull;             // tiles 0 .. nfull-1 are one work unit each; the others are cut along K:
+    int ksplit;            // ksplit equal ranges of whole raw stages, work unit = (tile, range)
+    float* partial;        // ksplit > 1: [tile - nfull][range][128 tokens][128 rows] partial sums
+    unsigned* tile_count;  //             arrivals per split tile (returns to zero)
     int stages, raw_stages;
     int dbg;
     PeerOut peer;
@@ -187,11 +188,17 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
     const int nkc = p.nkc;
     const int nbp = nkc * kBPS;
     const int ntiles = p.tiles_m * p.tiles_n;
-    // Work units: every tile once per K range.  With few tiles (T <= 256 at Llama widths) the K loop is split so that the
-    // whole chip works on the call; the ranges of a tile are added in FIXED order by whichever CTA finishes last.
-    const int ksplit = p.ksplit;
-    const int nkc_u = nkc / ksplit;             // operand stages per unit (even: whole raw stages)
-    const int units = ntiles * ksplit;          // unit u = (tile u % ntiles, range u / ntiles)
+    // Work units: tiles 0 .. nfull-1 whole, the others once per K range.  With few tiles (T <= 256 at Llama widths) every
+    // tile is split so that the whole chip works on the call; with many, the tiles of the ragged last wave are.  The ranges
+    // of a tile are added in FIXED order by whichever CTA finishes last.
+    const int ksplit = p.ksplit, nfull = p.nfull;
+    const int nsplit = ntiles - nfull;          // tiles that are cut along K
+    const int nkc_s = nkc / ksplit;             // operand stages per range (even: whole raw stages)
+    const int units = nfull + nsplit * ksplit;  // unit u >= nfull = (tile nfull + v % nsplit, range v / nsplit), v = u - nfull
+    auto unit_of = [&](int u, int& tile, int& ks, int& kc0, int& nk) {
+        if (u < nfull) { tile = u; ks = 0; kc0 = 0; nk = nkc; }
+        else { const int v = u - nfull; ks = v / nsplit; tile = nfull + (v - ks * nsplit); kc0 = ks * nkc_s; nk = nkc_s; }
+    };
 
     if (threadIdx.x == kWarpProd * 32) {
         for (int s = 0; s < kMaxStages; s++) {
@@ -220,9 +227,10 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
             uint32_t ph = 0;
             PROF_DECL;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                const int tile = u % ntiles, kc0 = (u / ntiles) * nkc_u;
+                int tile, ks, kc0, nk;
+                unit_of(u, tile, ks, kc0, nk);
                 const int mt = tile % p.tiles_m;
-                for (int kc = kc0; kc < kc0 + nkc_u; kc++) {
+                for (int kc = kc0; kc < kc0 + nk; kc++) {
                     PROF_WAIT(pf_wait, ptx::mbar_wait_backoff_guarded(&empty[s], ph ^ 1));
                     uint8_t* st = stages + s * kStageBytes;
                     ptx::mbar_arrive_expect_tx(&full[s], kBM * kKC + kBPS * kBM * 8);
@@ -244,7 +252,8 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
         uint32_t ph = 0, tph = 0;
         PROF_DECL;
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
-            for (int kc = 0; kc < nkc_u; kc++) {
+            const int nk = u < nfull ? nkc : nkc_s;
+            for (int kc = 0; kc < nk; kc++) {
                 PROF_WAIT(pf_wait, ptx::mbar_wait_guarded(&full[s], ph));
                 t5::fence_after();
                 const uint64_t adesc = t5::smem_desc(ptx::smem_u32(stages + s * kStageBytes + kStageA));
@@ -275,18 +284,19 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
         const int u = threadIdx.x - kWarpUnpack * 32;   // this thread owns weight rows u, u + 64 of the tile
         constexpr int kRow = raw_row_bytes<WT>();
         constexpr int kHalf = kBPS * Fmt<WT>::bytes;
-        const int nrs = nkc_u >> 1;                       // raw stages per unit
-        const int my_units = (units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-        const int total = my_units * nrs;                 // raw stages of this CTA, units back to back
+        int total = 0;                                    // raw stages (two operand stages each) of this CTA, units back to back
+        for (int q = blockIdx.x; q < units; q += gridDim.x) total += (q < nfull ? nkc : nkc_s) >> 1;
         // issue side: (unit, rs) of the next raw stage to request, and the slot it goes to
         int iunit = blockIdx.x, irs = 0, islot = 0, issued = 0;
+        int inrs = (iunit < nfull ? nkc : nkc_s) >> 1;    // raw stages of the unit being requested
         auto issue = [&]() {   // one 2-D tensor load: the next 8 raw blocks of the tile's 128 rows (rows >= F arrive as zeros)
             if (u == 0) {
-                const int itile = iunit % ntiles, rs0 = (iunit / ntiles) * nrs;
+                int itile, iks, ikc0, ink;
+                unit_of(iunit, itile, iks, ikc0, ink);
                 ptx::mbar_arrive_expect_tx(&rawfull[islot], (uint32_t)raw_stage_bytes<WT>());
-                tma_load_2d(raw_ring + islot * raw_stage_bytes<WT>(), &wmap, (rs0 + irs) * (kRow / 2), (itile / p.tiles_m) * kBN, &rawfull[islot]);
+                tma_load_2d(raw_ring + islot * raw_stage_bytes<WT>(), &wmap, ((ikc0 >> 1) + irs) * (kRow / 2), (itile / p.tiles_m) * kBN, &rawfull[islot]);
             }
-            if (++irs == nrs) { irs = 0; iunit += gridDim.x; }
+            if (++irs == inrs) { irs = 0; iunit += gridDim.x; inrs = (iunit < nfull ? nkc : nkc_s) >> 1; }
             if (++islot == nraw) islot = 0;
             issued++;
         };
@@ -331,13 +341,14 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
         uint32_t ph = 0, tph = 0;
         PROF_DECL;
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
-            const int tile = u % ntiles, ks = u / ntiles, kc0 = ks * nkc_u;
+            int tile, ks, kc0, nk;
+            unit_of(u, tile, ks, kc0, nk);
             const int mt = tile % p.tiles_m, nt = tile / p.tiles_m;
             uint64_t acc[kEpiCols / 2];  // fp32 accumulators as packed pairs (columns 2i, 2i+1)
 #pragma unroll
             for (int i = 0; i < kEpiCols / 2; i++) acc[i] = 0ull;
 #pragma unroll 1
-            for (int kc = kc0; kc < kc0 + nkc_u; kc++) {
+            for (int kc = kc0; kc < kc0 + nk; kc++) {
                 PROF_WAIT(pf_wait, ptx::mbar_wait_guarded(&full[s], ph));  // scale slabs of this stage are visible
                 const uint8_t* st = stages + s * kStageBytes;
 #pragma unroll 1
@@ -387,10 +398,10 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
                 if (++s == nstages) { s = 0; ph ^= 1; }
             }
             if constexpr (!kDump) {
-                if (ksplit > 1) {
+                if (u >= nfull) {
                     // this unit's partial tile -> scratch; the CTA that completes the tile adds the ranges in order
                     // 0 .. ksplit-1 (a fixed association, whatever the arrival order) and stores C
-                    float* part = p.partial + ((size_t)tile * ksplit + ks) * (kBM * kBN) + (size_t)row * kBN + cgrp * kEpiCols;
+                    float* part = p.partial + ((size_t)(tile - nfull) * ksplit + ks) * (kBM * kBN) + (size_t)row * kBN + cgrp * kEpiCols;
 #pragma unroll
                     for (int i = 0; i < kEpiCols / 4; i++) {
                         float4 v;
@@ -401,9 +412,9 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
                     __threadfence();
                     ptx::bar_sync(3, kEpiWarps * 32);
                     if (threadIdx.x == 0) {
-                        const unsigned prev = atomicAdd(p.tile_count + tile, 1u);
+                        const unsigned prev = atomicAdd(p.tile_count + (tile - nfull), 1u);
                         const int last = (prev == (unsigned)ksplit - 1u);
-                        if (last) p.tile_count[tile] = 0u;       // ready for the next call
+                        if (last) p.tile_count[tile - nfull] = 0u;       // ready for the next call
                         *split_flag = last;
                     }
                     ptx::bar_sync(3, kEpiWarps * 32);
@@ -411,7 +422,7 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
                     ptx::bar_sync(3, kEpiWarps * 32);            // the flag may be rewritten by the next unit
                     if (!last) continue;
                     __threadfence();
-                    const float* p0 = p.partial + (size_t)tile * ksplit * (kBM * kBN) + (size_t)row * kBN + cgrp * kEpiCols;
+                    const float* p0 = p.partial + (size_t)(tile - nfull) * ksplit * (kBM * kBN) + (size_t)row * kBN + cgrp * kEpiCols;
 #pragma unroll
                     for (int i = 0; i < kEpiCols / 4; i++) {
                         float4 sum = __ldcg(reinterpret_cast<const float4*>(p0) + i);
@@ -544,7 +555,7 @@ static cudaError_t launch_t(Params p, const void* wgt, bool refseq, int num_sms,
     if (cudaError_t e = smem_optin(fn, smem)) return e;
     const int ntiles = p.tiles_m * p.tiles_n;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(min(ntiles * p.ksplit, num_sms));
+    cfg.gridDim = dim3(min(p.nfull + (ntiles - p.nfull) * p.ksplit, num_sms));
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -568,26 +579,33 @@ bool mmq_native_supported(int wtype, const void* wgt, int T, int F, int K) {
     return reinterpret_cast<uintptr_t>(wgt) % 16 == 0 && nat::encode_tiled_fn() != nullptr;   // nullptr counts as aligned
 }
 
-// Split-K factor for a call: 1 when the tiles alone fill the chip (or the caller wants the reference's summation order);
-// otherwise the largest number of equal K ranges (whole raw stages each, at least four operand stages) that still fits
-// ONE wave of work units.  Measured on 4096-wide weights, K = 4096: T = 128 (32 tiles) 62 -> 40 us with 4 ranges,
-// T = 256 (64 tiles) 64.5 -> 48 us with 2; splitting into more than one wave was slower than not splitting (T = 384:
-// 85 vs 64.5 us), every unit paying its own pipeline fill and reduction.
-int mmq_native_ksplit(int T, int F, int K, uint32_t flags, int num_sms) {
-    if ((flags & QGEMM_FOLD_REFSEQ) || QGEMM_ENV("QGEMM_MMQ_NO_SPLITK")) return 1;
+// Split-K plan of a call.  Unsplit when the caller wants the reference's summation order, or when nothing is gained.
+//  * few tiles (at most one wave): every tile is cut into the largest number of equal K ranges (whole raw stages each, at
+//    least four operand stages) that still fits ONE wave of work units.  Measured on 4096-wide weights, K = 4096: T = 128
+//    (32 tiles) 62 -> 40 us with 4 ranges, T = 256 (64 tiles) 64.5 -> 48 us with 2; splitting into more than one wave was
+//    slower than not splitting (T = 384: 85 vs 64.5 us), every unit paying its own pipeline fill and reduction.
+//  * many tiles: the whole waves run unsplit and only the tiles of the ragged last wave are cut, so that it costs 1/s of a
+//    tile time instead of a whole one (896 tiles on 148 SMs: 6 + 1/8 instead of 7 tile times).
+struct NatSplit { int nfull, ksplit, nsplit; };
+static NatSplit mmq_native_plan(int T, int F, int K, uint32_t flags, int num_sms) {
     const int tiles = ((T + nat::kBM - 1) / nat::kBM) * ((F + nat::kBN - 1) / nat::kBN), nkc = K / nat::kKC;
+    NatSplit pl{tiles, 1, 0};
+    if ((flags & QGEMM_FOLD_REFSEQ) || QGEMM_ENV("QGEMM_MMQ_NO_SPLITK") || num_sms < 1) return pl;
+    const int rest = tiles <= num_sms ? tiles : tiles % num_sms;
+    if (rest == 0 || (tiles > num_sms && QGEMM_ENV("QGEMM_MMQ_NO_TAILSPLIT"))) return pl;
     int best = 1;
     for (int s : {2, 3, 4, 6, 8}) {
-        if (nkc % (2 * s) != 0 || nkc / s < 4 || tiles * s > num_sms) continue;
+        if (nkc % (2 * s) != 0 || nkc / s < 4 || rest * s > num_sms) continue;
         best = s;
     }
-    return best;
+    if (best > 1) pl = NatSplit{tiles - rest, best, rest};
+    return pl;
 }
+int mmq_native_ksplit(int T, int F, int K, uint32_t flags, int num_sms) { return mmq_native_plan(T, F, K, flags, num_sms).ksplit; }
 size_t mmq_native_split_bytes(int T, int F, int K, uint32_t flags, int num_sms) {
-    const int s = mmq_native_ksplit(T, F, K, flags, num_sms);
-    if (s == 1) return 0;
-    const size_t tiles = (size_t)((T + nat::kBM - 1) / nat::kBM) * ((F + nat::kBN - 1) / nat::kBN);
-    return tiles * s * nat::kBM * nat::kBN * sizeof(float) + (tiles * sizeof(unsigned) + 255) / 256 * 256;
+    const NatSplit pl = mmq_native_plan(T, F, K, flags, num_sms);
+    if (pl.ksplit == 1) return 0;
+    return (size_t)pl.nsplit * pl.ksplit * nat::kBM * nat::kBN * sizeof(float) + ((size_t)pl.nsplit * sizeof(unsigned) + 255) / 256 * 256;
 }
 
 // Where the arrival counters of a split-K call live inside its scratch (nullptr / 0: the call runs unsplit).  They must be
@@ -596,13 +614,13 @@ size_t mmq_native_split_bytes(int T, int F, int K, uint32_t flags, int num_sms) 
 unsigned* mmq_native_split_counters(int T, int F, int K, uint32_t flags, int num_sms, void* split_ws, size_t split_ws_bytes, bool dump,
                                     const PeerOut* peer, int* count) {
     *count = 0;
-    if (dump || (peer && peer->world > 1)) return nullptr;
-    const int ks = mmq_native_ksplit(T, F, K, flags, num_sms);
-    if (ks == 1 || !split_ws || split_ws_bytes < mmq_native_split_bytes(T, F, K, flags, num_sms) || reinterpret_cast<uintptr_t>(split_ws) % 16 != 0)
+    if (dump) return nullptr;
+    (void)peer;
+    const NatSplit pl = mmq_native_plan(T, F, K, flags, num_sms);
+    if (pl.ksplit == 1 || !split_ws || split_ws_bytes < mmq_native_split_bytes(T, F, K, flags, num_sms) || reinterpret_cast<uintptr_t>(split_ws) % 16 != 0)
         return nullptr;
-    const size_t tiles = (size_t)((T + nat::kBM - 1) / nat::kBM) * ((F + nat::kBN - 1) / nat::kBN);
-    *count = (int)tiles;
-    return (unsigned*)((char*)split_ws + tiles * ks * nat::kBM * nat::kBN * sizeof(float));
+    *count = pl.nsplit;
+    return (unsigned*)((char*)split_ws + (size_t)pl.nsplit * pl.ksplit * nat::kBM * nat::kBN * sizeof(float));
 }
 
 // a8 / as: the activation prepass of mmq.cu (Tpad tokens, nkc operand stages); split_ws: mmq_native_split_bytes() bytes whose
@@ -616,12 +634,14 @@ cudaError_t launch_mmq_native(int wtype, const uint8_t* a8, const float2* as, co
     p.ldc_t = ldc_t; p.ldc_f = ldc_f;
     p.tiles_m = Tpad / nat::kBM; p.tiles_n = (F + nat::kBN - 1) / nat::kBN;
     p.stages = 0; p.raw_stages = 0;
-    p.ksplit = 1; p.partial = nullptr; p.tile_count = nullptr;
+    p.nfull = p.tiles_m * p.tiles_n; p.ksplit = 1; p.partial = nullptr; p.tile_count = nullptr;
     {
         int ncount = 0;
         unsigned* counters = mmq_native_split_counters(T, F, K, flags, num_sms, split_ws, split_ws_bytes, sumi != nullptr, peer, &ncount);
         if (counters) {
-            p.ksplit = mmq_native_ksplit(T, F, K, flags, num_sms);
+            const NatSplit pl = mmq_native_plan(T, F, K, flags, num_sms);
+            p.nfull = pl.nfull;
+            p.ksplit = pl.ksplit;
             p.partial = (float*)split_ws;
             p.tile_count = counters;
         }

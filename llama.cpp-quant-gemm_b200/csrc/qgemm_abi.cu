@@ -550,12 +550,14 @@ int qgemm_gemm_peers(int wtype, const void* act_q8_1, const void* weight, const 
         }
         void* pool_ws = nullptr;
         if ((!ws || ws_bytes < need) && (flags & QGEMM_STREAM_ALLOC)) {
-            if (scratch_alloc(&pool_ws, align_up(need, 256), st) != cudaSuccess) {
+            // what the call needs, or what it can use (split-K scratch), whichever is larger
+            const size_t want = align_up(std::max(need, mmq_workspace_bytes(wtype, T, F, K)), 256);
+            if (scratch_alloc(&pool_ws, want, st) != cudaSuccess) {
                 (void)cudaGetLastError();
                 return QGEMM_E_WORKSPACE;
             }
             ws = pool_ws;
-            ws_bytes = align_up(need, 256);
+            ws_bytes = want;
         }
         if (!ws || ws_bytes < need) return QGEMM_E_WORKSPACE;
         if (po.world > 1 && po.li > 0) {
