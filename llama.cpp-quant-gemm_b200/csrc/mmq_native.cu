@@ -20,6 +20,7 @@
 //
 // Needs K % 256 == 0 (a raw stage is 8 blocks so that every format's row chunk is a 16-byte multiple) and a 16-byte
 // aligned weight base; other shapes take mmq.cu's prepass kernel.
+#include <algorithm>
 #include <cstdlib>
 
 #include <cuda.h>   // CUtensorMap + enums only; the encoder is looked up through the runtime, libcuda is not linked
@@ -30,13 +31,21 @@
 #include <cstdio>
 #define PROF_DECL long long pf_wait = 0, pf_wait2 = 0, pf_t0 = clock64()
 #define PROF_WAIT(acc, stmt) do { const long long c0_ = clock64(); stmt; acc += clock64() - c0_; } while (0)
+#define PROF_STAMP(i) do { if (threadIdx.x == 0) pf_ts[i] = clock64(); } while (0)
 #else
 #define PROF_DECL
 #define PROF_WAIT(acc, stmt) stmt
+#define PROF_STAMP(i)
 #endif
 
 namespace qgemm {
 namespace nat {
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 constexpr int kBM = 128;            // tokens per tile = TMEM lanes
 constexpr int kBN = 128;            // weight rows per tile = TMEM columns per block buffer
@@ -76,10 +85,10 @@ struct Params {
     int T, F, nb, nkc, Tpad;
     int64_t ldc_t, ldc_f;
     int tiles_m, tiles_n;
-    int nfull;             // tiles 0 .. nfull-1 are one work unit each; the others are cut along K:
-    int ksplit;            // ksplit equal ranges of whole raw stages, work unit = (tile, range)
-    float* partial;        // ksplit > 1: [tile - nfull][range][128 tokens][128 rows] partial sums
-    unsigned* tile_count;  //             arrivals per split tile (returns to zero)
+    int nfull;             // tiles 0 .. nfull-1 are one work unit each, dealt round robin; each of the others is cut
+    int ksplit;            // along K into ksplit segments of whole raw stages, one segment per CTA
+    float* partial;        // ksplit > 1: [segment][cut tile][128 tokens][128 rows] partial sums
+    unsigned* tile_count;  //             [cut tile][2]: tickets taken, partial sums published (both return to zero)
     int stages, raw_stages;
     int dbg;
     PeerOut peer;
@@ -179,7 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
     uint64_t* tfull = rawfull + kMaxRaw;                      // [2]          MMA commit per TMEM half
     uint64_t* tempty = tfull + 2;                             // [2]          16 epilogue warps
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    volatile int* split_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+    volatile int* split_info = reinterpret_cast<volatile int*>(tmem_slot + 1);   // this CTA completes its cut tile
     uint8_t* stages = smem + kBarBytes;
     uint8_t* raw_ring = stages + nstages * kStageBytes;
     float* out_tile = reinterpret_cast<float*>(raw_ring + nraw * raw_stage_bytes<WT>());   // [kBN][kBM], only with p.tma_out
@@ -188,16 +197,27 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
     const int nkc = p.nkc;
     const int nbp = nkc * kBPS;
     const int ntiles = p.tiles_m * p.tiles_n;
-    // Work units: tiles 0 .. nfull-1 whole, the others once per K range.  With few tiles (T <= 256 at Llama widths) every
-    // tile is split so that the whole chip works on the call; with many, the tiles of the ragged last wave are.  The ranges
-    // of a tile are added in FIXED order by whichever CTA finishes last.
-    const int ksplit = p.ksplit, nfull = p.nfull;
-    const int nsplit = ntiles - nfull;          // tiles that are cut along K
-    const int nkc_s = nkc / ksplit;             // operand stages per range (even: whole raw stages)
-    const int units = nfull + nsplit * ksplit;  // unit u >= nfull = (tile nfull + v % nsplit, range v / nsplit), v = u - nfull
-    auto unit_of = [&](int u, int& tile, int& ks, int& kc0, int& nk) {
-        if (u < nfull) { tile = u; ks = 0; kc0 = 0; nk = nkc; }
-        else { const int v = u - nfull; ks = v / nsplit; tile = nfull + (v - ks * nsplit); kc0 = ks * nkc_s; nk = nkc_s; }
+    // Work units of this CTA: whole tiles blockIdx.x, blockIdx.x + grid, ... below nfull, then at most one segment of a cut
+    // tile.  With few tiles (T <= 256 at Llama widths) every tile is cut so that the whole chip works on the call; with many,
+    // the tiles of the ragged last wave are.  A cut tile's segments are added in K order by the CTA that arrives last, so
+    // the result does not depend on the arrival order.
+    const int nrs = nkc >> 1;                   // raw stages (two operand stages) per tile
+    const int nfull = p.nfull, ksplit = p.ksplit;
+    const int ncut = ntiles - nfull;            // cut tiles; segment q of cut tile t belongs to CTA q * ncut + t
+    struct Cursor { int full, cut; };
+    const Cursor cur0{(int)blockIdx.x, (int)blockIdx.x < ncut * ksplit ? 1 : 0};
+    // next unit: tile, first raw stage, raw stages, segment index (-1: a whole tile, stored directly)
+    auto next_unit = [&](Cursor& cu, int& tile, int& rs0, int& n, int& seg) -> bool {
+        if (cu.full < nfull) { tile = cu.full; rs0 = 0; n = nrs; seg = -1; cu.full += gridDim.x; return true; }
+        if (cu.cut) {
+            cu.cut = 0;
+            seg = blockIdx.x / ncut;
+            tile = nfull + (blockIdx.x - seg * ncut);
+            rs0 = seg * nrs / ksplit;
+            n = (seg + 1) * nrs / ksplit - rs0;
+            return true;
+        }
+        return false;
     };
 
     if (threadIdx.x == kWarpProd * 32) {
@@ -226,11 +246,11 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
             int s = 0;
             uint32_t ph = 0;
             PROF_DECL;
-            for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                int tile, ks, kc0, nk;
-                unit_of(u, tile, ks, kc0, nk);
+            Cursor cu = cur0;
+            int tile, rs0, n, seg;
+            while (next_unit(cu, tile, rs0, n, seg)) {
                 const int mt = tile % p.tiles_m;
-                for (int kc = kc0; kc < kc0 + nk; kc++) {
+                for (int kc = 2 * rs0; kc < 2 * (rs0 + n); kc++) {
                     PROF_WAIT(pf_wait, ptx::mbar_wait_backoff_guarded(&empty[s], ph ^ 1));
                     uint8_t* st = stages + s * kStageBytes;
                     ptx::mbar_arrive_expect_tx(&full[s], kBM * kKC + kBPS * kBM * 8);
@@ -251,9 +271,10 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
         int s = 0;
         uint32_t ph = 0, tph = 0;
         PROF_DECL;
-        for (int u = blockIdx.x; u < units; u += gridDim.x) {
-            const int nk = u < nfull ? nkc : nkc_s;
-            for (int kc = 0; kc < nk; kc++) {
+        Cursor cu = cur0;
+        int tile, rs0, n, seg;
+        while (next_unit(cu, tile, rs0, n, seg)) {
+            for (int kc = 0; kc < 2 * n; kc++) {
                 PROF_WAIT(pf_wait, ptx::mbar_wait_guarded(&full[s], ph));
                 t5::fence_after();
                 const uint64_t adesc = t5::smem_desc(ptx::smem_u32(stages + s * kStageBytes + kStageA));
@@ -284,19 +305,22 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
         const int u = threadIdx.x - kWarpUnpack * 32;   // this thread owns weight rows u, u + 64 of the tile
         constexpr int kRow = raw_row_bytes<WT>();
         constexpr int kHalf = kBPS * Fmt<WT>::bytes;
-        int total = 0;                                    // raw stages (two operand stages each) of this CTA, units back to back
-        for (int q = blockIdx.x; q < units; q += gridDim.x) total += (q < nfull ? nkc : nkc_s) >> 1;
-        // issue side: (unit, rs) of the next raw stage to request, and the slot it goes to
-        int iunit = blockIdx.x, irs = 0, islot = 0, issued = 0;
-        int inrs = (iunit < nfull ? nkc : nkc_s) >> 1;    // raw stages of the unit being requested
+        int total = 0;                                    // raw stages of this CTA, units back to back
+        {
+            Cursor cu = cur0;
+            int tile, rs0, n, seg;
+            while (next_unit(cu, tile, rs0, n, seg)) total += n;
+        }
+        // issue side: the unit being requested, the next raw stage inside it, and the ring slot it goes to
+        Cursor icu = cur0;
+        int itile = 0, irs0 = 0, inrs = 0, islotp = 0, irs = 0, islot = 0, issued = 0;
+        next_unit(icu, itile, irs0, inrs, islotp);
         auto issue = [&]() {   // one 2-D tensor load: the next 8 raw blocks of the tile's 128 rows (rows >= F arrive as zeros)
             if (u == 0) {
-                int itile, iks, ikc0, ink;
-                unit_of(iunit, itile, iks, ikc0, ink);
                 ptx::mbar_arrive_expect_tx(&rawfull[islot], (uint32_t)raw_stage_bytes<WT>());
-                tma_load_2d(raw_ring + islot * raw_stage_bytes<WT>(), &wmap, ((ikc0 >> 1) + irs) * (kRow / 2), (itile / p.tiles_m) * kBN, &rawfull[islot]);
+                tma_load_2d(raw_ring + islot * raw_stage_bytes<WT>(), &wmap, (irs0 + irs) * (kRow / 2), (itile / p.tiles_m) * kBN, &rawfull[islot]);
             }
-            if (++irs == inrs) { irs = 0; iunit += gridDim.x; inrs = (iunit < nfull ? nkc : nkc_s) >> 1; }
+            if (++irs == inrs) { irs = 0; next_unit(icu, itile, irs0, inrs, islotp); }
             if (++islot == nraw) islot = 0;
             issued++;
         };
@@ -340,15 +364,19 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
         int s = 0;
         uint32_t ph = 0, tph = 0;
         PROF_DECL;
-        for (int u = blockIdx.x; u < units; u += gridDim.x) {
-            int tile, ks, kc0, nk;
-            unit_of(u, tile, ks, kc0, nk);
+        Cursor cu = cur0;
+        int tile, rs0, n, seg;
+        while (next_unit(cu, tile, rs0, n, seg)) {
             const int mt = tile % p.tiles_m, nt = tile / p.tiles_m;
+#ifdef QGEMM_MMQ_PROFILE
+            long long pf_ts[6] = {0, 0, 0, 0, 0, 0};
+            PROF_STAMP(0);
+#endif
             uint64_t acc[kEpiCols / 2];  // fp32 accumulators as packed pairs (columns 2i, 2i+1)
 #pragma unroll
             for (int i = 0; i < kEpiCols / 2; i++) acc[i] = 0ull;
 #pragma unroll 1
-            for (int kc = kc0; kc < kc0 + nk; kc++) {
+            for (int kc = 2 * rs0; kc < 2 * (rs0 + n); kc++) {
                 PROF_WAIT(pf_wait, ptx::mbar_wait_guarded(&full[s], ph));  // scale slabs of this stage are visible
                 const uint8_t* st = stages + s * kStageBytes;
 #pragma unroll 1
@@ -398,43 +426,90 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
                 if (++s == nstages) { s = 0; ph ^= 1; }
             }
             if constexpr (!kDump) {
-                if (u >= nfull) {
-                    // this unit's partial tile -> scratch; the CTA that completes the tile adds the ranges in order
-                    // 0 .. ksplit-1 (a fixed association, whatever the arrival order) and stores C
-                    float* part = p.partial + ((size_t)(tile - nfull) * ksplit + ks) * (kBM * kBN) + (size_t)row * kBN + cgrp * kEpiCols;
-#pragma unroll
-                    for (int i = 0; i < kEpiCols / 4; i++) {
-                        float4 v;
-                        unpk(acc[2 * i], v.x, v.y);
-                        unpk(acc[2 * i + 1], v.z, v.w);
-                        __stcg(reinterpret_cast<float4*>(part) + i, v);
-                    }
-                    __threadfence();
+                PROF_STAMP(1);
+                if (seg >= 0) {
+                    // A cut tile.  Every segment takes a ticket; all but the last to arrive put their partial sums into
+                    // scratch and publish them; the last one waits for those, adds the segments in K order (its own from
+                    // registers) and stores C.
+                    const int ct = tile - nfull;
+                    if (threadIdx.x == 0) split_info[0] = atomicAdd(p.tile_count + 2 * ct, 1u) == (unsigned)(ksplit - 1);
                     ptx::bar_sync(3, kEpiWarps * 32);
-                    if (threadIdx.x == 0) {
-                        const unsigned prev = atomicAdd(p.tile_count + (tile - nfull), 1u);
-                        const int last = (prev == (unsigned)ksplit - 1u);
-                        if (last) p.tile_count[tile - nfull] = 0u;       // ready for the next call
-                        *split_flag = last;
-                    }
-                    ptx::bar_sync(3, kEpiWarps * 32);
-                    const bool last = *split_flag != 0;
-                    ptx::bar_sync(3, kEpiWarps * 32);            // the flag may be rewritten by the next unit
-                    if (!last) continue;
-                    __threadfence();
-                    const float* p0 = p.partial + (size_t)(tile - nfull) * ksplit * (kBM * kBN) + (size_t)row * kBN + cgrp * kEpiCols;
+                    const bool last = split_info[0] != 0;
+                    // scratch layout of a partial tile: float4 (columns 4j .. 4j+3 of token `row`) at [j][row], so that the
+                    // lanes of a warp (consecutive tokens) touch consecutive 16-byte words
+                    const size_t off = (size_t)(cgrp * (kEpiCols / 4)) * kBM + row;
+                    if (!last) {
+                        float4* part = reinterpret_cast<float4*>(p.partial + ((size_t)seg * ncut + ct) * (kBM * kBN)) + off;
 #pragma unroll
-                    for (int i = 0; i < kEpiCols / 4; i++) {
-                        float4 sum = __ldcg(reinterpret_cast<const float4*>(p0) + i);
-                        for (int q = 1; q < ksplit; q++) {
-                            const float4 v = __ldcg(reinterpret_cast<const float4*>(p0 + (size_t)q * (kBM * kBN)) + i);
-                            sum.x = __fadd_rn(sum.x, v.x); sum.y = __fadd_rn(sum.y, v.y);
-                            sum.z = __fadd_rn(sum.z, v.z); sum.w = __fadd_rn(sum.w, v.w);
+                        for (int i = 0; i < kEpiCols / 4; i++) {
+                            float4 v;
+                            unpk(acc[2 * i], v.x, v.y);
+                            unpk(acc[2 * i + 1], v.z, v.w);
+                            __stcg(part + i * kBM, v);
                         }
-                        acc[2 * i] = pk(sum.x, sum.y);
-                        acc[2 * i + 1] = pk(sum.z, sum.w);
+                        PROF_STAMP(2);
+                        ptx::bar_sync(3, kEpiWarps * 32);
+                        if (threadIdx.x == 0) {
+                            __threadfence();   // cumulative: covers the stores the barrier has ordered before this thread
+                            atomicAdd(p.tile_count + 2 * ct + 1, 1u);
+                        }
+                        PROF_STAMP(3);
+#ifdef QGEMM_MMQ_PROFILE
+                        if (threadIdx.x == 0 && (p.dbg & 64) && blockIdx.x % 37 == 0)
+                            printf("cta %d tile %d rs0 %d n %d: loop %lld ticket+write %lld sync+publish %lld (not last)\n", blockIdx.x, tile, rs0, n,
+                                   pf_ts[1] - pf_ts[0], pf_ts[2] - pf_ts[1], pf_ts[3] - pf_ts[2]);
+#endif
+                        continue;
+                    }
+                    PROF_STAMP(2);
+                    if (threadIdx.x == 0) {
+                        unsigned polls = 0;
+                        while (ld_acquire_gpu(p.tile_count + 2 * ct + 1) < (unsigned)(ksplit - 1)) {
+                            __nanosleep(64);
+                            if (++polls > (1u << 24)) asm volatile("trap;");
+                        }
+                        p.tile_count[2 * ct] = 0u;       // ready for the next call
+                        p.tile_count[2 * ct + 1] = 0u;
+                    }
+                    ptx::bar_sync(3, kEpiWarps * 32);
+                    PROF_STAMP(3);
+                    // own partial sums -> shared memory (the operand stages are idle: a segment is its CTA's last unit), so
+                    // that the sum can be formed in place, in K order, whichever segment this CTA holds
+                    float4* own = reinterpret_cast<float4*>(stages) + threadIdx.x;
+                    if (seg != 0) {
+#pragma unroll
+                        for (int i = 0; i < kEpiCols / 4; i++) {
+                            float4 v;
+                            unpk(acc[2 * i], v.x, v.y);
+                            unpk(acc[2 * i + 1], v.z, v.w);
+                            own[i * (kEpiWarps * 32)] = v;
+                        }
+                    }
+#pragma unroll 1
+                    for (int q = (seg == 0 ? 1 : 0); q < ksplit; q++) {
+                        const float4* ps = reinterpret_cast<const float4*>(p.partial + ((size_t)q * ncut + ct) * (kBM * kBN)) + off;
+                        float4 in[kEpiCols / 4];
+                        if (q == seg) {
+#pragma unroll
+                            for (int i = 0; i < kEpiCols / 4; i++) in[i] = own[i * (kEpiWarps * 32)];
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < kEpiCols / 4; i++) in[i] = __ldcg(ps + i * kBM);
+                        }
+#pragma unroll
+                        for (int i = 0; i < kEpiCols / 4; i++) {
+                            const float4 v = in[i];
+                            if (q == 0) {
+                                acc[2 * i] = pk(v.x, v.y);
+                                acc[2 * i + 1] = pk(v.z, v.w);
+                            } else {
+                                fadd2_acc(acc[2 * i], pk(v.x, v.y));
+                                fadd2_acc(acc[2 * i + 1], pk(v.z, v.w));
+                            }
+                        }
                     }
                 }
+                PROF_STAMP(4);
                 const int t = mt * kBM + row;
                 if (p.tma_out) {
                     // Fused all-gather, bulk variant (see mmq.cu): the tile is staged as [f][t] and carried to every rank's
@@ -485,6 +560,12 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
                         }
                     }
                 }
+#ifdef QGEMM_MMQ_PROFILE
+                PROF_STAMP(5);
+                if (threadIdx.x == 0 && (p.dbg & 64) && blockIdx.x % 37 == 0)
+                    printf("cta %d tile %d rs0 %d n %d: loop %lld write+fence %lld sync+count %lld reduce %lld store %lld\n", blockIdx.x, tile, rs0, n,
+                           pf_ts[1] - pf_ts[0], pf_ts[2] - pf_ts[1], pf_ts[3] - pf_ts[2], pf_ts[4] - pf_ts[3], pf_ts[5] - pf_ts[4]);
+#endif
             }
         }
 #ifdef QGEMM_MMQ_PROFILE
@@ -555,7 +636,7 @@ static cudaError_t launch_t(Params p, const void* wgt, bool refseq, int num_sms,
     if (cudaError_t e = smem_optin(fn, smem)) return e;
     const int ntiles = p.tiles_m * p.tiles_n;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(min(p.nfull + (ntiles - p.nfull) * p.ksplit, num_sms));
+    cfg.gridDim = dim3(max(min(p.nfull, num_sms), (ntiles - p.nfull) * p.ksplit));
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -580,32 +661,28 @@ bool mmq_native_supported(int wtype, const void* wgt, int T, int F, int K) {
 }
 
 // Split-K plan of a call.  Unsplit when the caller wants the reference's summation order, or when nothing is gained.
-//  * few tiles (at most one wave): every tile is cut into the largest number of equal K ranges (whole raw stages each, at
-//    least four operand stages) that still fits ONE wave of work units.  Measured on 4096-wide weights, K = 4096: T = 128
-//    (32 tiles) 62 -> 40 us with 4 ranges, T = 256 (64 tiles) 64.5 -> 48 us with 2; splitting into more than one wave was
-//    slower than not splitting (T = 384: 85 vs 64.5 us), every unit paying its own pipeline fill and reduction.
-//  * many tiles: the whole waves run unsplit and only the tiles of the ragged last wave are cut, so that it costs 1/s of a
-//    tile time instead of a whole one (896 tiles on 148 SMs: 6 + 1/8 instead of 7 tile times).
-struct NatSplit { int nfull, ksplit, nsplit; };
+// The whole waves of tiles (nfull, a multiple of the SM count) run as they are, round robin.  The tiles of the ragged last
+// wave -- all tiles when there is less than one wave -- are each cut along K into as many segments as there are SMs per
+// such tile (at least two raw stages = 16 blocks per segment, segment lengths differing by at most one raw stage), one
+// segment per CTA, so that the last wave costs 1/segments of a tile time instead of a whole one.  Measured (q4_0):
+// 128 x 4096 x 4096 (32 tiles) 62 -> 40 us, 256 x 4096 x 4096 64.5 -> 48 us; 896 tiles (config 5 on 8 GPUs, per rank)
+// 0.70 -> 0.64 ms.  Several segments per CTA (contiguous shares across tile boundaries) were measured and lose: every
+// extra partial tile costs its CTA ~8 us of stores, fences and reduction.
+struct NatSplit { int nfull, ncut, ksplit; };
 static NatSplit mmq_native_plan(int T, int F, int K, uint32_t flags, int num_sms) {
-    const int tiles = ((T + nat::kBM - 1) / nat::kBM) * ((F + nat::kBN - 1) / nat::kBN), nkc = K / nat::kKC;
-    NatSplit pl{tiles, 1, 0};
+    const int tiles = ((T + nat::kBM - 1) / nat::kBM) * ((F + nat::kBN - 1) / nat::kBN), nrs = K / (2 * nat::kKC);
+    NatSplit pl{tiles, 0, 1};
     if ((flags & QGEMM_FOLD_REFSEQ) || QGEMM_ENV("QGEMM_MMQ_NO_SPLITK") || num_sms < 1) return pl;
-    const int rest = tiles <= num_sms ? tiles : tiles % num_sms;
+    const int rest = tiles % num_sms;
     if (rest == 0 || (tiles > num_sms && QGEMM_ENV("QGEMM_MMQ_NO_TAILSPLIT"))) return pl;
-    int best = 1;
-    for (int s : {2, 3, 4, 6, 8}) {
-        if (nkc % (2 * s) != 0 || nkc / s < 4 || rest * s > num_sms) continue;
-        best = s;
-    }
-    if (best > 1) pl = NatSplit{tiles - rest, best, rest};
-    return pl;
+    const int k = std::min(num_sms / rest, nrs / 2);
+    if (k < 2) return pl;
+    return NatSplit{tiles - rest, rest, k};
 }
-int mmq_native_ksplit(int T, int F, int K, uint32_t flags, int num_sms) { return mmq_native_plan(T, F, K, flags, num_sms).ksplit; }
 size_t mmq_native_split_bytes(int T, int F, int K, uint32_t flags, int num_sms) {
     const NatSplit pl = mmq_native_plan(T, F, K, flags, num_sms);
     if (pl.ksplit == 1) return 0;
-    return (size_t)pl.nsplit * pl.ksplit * nat::kBM * nat::kBN * sizeof(float) + ((size_t)pl.nsplit * sizeof(unsigned) + 255) / 256 * 256;
+    return (size_t)pl.ncut * pl.ksplit * nat::kBM * nat::kBN * sizeof(float) + ((size_t)pl.ncut * 2 * sizeof(unsigned) + 255) / 256 * 256;
 }
 
 // Where the arrival counters of a split-K call live inside its scratch (nullptr / 0: the call runs unsplit).  They must be
@@ -619,8 +696,8 @@ unsigned* mmq_native_split_counters(int T, int F, int K, uint32_t flags, int num
     const NatSplit pl = mmq_native_plan(T, F, K, flags, num_sms);
     if (pl.ksplit == 1 || !split_ws || split_ws_bytes < mmq_native_split_bytes(T, F, K, flags, num_sms) || reinterpret_cast<uintptr_t>(split_ws) % 16 != 0)
         return nullptr;
-    *count = pl.nsplit;
-    return (unsigned*)((char*)split_ws + (size_t)pl.nsplit * pl.ksplit * nat::kBM * nat::kBN * sizeof(float));
+    *count = 2 * pl.ncut;
+    return (unsigned*)((char*)split_ws + (size_t)pl.ncut * pl.ksplit * nat::kBM * nat::kBN * sizeof(float));
 }
 
 // a8 / as: the activation prepass of mmq.cu (Tpad tokens, nkc operand stages); split_ws: mmq_native_split_bytes() bytes whose

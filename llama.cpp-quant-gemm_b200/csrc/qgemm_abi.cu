@@ -48,7 +48,19 @@ cudaError_t launch_mmq(int wtype, const void* act, const void* wgt, float* C, in
                        cudaStream_t, const PeerOut* peer = nullptr);
 
 constexpr int kMmaMinTokens = 2;   // dp4a GEMV for a single token, mma.sync skinny path from here (measured crossover)
-constexpr int kMmqMinTokens = 96;  // AUTO switches to the tcgen05 path here (below it the skinny passes are faster)
+constexpr int kMmqMinTokens = 96;  // AUTO always takes the tcgen05 path from here on (a call without scratch is refused)
+
+// Below kMmqMinTokens AUTO takes the tcgen05 path only when scratch is at hand, from the measured crossover against the
+// mma.sync passes (profiles/r02_small_batch_crossover.md; the tcgen05 call costs the same for any T <= 128): T = 64 at
+// 4096 x 4096 28.0 -> 25.5 us, T = 80 at 11008 x 4096 65 -> 56 us; rows of other lengths than 4096 / 8192 have no wide
+// mma.sync variant and cross over at T = 24 (4096 x 11008: T = 32 61 -> 46 us, T = 95 183 -> 46 us).
+bool mmq_native_supported(int wtype, const void* wgt, int T, int F, int K);
+static int mmq_min_tokens(int wtype, const void* wgt, int T, int F, int K) {
+    if (!mmq_native_supported(wtype, wgt, T, F, K)) return kMmqMinTokens;
+    if (K != 4096 && K != 8192) return 24;
+    const int tiles = (F + 127) / 128;
+    return (tiles > 74 && tiles <= 148) ? 72 : 64;   // one unsplit wave of tiles is the worst case for the tcgen05 path
+}
 
 static std::atomic<int64_t> g_launches{0};
 void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
@@ -188,7 +200,8 @@ static int run_gemm(int wtype, const void* act, const void* wgt, float* C, int T
     if (flags & QGEMM_SEQUENTIAL) path = QGEMM_PATH_GENERIC;
     // no scratch from the caller: borrow it from the stream's pool for the duration of this call
     void* pool_ws = nullptr;
-    if (!ws && (flags & QGEMM_STREAM_ALLOC) && (path == QGEMM_PATH_TCGEN05 || (path == QGEMM_PATH_AUTO && T >= kMmqMinTokens)) &&
+    const int tc_min = (flags & QGEMM_WEIGHTS_PREPACKED) ? kMmqMinTokens : mmq_min_tokens(wtype, wgt, T, F, K);
+    if (!ws && (flags & QGEMM_STREAM_ALLOC) && (path == QGEMM_PATH_TCGEN05 || (path == QGEMM_PATH_AUTO && T >= tc_min)) &&
         mmq_supported(wtype, act, wgt, T, F, K)) {
         // what the call needs, or what it can use (the split-K scratch of small-T calls), whichever is larger
         const size_t need = align_up(std::max(mmq_workspace_need(wtype, wgt, T, F, K, flags), mmq_workspace_bytes(wtype, T, F, K)), 256);
@@ -209,10 +222,11 @@ static int run_gemm(int wtype, const void* act, const void* wgt, float* C, int T
         path = QGEMM_PATH_TCGEN05;
     }
     if (path == QGEMM_PATH_AUTO) {
-        const bool tc_size = T >= kMmqMinTokens && mmq_supported(wtype, act, wgt, T, F, K);
+        const bool have_ws = ws && ws_bytes >= mmq_workspace_need(wtype, wgt, T, F, K, flags);
+        const bool tc_size = T >= (have_ws ? tc_min : kMmqMinTokens) && mmq_supported(wtype, act, wgt, T, F, K);
         // a prefill-sized call without scratch would fall to the weight-streaming passes at a fraction of the speed:
         // say so instead of doing it silently (QGEMM_PATH_MMA asks for that path explicitly, QGEMM_STREAM_ALLOC lends scratch)
-        if (tc_size && (!ws || ws_bytes < mmq_workspace_need(wtype, wgt, T, F, K, flags))) return QGEMM_E_WORKSPACE;
+        if (tc_size && !have_ws) return QGEMM_E_WORKSPACE;
         if (tc_size)
             path = QGEMM_PATH_TCGEN05;
         else if (T >= (K > 8192 ? kMmaMinTokens + 1 : kMmaMinTokens) && gemv_mma_supported(wtype, act, wgt, T, F, K))
@@ -315,7 +329,7 @@ size_t qgemm_workspace_bytes(int wtype, int T, int F, int K, uint32_t flags) {
     const size_t a_q = align_up((size_t)T * (K / kQK) * kQ81Bytes, 256);
     const uint32_t path = flags & QGEMM_PATH_MASK;
     const bool mmq = (path == QGEMM_PATH_TCGEN05 || (flags & QGEMM_WEIGHTS_PREPACKED) ||
-                      (path == QGEMM_PATH_AUTO && T >= kMmqMinTokens)) &&
+                      (path == QGEMM_PATH_AUTO && T >= mmq_min_tokens(wtype, nullptr, T, F, K))) &&
                      !(flags & QGEMM_SEQUENTIAL);
     return a_q + (mmq ? align_up(mmq_workspace_bytes(wtype, T, F, K), 256) : 0);
 }
@@ -404,7 +418,7 @@ int qgemm_gemm_f32act(int wtype, const float* act_f32, const void* weight, float
     cudaStream_t st = (cudaStream_t)stream;
     {   // tensor-core sizes: the quantizer writes the GEMM's operand tiles directly (two launches in all)
         const uint32_t gflags = flags & 0xffffu, path = gflags & QGEMM_PATH_MASK;
-        const bool tc = !(gflags & QGEMM_SEQUENTIAL) && (path == QGEMM_PATH_TCGEN05 || (path == QGEMM_PATH_AUTO && T >= kMmqMinTokens));
+        const bool tc = !(gflags & QGEMM_SEQUENTIAL) && (path == QGEMM_PATH_TCGEN05 || (path == QGEMM_PATH_AUTO && T >= mmq_min_tokens(wtype, weight, T, F, K)));
         if (tc && K > 0 && workspace_bytes > a_q) {
             const cudaError_t e = launch_mmq_f32act(wtype, act_f32, weight, C, T, F, K, ldc_t, ldc_f, gflags, (flags >> 16) & 0xffu,
                                                     (char*)workspace + a_q, workspace_bytes - a_q, dev.sms, st);
