@@ -85,10 +85,10 @@ struct Params {
     int T, F, nb, nkc, Tpad;
     int64_t ldc_t, ldc_f;
     int tiles_m, tiles_n;
-    int nfull;             // tiles 0 .. nfull-1 are one work unit each, dealt round robin; each of the others is cut
-    int ksplit;            // along K into ksplit segments of whole raw stages, one segment per CTA
-    float* partial;        // ksplit > 1: [segment][cut tile][128 tokens][128 rows] partial sums
-    unsigned* tile_count;  //             [cut tile][2]: tickets taken, partial sums published (both return to zero)
+    int nfull;             // tiles 0 .. nfull-1 are one work unit each, dealt round robin; the raw stages of the others
+    int sk_ctas;           // are shared by CTAs 0 .. sk_ctas-1 in equal contiguous ranges, cut at tile boundaries
+    float* partial;        // sk_ctas > 0: [2][cta][128 tokens][128 rows] partial sums of a CTA's first / second cut unit
+    unsigned* tile_count;  //              [cut tile][2]: tickets taken, partial sums published (both return to zero)
     int stages, raw_stages;
     int dbg;
     PeerOut peer;
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
     uint64_t* tfull = rawfull + kMaxRaw;                      // [2]          MMA commit per TMEM half
     uint64_t* tempty = tfull + 2;                             // [2]          16 epilogue warps
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    volatile int* split_info = reinterpret_cast<volatile int*>(tmem_slot + 1);   // this CTA completes its cut tile
+    volatile int* split_info = reinterpret_cast<volatile int*>(tmem_slot + 1);   // [3]: this CTA completes the cut tile; its first / last CTA
     uint8_t* stages = smem + kBarBytes;
     uint8_t* raw_ring = stages + nstages * kStageBytes;
     float* out_tile = reinterpret_cast<float*>(raw_ring + nraw * raw_stage_bytes<WT>());   // [kBN][kBM], only with p.tma_out
@@ -197,24 +197,27 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
     const int nkc = p.nkc;
     const int nbp = nkc * kBPS;
     const int ntiles = p.tiles_m * p.tiles_n;
-    // Work units of this CTA: whole tiles blockIdx.x, blockIdx.x + grid, ... below nfull, then at most one segment of a cut
-    // tile.  With few tiles (T <= 256 at Llama widths) every tile is cut so that the whole chip works on the call; with many,
-    // the tiles of the ragged last wave are.  A cut tile's segments are added in K order by the CTA that arrives last, so
-    // the result does not depend on the arrival order.
+    // Work units of this CTA: whole tiles blockIdx.x, blockIdx.x + grid, ... below nfull, then its share of the cut tiles:
+    // a contiguous range of their raw stages, i.e. one segment of a tile or (when the range crosses a tile boundary) the
+    // end of one tile and the start of the next.  With few tiles (T <= 256 at Llama widths) every tile is cut so that the
+    // whole chip works on the call; with many, the tiles of the ragged last wave are.  A cut tile's segments are added in
+    // K order by the CTA that arrives last, so the result does not depend on the arrival order.
     const int nrs = nkc >> 1;                   // raw stages (two operand stages) per tile
-    const int nfull = p.nfull, ksplit = p.ksplit;
-    const int ncut = ntiles - nfull;            // cut tiles; segment q of cut tile t belongs to CTA q * ncut + t
-    struct Cursor { int full, cut; };
-    const Cursor cur0{(int)blockIdx.x, (int)blockIdx.x < ncut * ksplit ? 1 : 0};
-    // next unit: tile, first raw stage, raw stages, segment index (-1: a whole tile, stored directly)
+    const int nfull = p.nfull;
+    const int sk_total = (ntiles - nfull) * nrs;
+    auto sk_begin = [&](int c) { return (int)((long long)c * sk_total / p.sk_ctas); };   // first raw stage of CTA c's share
+    const int sk_w0 = (int)blockIdx.x < p.sk_ctas ? sk_begin(blockIdx.x) : 0;
+    const int sk_w1 = (int)blockIdx.x < p.sk_ctas ? sk_begin(blockIdx.x + 1) : 0;
+    struct Cursor { int full, w; };
+    const Cursor cur0{(int)blockIdx.x, sk_w0};
+    // next unit: tile, first raw stage, raw stages, cut unit number (-1: a whole tile, stored directly; else 0 / 1)
     auto next_unit = [&](Cursor& cu, int& tile, int& rs0, int& n, int& seg) -> bool {
         if (cu.full < nfull) { tile = cu.full; rs0 = 0; n = nrs; seg = -1; cu.full += gridDim.x; return true; }
-        if (cu.cut) {
-            cu.cut = 0;
-            seg = blockIdx.x / ncut;
-            tile = nfull + (blockIdx.x - seg * ncut);
-            rs0 = seg * nrs / ksplit;
-            n = (seg + 1) * nrs / ksplit - rs0;
+        if (cu.w < sk_w1) {
+            const int t = cu.w / nrs;
+            seg = cu.w == sk_w0 ? 0 : 1;
+            tile = nfull + t; rs0 = cu.w - t * nrs; n = min(nrs - rs0, sk_w1 - cu.w);
+            cu.w += n;
             return true;
         }
         return false;
@@ -429,17 +432,16 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
                 PROF_STAMP(1);
                 if (seg >= 0) {
                     // A cut tile.  Every segment takes a ticket; all but the last to arrive put their partial sums into
-                    // scratch and publish them; the last one waits for those, adds the segments in K order (its own from
-                    // registers) and stores C.
-                    const int ct = tile - nfull;
-                    if (threadIdx.x == 0) split_info[0] = atomicAdd(p.tile_count + 2 * ct, 1u) == (unsigned)(ksplit - 1);
-                    ptx::bar_sync(3, kEpiWarps * 32);
-                    const bool last = split_info[0] != 0;
+                    // scratch and publish them; the last one waits for those, adds the segments in K order and stores C.
+                    // A CTA's final unit keeps its own sums on chip while it finds out whether it is last; a unit with
+                    // another one behind it (the end of a tile whose successor the CTA also works on) publishes first.
+                    const int ct = tile - nfull, x0 = ct * nrs;
+                    const bool final_unit = cu.w >= sk_w1;
                     // scratch layout of a partial tile: float4 (columns 4j .. 4j+3 of token `row`) at [j][row], so that the
                     // lanes of a warp (consecutive tokens) touch consecutive 16-byte words
                     const size_t off = (size_t)(cgrp * (kEpiCols / 4)) * kBM + row;
-                    if (!last) {
-                        float4* part = reinterpret_cast<float4*>(p.partial + ((size_t)seg * ncut + ct) * (kBM * kBN)) + off;
+                    float4* part = reinterpret_cast<float4*>(p.partial + ((size_t)seg * p.sk_ctas + blockIdx.x) * (kBM * kBN)) + off;
+                    auto publish = [&]() {
 #pragma unroll
                         for (int i = 0; i < kEpiCols / 4; i++) {
                             float4 v;
@@ -447,36 +449,54 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
                             unpk(acc[2 * i + 1], v.z, v.w);
                             __stcg(part + i * kBM, v);
                         }
-                        PROF_STAMP(2);
                         ptx::bar_sync(3, kEpiWarps * 32);
                         if (threadIdx.x == 0) {
                             __threadfence();   // cumulative: covers the stores the barrier has ordered before this thread
                             atomicAdd(p.tile_count + 2 * ct + 1, 1u);
                         }
+                    };
+                    if (!final_unit) publish();
+                    if (threadIdx.x == 0) {
+                        // CTAs c0 .. c1 hold the tile's raw stages [x0, x0 + nrs)
+                        int c0 = (int)((long long)x0 * p.sk_ctas / sk_total);
+                        while (c0 + 1 < p.sk_ctas && sk_begin(c0 + 1) <= x0) c0++;
+                        int c1 = (int)((long long)(x0 + nrs - 1) * p.sk_ctas / sk_total);
+                        while (c1 + 1 < p.sk_ctas && sk_begin(c1 + 1) <= x0 + nrs - 1) c1++;
+                        const bool last = atomicAdd(p.tile_count + 2 * ct, 1u) == (unsigned)(c1 - c0);
+                        if (last) {
+                            // everybody else has a ticket, so their sums are on their way
+                            const unsigned want = (unsigned)(c1 - c0) + (final_unit ? 0u : 1u);
+                            unsigned polls = 0;
+                            while (ld_acquire_gpu(p.tile_count + 2 * ct + 1) < want) {
+                                __nanosleep(64);
+                                if (++polls > (1u << 24)) asm volatile("trap;");
+                            }
+                            p.tile_count[2 * ct] = 0u;       // ready for the next call
+                            p.tile_count[2 * ct + 1] = 0u;
+                        }
+                        split_info[0] = last; split_info[1] = c0; split_info[2] = c1;
+                    }
+                    ptx::bar_sync(3, kEpiWarps * 32);
+                    const bool last = split_info[0] != 0;
+                    const int c0 = split_info[1], c1 = split_info[2];
+                    ptx::bar_sync(3, kEpiWarps * 32);            // the words may be rewritten by the next unit
+                    PROF_STAMP(2);
+                    if (!last) {
+                        if (final_unit) publish();
                         PROF_STAMP(3);
 #ifdef QGEMM_MMQ_PROFILE
                         if (threadIdx.x == 0 && (p.dbg & 64) && blockIdx.x % 37 == 0)
-                            printf("cta %d tile %d rs0 %d n %d: loop %lld ticket+write %lld sync+publish %lld (not last)\n", blockIdx.x, tile, rs0, n,
-                                   pf_ts[1] - pf_ts[0], pf_ts[2] - pf_ts[1], pf_ts[3] - pf_ts[2]);
+                            printf("cta %d tile %d rs0 %d n %d: loop %lld ticket %lld publish %lld (not last, final %d)\n", blockIdx.x, tile, rs0, n,
+                                   pf_ts[1] - pf_ts[0], pf_ts[2] - pf_ts[1], pf_ts[3] - pf_ts[2], (int)final_unit);
 #endif
                         continue;
                     }
-                    PROF_STAMP(2);
-                    if (threadIdx.x == 0) {
-                        unsigned polls = 0;
-                        while (ld_acquire_gpu(p.tile_count + 2 * ct + 1) < (unsigned)(ksplit - 1)) {
-                            __nanosleep(64);
-                            if (++polls > (1u << 24)) asm volatile("trap;");
-                        }
-                        p.tile_count[2 * ct] = 0u;       // ready for the next call
-                        p.tile_count[2 * ct + 1] = 0u;
-                    }
-                    ptx::bar_sync(3, kEpiWarps * 32);
                     PROF_STAMP(3);
-                    // own partial sums -> shared memory (the operand stages are idle: a segment is its CTA's last unit), so
-                    // that the sum can be formed in place, in K order, whichever segment this CTA holds
+                    // own sums of a final unit -> shared memory (the operand stages are idle by now), so that the sum can be
+                    // formed in place, in K order, wherever this CTA's segment lies
                     float4* own = reinterpret_cast<float4*>(stages) + threadIdx.x;
-                    if (seg != 0) {
+                    const int me = final_unit ? (int)blockIdx.x : -1;
+                    if (me >= 0 && me != c0) {
 #pragma unroll
                         for (int i = 0; i < kEpiCols / 4; i++) {
                             float4 v;
@@ -486,10 +506,11 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
                         }
                     }
 #pragma unroll 1
-                    for (int q = (seg == 0 ? 1 : 0); q < ksplit; q++) {
-                        const float4* ps = reinterpret_cast<const float4*>(p.partial + ((size_t)q * ncut + ct) * (kBM * kBN)) + off;
+                    for (int c = (me == c0 ? c0 + 1 : c0); c <= c1; c++) {
+                        // CTA c's segment of this tile is its first cut unit unless its share began in the tile before
+                        const float4* ps = reinterpret_cast<const float4*>(p.partial + ((size_t)(sk_begin(c) >= x0 ? 0 : 1) * p.sk_ctas + c) * (kBM * kBN)) + off;
                         float4 in[kEpiCols / 4];
-                        if (q == seg) {
+                        if (c == me) {
 #pragma unroll
                             for (int i = 0; i < kEpiCols / 4; i++) in[i] = own[i * (kEpiWarps * 32)];
                         } else {
@@ -499,7 +520,7 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
 #pragma unroll
                         for (int i = 0; i < kEpiCols / 4; i++) {
                             const float4 v = in[i];
-                            if (q == 0) {
+                            if (c == c0) {
                                 acc[2 * i] = pk(v.x, v.y);
                                 acc[2 * i + 1] = pk(v.z, v.w);
                             } else {
@@ -636,7 +657,7 @@ static cudaError_t launch_t(Params p, const void* wgt, bool refseq, int num_sms,
     if (cudaError_t e = smem_optin(fn, smem)) return e;
     const int ntiles = p.tiles_m * p.tiles_n;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(max(min(p.nfull, num_sms), (ntiles - p.nfull) * p.ksplit));
+    cfg.gridDim = dim3(max(min(p.nfull, num_sms), p.sk_ctas));
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -662,27 +683,35 @@ bool mmq_native_supported(int wtype, const void* wgt, int T, int F, int K) {
 
 // Split-K plan of a call.  Unsplit when the caller wants the reference's summation order, or when nothing is gained.
 // The whole waves of tiles (nfull, a multiple of the SM count) run as they are, round robin.  The tiles of the ragged last
-// wave -- all tiles when there is less than one wave -- are each cut along K into as many segments as there are SMs per
-// such tile (at least two raw stages = 16 blocks per segment, segment lengths differing by at most one raw stage), one
-// segment per CTA, so that the last wave costs 1/segments of a tile time instead of a whole one.  Measured (q4_0):
-// 128 x 4096 x 4096 (32 tiles) 62 -> 40 us, 256 x 4096 x 4096 64.5 -> 48 us; 896 tiles (config 5 on 8 GPUs, per rank)
-// 0.70 -> 0.64 ms.  Several segments per CTA (contiguous shares across tile boundaries) were measured and lose: every
-// extra partial tile costs its CTA ~8 us of stores, fences and reduction.
-struct NatSplit { int nfull, ncut, ksplit; };
+// wave -- all tiles when there is less than one wave -- are cut along K:
+//  * at most half a wave of them: each tile into as many segments as there are SMs per such tile (at least two raw stages
+//    = 16 blocks per segment, lengths differing by at most one raw stage), one segment per CTA, so that the wave costs
+//    1/segments of a tile time.  Measured (q4_0): 128 x 4096 x 4096 (32 tiles) 62 -> 32 us, 256 x 4096 x 4096 64.5 -> 42 us;
+//    896 tiles (config 5 on 8 GPUs, per rank) 0.70 -> 0.63 ms.
+//  * more than that: all SMs share the raw stages of those tiles in equal contiguous ranges; a range that crosses a tile
+//    boundary makes two units (the end of one tile, the start of the next), each tile is summed from two or three
+//    segments, and the wave costs tiles/SMs of a tile time.  Every extra partial tile costs its CTA a few thousand cycles
+//    (profiles/r02_split_k.md), so this needs a tile long enough to gain more than that.
+struct NatSplit { int nfull, ncut, sk_ctas, slots; };
 static NatSplit mmq_native_plan(int T, int F, int K, uint32_t flags, int num_sms) {
     const int tiles = ((T + nat::kBM - 1) / nat::kBM) * ((F + nat::kBN - 1) / nat::kBN), nrs = K / (2 * nat::kKC);
-    NatSplit pl{tiles, 0, 1};
+    NatSplit pl{tiles, 0, 0, 0};
     if ((flags & QGEMM_FOLD_REFSEQ) || QGEMM_ENV("QGEMM_MMQ_NO_SPLITK") || num_sms < 1) return pl;
     const int rest = tiles % num_sms;
     if (rest == 0 || (tiles > num_sms && QGEMM_ENV("QGEMM_MMQ_NO_TAILSPLIT"))) return pl;
     const int k = std::min(num_sms / rest, nrs / 2);
-    if (k < 2) return pl;
-    return NatSplit{tiles - rest, rest, k};
+    if (k >= 2) return NatSplit{tiles - rest, rest, rest * k, 1};
+    // shared ranges: worth it when a CTA saves more raw stages than its second partial tile and the reduction cost (at
+    // 2.2 raw stages saved, 512 x 4096 x 4096, it is a draw: 64.5 us either way)
+    const int min_gain = QGEMM_ENV("QGEMM_MMQ_SK_MINGAIN") ? atoi(QGEMM_ENV("QGEMM_MMQ_SK_MINGAIN")) : 3;
+    if (2 * rest > num_sms && (long long)nrs * (num_sms - rest) >= (long long)min_gain * num_sms)
+        return NatSplit{tiles - rest, rest, num_sms, 2};
+    return pl;
 }
 size_t mmq_native_split_bytes(int T, int F, int K, uint32_t flags, int num_sms) {
     const NatSplit pl = mmq_native_plan(T, F, K, flags, num_sms);
-    if (pl.ksplit == 1) return 0;
-    return (size_t)pl.ncut * pl.ksplit * nat::kBM * nat::kBN * sizeof(float) + ((size_t)pl.ncut * 2 * sizeof(unsigned) + 255) / 256 * 256;
+    if (pl.sk_ctas == 0) return 0;
+    return (size_t)pl.sk_ctas * pl.slots * nat::kBM * nat::kBN * sizeof(float) + ((size_t)pl.ncut * 2 * sizeof(unsigned) + 255) / 256 * 256;
 }
 
 // Where the arrival counters of a split-K call live inside its scratch (nullptr / 0: the call runs unsplit).  They must be
@@ -694,10 +723,10 @@ unsigned* mmq_native_split_counters(int T, int F, int K, uint32_t flags, int num
     if (dump) return nullptr;
     (void)peer;
     const NatSplit pl = mmq_native_plan(T, F, K, flags, num_sms);
-    if (pl.ksplit == 1 || !split_ws || split_ws_bytes < mmq_native_split_bytes(T, F, K, flags, num_sms) || reinterpret_cast<uintptr_t>(split_ws) % 16 != 0)
+    if (pl.sk_ctas == 0 || !split_ws || split_ws_bytes < mmq_native_split_bytes(T, F, K, flags, num_sms) || reinterpret_cast<uintptr_t>(split_ws) % 16 != 0)
         return nullptr;
     *count = 2 * pl.ncut;
-    return (unsigned*)((char*)split_ws + (size_t)pl.ncut * pl.ksplit * nat::kBM * nat::kBN * sizeof(float));
+    return (unsigned*)((char*)split_ws + (size_t)pl.sk_ctas * pl.slots * nat::kBM * nat::kBN * sizeof(float));
 }
 
 // a8 / as: the activation prepass of mmq.cu (Tpad tokens, nkc operand stages); split_ws: mmq_native_split_bytes() bytes whose
@@ -711,14 +740,14 @@ cudaError_t launch_mmq_native(int wtype, const uint8_t* a8, const float2* as, co
     p.ldc_t = ldc_t; p.ldc_f = ldc_f;
     p.tiles_m = Tpad / nat::kBM; p.tiles_n = (F + nat::kBN - 1) / nat::kBN;
     p.stages = 0; p.raw_stages = 0;
-    p.nfull = p.tiles_m * p.tiles_n; p.ksplit = 1; p.partial = nullptr; p.tile_count = nullptr;
+    p.nfull = p.tiles_m * p.tiles_n; p.sk_ctas = 0; p.partial = nullptr; p.tile_count = nullptr;
     {
         int ncount = 0;
         unsigned* counters = mmq_native_split_counters(T, F, K, flags, num_sms, split_ws, split_ws_bytes, sumi != nullptr, peer, &ncount);
         if (counters) {
             const NatSplit pl = mmq_native_plan(T, F, K, flags, num_sms);
             p.nfull = pl.nfull;
-            p.ksplit = pl.ksplit;
+            p.sk_ctas = pl.sk_ctas;
             p.partial = (float*)split_ws;
             p.tile_count = counters;
         }

@@ -52,14 +52,13 @@ constexpr int kMmqMinTokens = 96;  // AUTO always takes the tcgen05 path from he
 
 // Below kMmqMinTokens AUTO takes the tcgen05 path only when scratch is at hand, from the measured crossover against the
 // mma.sync passes (profiles/r02_small_batch_crossover.md; the tcgen05 call costs the same for any T <= 128): T = 64 at
-// 4096 x 4096 28.0 -> 25.5 us, T = 80 at 11008 x 4096 65 -> 56 us; rows of other lengths than 4096 / 8192 have no wide
+// 4096 x 4096 28.0 -> 25.5 us, T = 64 at 11008 x 4096 49.6 -> 47 us; rows of other lengths than 4096 / 8192 have no wide
 // mma.sync variant and cross over at T = 24 (4096 x 11008: T = 32 61 -> 46 us, T = 95 183 -> 46 us).
 bool mmq_native_supported(int wtype, const void* wgt, int T, int F, int K);
 static int mmq_min_tokens(int wtype, const void* wgt, int T, int F, int K) {
     if (!mmq_native_supported(wtype, wgt, T, F, K)) return kMmqMinTokens;
-    if (K != 4096 && K != 8192) return 24;
-    const int tiles = (F + 127) / 128;
-    return (tiles > 74 && tiles <= 148) ? 72 : 64;   // one unsplit wave of tiles is the worst case for the tcgen05 path
+    (void)F;
+    return (K == 4096 || K == 8192) ? 64 : 24;
 }
 
 static std::atomic<int64_t> g_launches{0};

@@ -425,7 +425,9 @@ def test_mmq_full_size_prefill_other_formats(qg, O, wt):
                                       (qo.Q8_0, 256, 9600, 2048),    # 150 tiles: one whole wave + 2 tiles cut in 4
                                       (qo.Q4_1, 96, 2500, 4096),     # 20 tiles x 7 segments, ragged
                                       (qo.Q5_1, 300, 19072, 1024),   # 447 tiles: three waves + 3 tiles cut in 2
-                                      (qo.Q4_0, 640, 4096, 11008)])  # 160 tiles: one wave + 12 tiles cut in 12
+                                      (qo.Q4_0, 640, 4096, 11008),   # 160 tiles: one wave + 12 tiles cut in 12
+                                      (qo.Q5_0, 384, 4096, 4096),    # 96 tiles: shared ranges, two units per CTA
+                                      (qo.Q4_1, 128, 11008, 2048)])  # 86 tiles of 8 raw stages: shared ranges
 def test_mmq_split_k_plans(qg, O, wt, T, F, K):
     """K-split of the last (or only) wave of tiles: the segments of a tile are added in K order by whichever CTA
     arrives last, so the result is deterministic, within the tolerance of the unsplit evaluation (reference
