@@ -554,12 +554,12 @@ def main():
     extra = {}
     if rank == 0 and world == 1:
         import bench_detail
-        r = bench_detail.time_prefill(torch, quant_gemm, WTYPE, 512, 4096, 4096, reps=5)
+        r = bench_detail.time_prefill(torch, quant_gemm, WTYPE, 512, 4096, 4096, reps=20)
         extra = {"prefill_q4_0_M512_N4096_K4096": {"us": r["us"], "tops": r["tops"], "path": r["path"],
                                                    "frac_of_nominal_int8_4500_tops": r["tops"] / 4500.0,
                                                    "note": "BASELINE configs[2]; whole qgemm_gemm call incl. the activation prepass "
                                                            "(weights are unpacked inside the kernel), L2 flushed between reps"}}
-        r = bench_detail.time_prefill(torch, quant_gemm, 7, 2048, 14336, 4096, reps=3, fused_f32=True)
+        r = bench_detail.time_prefill(torch, quant_gemm, 7, 2048, 14336, 4096, reps=8, fused_f32=True)
         extra["prefill_q5_1_M2048_N14336_K4096_incl_quantize"] = {
             "us": r["us"], "tops": r["tops"], "path": r["path"], "frac_of_nominal_int8_4500_tops": r["tops"] / 4500.0,
             "note": "BASELINE configs[3]; fp32 activations in, quantize_q8_1 inside the call (two launches), L2 flushed between reps"}

@@ -8,13 +8,14 @@
 // per-block scale is applied once per block, d * sum_k a_k * (q_k - 8), and K is summed in a different (parallel)
 // order, so results agree with the reference's sequential FMA chain to ~1e-6 of max|C| (tests: <= 1e-5), not bit for bit.
 //
-//   T <= 8  (decode): HBM-bound weight stream.  One warp per weight row, a lane owns pairs of adjacent blocks (a pair
-//            starts 4-byte aligned, 9 / 17 coalesced words); weights go nibble -> fp32 with one byte-permute and one
-//            packed add per two values (0x4B000000 | n is the float 2^23 + n), then packed FMAs against the activations,
-//            which every warp of the CTA re-reads through L1.
+//   T <= 8  (decode): weight stream against activations held in shared memory (f32act_gemv_smem_kernel), or, when they do
+//            not fit, re-read coalesced through L1 (f32act_gemv_kernel).  fp32 activations cost 4 bytes of on-chip traffic
+//            per weight element and token, so unlike the q8_1 path this one is bound by the load/store pipe, not by HBM.
 //   T  > 8  (prefill): 64 rows x 64 tokens register-tiled fp32 GEMM; weights are dequantized into shared memory one
 //            block column (32 k) at a time.  CUDA cores only: fp32 x fp32 has no exact tensor-core form short of a
 //            3-way split; this path is a neighbour of the hot path, not the hot path.
+#include <algorithm>
+
 #include "qgemm_common.cuh"
 
 namespace qgemm {
@@ -95,42 +96,126 @@ constexpr int kFaWarps = 8;
 template <int WT, int TT>
 __global__ void __launch_bounds__(kFaWarps * 32) f32act_gemv_kernel(const float* __restrict__ act, const uint8_t* __restrict__ wgt,
                                                                    float* __restrict__ C, int F, int K, int64_t ldc_t, int64_t ldc_f) {
-    constexpr int kPairWords = Fmt<WT>::bytes / 2;   // 9 (q4_0) or 17 (q8_0) words per pair of blocks
+    // Activations too large for shared memory (T * K * 4 > ~200 KB).  One warp per weight row.  A warp step covers four
+    // adjacent blocks (128 k): lane = (block b of the four, float4 j of its 32 elements), so the activations are read as one
+    // coalesced 512-byte run per token and the 72 / 136 weight bytes as adjacent half-words.  q4_0: elements 4j .. 4j+3 are
+    // the low (j < 4) or high (j >= 4) nibbles of bytes 4(j & 3) .. of the block.  (A first version gave every lane whole
+    // blocks and read their activations from global memory: 128-byte private reads, 32 L1 wavefronts per instruction,
+    // 0.56 TB/s.)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nb = K / 32, np = nb / 2;
+    const int j = lane & 7, bsub = lane >> 3;
+    const int nb = K / 32;
     const size_t rowbytes = (size_t)nb * Fmt<WT>::bytes;
+    constexpr float kOff = (WT == QGEMM_TYPE_Q4_0) ? 8.0f : 128.0f;
+    const uint64_t bias = pk2(-(8388608.0f + kOff), -(8388608.0f + kOff));
     for (int f = blockIdx.x * kFaWarps + warp; f < F; f += gridDim.x * kFaWarps) {
-        const uint32_t* row = reinterpret_cast<const uint32_t*>(wgt + (size_t)f * rowbytes);   // 4-byte aligned: nb even
+        const uint8_t* row = wgt + (size_t)f * rowbytes;
         float acc[TT];
 #pragma unroll
         for (int t = 0; t < TT; t++) acc[t] = 0.f;
-        for (int pg = lane; pg < np; pg += 32) {
-            uint32_t x[kPairWords];
-#pragma unroll
-            for (int i = 0; i < kPairWords; i++) x[i] = __ldcs(row + (size_t)pg * kPairWords + i);   // streamed once
-#pragma unroll
-            for (int which = 0; which < 2; which++) {
-                uint32_t w[8];
-                float d;
-                pair_block_words<WT, kPairWords>(x, which, w, d);
-                uint64_t v[16];
-                block_to_float<WT>(w, v);
-                const int k0 = (2 * pg + which) * 32;
-#pragma unroll
-                for (int t = 0; t < TT; t++) {
-                    const float4* a4 = reinterpret_cast<const float4*>(act + (size_t)t * K + k0);
-                    uint64_t s2 = 0ull;   // (even-k partial, odd-k partial)
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const float4 a = __ldg(a4 + i);
-                        s2 = ffma2r(pk2(a.x, a.y), v[2 * i], s2);
-                        s2 = ffma2r(pk2(a.z, a.w), v[2 * i + 1], s2);
-                    }
-                    float s0, s1;
-                    unpk2(s2, s0, s1);
-                    acc[t] = __fmaf_rn(d, s0 + s1, acc[t]);
-                }
+#pragma unroll 4
+        for (int b = bsub; b < nb; b += 4) {
+            const uint8_t* blk = row + (size_t)b * Fmt<WT>::bytes;
+            const float d = ld_half(blk);
+            uint32_t u;
+            if constexpr (WT == QGEMM_TYPE_Q4_0) {
+                const uint8_t* q = blk + 2 + 4 * (j & 3);
+                u = ld_u16(q) | (ld_u16(q + 2) << 16);
+                u = ((j & 4) ? (u >> 4) : u) & 0x0f0f0f0fu;
+            } else {
+                const uint8_t* q = blk + 2 + 4 * j;
+                u = (ld_u16(q) | (ld_u16(q + 2) << 16)) ^ 0x80808080u;
             }
+            const uint64_t w01 = fadd2r(pk2(byte_as_biased_float<0>(u), byte_as_biased_float<1>(u)), bias);
+            const uint64_t w23 = fadd2r(pk2(byte_as_biased_float<2>(u), byte_as_biased_float<3>(u)), bias);
+            const int k0 = b * 32 + 4 * j;
+#pragma unroll
+            for (int t = 0; t < TT; t++) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(act + (size_t)t * K + k0));
+                uint64_t s2 = ffma2r(pk2(a.x, a.y), w01, 0ull);   // (even-k partial, odd-k partial)
+                s2 = ffma2r(pk2(a.z, a.w), w23, s2);
+                float s0, s1;
+                unpk2(s2, s0, s1);
+                acc[t] = __fmaf_rn(d, s0 + s1, acc[t]);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < TT; t++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);
+        }
+        if (lane < TT) {
+            float v = acc[0];
+#pragma unroll
+            for (int t = 1; t < TT; t++) v = (lane == t) ? acc[t] : v;
+            C[(int64_t)lane * ldc_t + (int64_t)f * ldc_f] = v;
+        }
+    }
+}
+
+// Decode with the activations resident in shared memory (T * K * 4 bytes <= ~200 KB: every Llama shape up to T = 4, and
+// K = 4096 up to T = 8).  Persistent CTAs, one warp per weight row, a lane owns PAIRS of adjacent blocks (a pair starts
+// 4-byte aligned: 9 / 17 words), so a warp instruction dequantizes and multiplies 32 blocks at once -- five times fewer
+// instructions per element than the kernel above.  Weights go nibble -> fp32 with one byte-permute and one packed add per
+// two values (0x4B000000 | n is the float 2^23 + n).  The activations are stored float4-wise with the float4 index inside
+// a block XORed by the pair index, so that the lanes of a quarter warp (8 consecutive pairs, same float4 index) read 8
+// different bank groups.  The words of a row's first two pair groups are requested before either is used.
+constexpr int kFsWarps = 16;
+
+template <int WT, int TT>
+__global__ void __launch_bounds__(kFsWarps * 32) f32act_gemv_smem_kernel(const float* __restrict__ act, const uint8_t* __restrict__ wgt,
+                                                                        float* __restrict__ C, int F, int K, int64_t ldc_t, int64_t ldc_f) {
+    extern __shared__ float4 sA[];   // [TT][K / 4], swizzled inside every block of 8
+    constexpr int kPairWords = Fmt<WT>::bytes / 2;   // 9 (q4_0) or 17 (q8_0) words per pair of blocks
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nb = K / 32, np = nb / 2, ng = K / 4;
+    for (int g = threadIdx.x; g < TT * ng; g += blockDim.x) {
+        const int t = g / ng, q = g - t * ng, b = q >> 3, i = q & 7;
+        sA[t * ng + (b << 3) + (i ^ ((b >> 1) & 7))] = __ldg(reinterpret_cast<const float4*>(act) + g);
+    }
+    __syncthreads();
+    const size_t rowbytes = (size_t)nb * Fmt<WT>::bytes;
+    float acc[TT];
+    auto fold_pair_words = [&](const uint32_t (&x)[kPairWords], int pg) {
+#pragma unroll
+        for (int which = 0; which < 2; which++) {
+            uint32_t w[8];
+            float d;
+            pair_block_words<WT, kPairWords>(x, which, w, d);
+            uint64_t v[16];
+            block_to_float<WT>(w, v);
+            const int b = 2 * pg + which, sw = pg & 7;
+#pragma unroll
+            for (int t = 0; t < TT; t++) {
+                const float4* a4 = sA + t * ng + (b << 3);
+                uint64_t s2 = 0ull;   // (even-k partial, odd-k partial)
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const float4 a = a4[i ^ sw];
+                    s2 = ffma2r(pk2(a.x, a.y), v[2 * i], s2);
+                    s2 = ffma2r(pk2(a.z, a.w), v[2 * i + 1], s2);
+                }
+                float s0, s1;
+                unpk2(s2, s0, s1);
+                acc[t] = __fmaf_rn(d, s0 + s1, acc[t]);
+            }
+        }
+    };
+    for (int f = blockIdx.x * kFsWarps + warp; f < F; f += gridDim.x * kFsWarps) {
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(wgt + (size_t)f * rowbytes);   // 4-byte aligned: nb even
+#pragma unroll
+        for (int t = 0; t < TT; t++) acc[t] = 0.f;
+        for (int pg = lane; pg < np; pg += 64) {
+            uint32_t x0[kPairWords], x1[kPairWords];
+            const bool two = pg + 32 < np;
+#pragma unroll
+            for (int i = 0; i < kPairWords; i++) x0[i] = __ldcs(row + (size_t)pg * kPairWords + i);   // streamed once
+            if (two) {
+#pragma unroll
+                for (int i = 0; i < kPairWords; i++) x1[i] = __ldcs(row + (size_t)(pg + 32) * kPairWords + i);
+            }
+            fold_pair_words(x0, pg);
+            if (two) fold_pair_words(x1, pg + 32);
         }
 #pragma unroll
         for (int t = 0; t < TT; t++) {
@@ -295,6 +380,20 @@ static cudaError_t launch_f32act_t(const float* act, const void* wgt, float* C, 
                                    int num_sms, cudaStream_t st) {
     const uint8_t* w = (const uint8_t*)wgt;
     if (T <= 8) {
+        const size_t smem = (size_t)T * K * sizeof(float);
+        if (smem <= 200 * 1024 && !QGEMM_ENV("QGEMM_A16_NO_SMEM")) {
+            const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / (kFsWarps * 32), (220 * 1024) / (smem + 1024)));
+            const int grid = min((F + kFsWarps - 1) / kFsWarps, num_sms * per_sm);
+#define QG_FS(TTv)                                                                                                   \
+    case TTv:                                                                                                        \
+        if (cudaError_t e = smem_optin(reinterpret_cast<const void*>(f32act_gemv_smem_kernel<WT, TTv>), smem)) return e; \
+        f32act_gemv_smem_kernel<WT, TTv><<<grid, kFsWarps * 32, smem, st>>>(act, w, C, F, K, ldc_t, ldc_f);             \
+        break;
+            switch (T) { QG_FS(1) QG_FS(2) QG_FS(3) QG_FS(4) QG_FS(5) QG_FS(6) QG_FS(7) QG_FS(8) default: return cudaErrorInvalidValue; }
+#undef QG_FS
+            note_launch();
+            return cudaGetLastError();
+        }
         const int grid = min((F + kFaWarps - 1) / kFaWarps, num_sms * 8);
 #define QG_FA(TTv) case TTv: f32act_gemv_kernel<WT, TTv><<<grid, kFaWarps * 32, 0, st>>>(act, w, C, F, K, ldc_t, ldc_f); break;
         switch (T) { QG_FA(1) QG_FA(2) QG_FA(3) QG_FA(4) QG_FA(5) QG_FA(6) QG_FA(7) QG_FA(8) default: return cudaErrorInvalidValue; }
