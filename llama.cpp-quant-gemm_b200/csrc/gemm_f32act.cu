@@ -205,17 +205,22 @@ __global__ void __launch_bounds__(kFsWarps * 32) f32act_gemv_smem_kernel(const f
         const uint32_t* row = reinterpret_cast<const uint32_t*>(wgt + (size_t)f * rowbytes);   // 4-byte aligned: nb even
 #pragma unroll
         for (int t = 0; t < TT; t++) acc[t] = 0.f;
-        for (int pg = lane; pg < np; pg += 64) {
-            uint32_t x0[kPairWords], x1[kPairWords];
-            const bool two = pg + 32 < np;
+        constexpr bool kTwoDeep = kPairWords <= 9;   // q8_0's 17-word pairs would spill
+        for (int pg = lane; pg < np; pg += (kTwoDeep ? 64 : 32)) {
+            uint32_t x0[kPairWords], x1[kTwoDeep ? kPairWords : 1];
+            const bool two = kTwoDeep && pg + 32 < np;
 #pragma unroll
             for (int i = 0; i < kPairWords; i++) x0[i] = __ldcs(row + (size_t)pg * kPairWords + i);   // streamed once
-            if (two) {
+            if constexpr (kTwoDeep) {
+                if (two) {
 #pragma unroll
-                for (int i = 0; i < kPairWords; i++) x1[i] = __ldcs(row + (size_t)(pg + 32) * kPairWords + i);
+                    for (int i = 0; i < kPairWords; i++) x1[i] = __ldcs(row + (size_t)(pg + 32) * kPairWords + i);
+                }
             }
             fold_pair_words(x0, pg);
-            if (two) fold_pair_words(x1, pg + 32);
+            if constexpr (kTwoDeep) {
+                if (two) fold_pair_words(x1, pg + 32);
+            }
         }
 #pragma unroll
         for (int t = 0; t < TT; t++) {
