@@ -551,10 +551,11 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
                         const uint32_t bytes = (uint32_t)min(kBM, p.T - t0) * 4u;
                         constexpr int kRowsPerWarp = kBN / kEpiWarps;
 #pragma unroll 1
-                        for (int q = 0; q < p.peer.world; q++) {
+                        const int ndst = p.peer.mc ? 1 : p.peer.world;   // one store to the multicast mapping reaches every rank
+                        for (int q = 0; q < ndst; q++) {
                             int r = p.peer.rank + 1 + q;   // staggered start: the ranks target different receivers
                             if (r >= p.peer.world) r -= p.peer.world;
-                            float* Cr = p.peer.C[r];
+                            float* Cr = p.peer.mc ? p.peer.mc : p.peer.C[r];
 #pragma unroll 1
                             for (int k = 0; k < kRowsPerWarp; k++) {
                                 const int fl = ew * kRowsPerWarp + k;
@@ -756,10 +757,12 @@ cudaError_t launch_mmq_native(int wtype, const uint8_t* a8, const float2* as, co
     p.dbg = QGEMM_ENV("QGEMM_MMQ_DBG") ? atoi(QGEMM_ENV("QGEMM_MMQ_DBG")) : 0;
     p.peer = peer ? *peer : PeerOut{};
     p.tma_out = 0;
-    if (p.peer.world > 1 && !p.peer.mc && !sumi && ldc_t == 1 && T % 4 == 0 && ldc_f % 4 == 0 && !QGEMM_ENV("QGEMM_MMQ_NO_TMA_OUT")) {
+    if (p.peer.world > 1 && (!p.peer.mc || QGEMM_ENV("QGEMM_MMQ_MC_TMA")) && !sumi && ldc_t == 1 && T % 4 == 0 && ldc_f % 4 == 0 &&
+        !QGEMM_ENV("QGEMM_MMQ_NO_TMA_OUT")) {
         p.tma_out = 1;
         for (int r = 0; r < p.peer.world; r++)
             if (reinterpret_cast<uintptr_t>(p.peer.C[r]) % 16 != 0) p.tma_out = 0;
+        if (p.peer.mc && reinterpret_cast<uintptr_t>(p.peer.mc) % 16 != 0) p.tma_out = 0;
     }
     switch (wtype) {
     case QGEMM_TYPE_Q4_0: return nat::launch_t<QGEMM_TYPE_Q4_0>(p, wgt, refseq, num_sms, st);
