@@ -113,7 +113,7 @@ static MmqPack mmq_pack_layout(int F, int K) {
 //   as[t / 128][b][t % 128] = (d_a, coef * s_a)     coef: -8 (q4_0), -16 (q5_0), 1/4 or 1 (q4_1/q5_1), 0 (q8_0)
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void repack_act_body(int64_t gid, const uint8_t* __restrict__ act, uint8_t* __restrict__ a8,
-                                                float2* __restrict__ as, int T, int Tpad, int nb, int nbp, float coef) {
+                                                float2* __restrict__ as, int T, int Tpad, int nb, int nbp, float coef, int pairs = 0) {
     if (gid >= (int64_t)Tpad * nbp) return;
     // 4 consecutive lanes = the 4 blocks of one 128-byte operand row: contiguous reads (4 x 36 B) and
     // a contiguous 128-byte write per row, 8 rows per warp
@@ -133,15 +133,21 @@ __device__ __forceinline__ void repack_act_body(int64_t gid, const uint8_t* __re
     uint8_t* row = a8 + ((size_t)kc * Tpad + t) * kKC;
     *reinterpret_cast<uint4*>(row + ((c ^ (t & 7)) << 4)) = q0;
     *reinterpret_cast<uint4*>(row + (((c + 1) ^ (t & 7)) << 4)) = q1;
-    as[((size_t)(t / kBM) * nbp + b) * kBM + (t % kBM)] = sc;
+    if (!pairs) {
+        as[((size_t)(t / kBM) * nbp + b) * kBM + (t % kBM)] = sc;
+    } else {   // (d_a, d_a') (c_a, c_a') per pair of tokens: the form the weight-major kernel reads as packed pairs
+        float* asf = reinterpret_cast<float*>(as + ((size_t)(t / kBM) * nbp + b) * kBM) + (((t % kBM) >> 1) << 2) + (t & 1);
+        asf[0] = sc.x;
+        asf[2] = sc.y;
+    }
 }
 __global__ void __launch_bounds__(256)
 mmq_repack_act_kernel(const uint8_t* __restrict__ act, uint8_t* __restrict__ a8, float2* __restrict__ as, int T,
-                      int Tpad, int nb, int nbp, float coef, unsigned* zero = nullptr, int nzero = 0) {
+                      int Tpad, int nb, int nbp, float coef, unsigned* zero = nullptr, int nzero = 0, int pairs = 0) {
     ptx::griddep_launch_dependents();   // the GEMM kernel behind this one may set itself up while we run
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid < nzero) zero[gid] = 0u;    // split-K arrival counters of the GEMM behind us
-    repack_act_body(gid, act, a8, as, T, Tpad, nb, nbp, coef);
+    repack_act_body(gid, act, a8, as, T, Tpad, nb, nbp, coef, pairs);
 }
 
 // ---------------------------------------------------------------------------
@@ -484,7 +490,8 @@ size_t mmq_workspace_need(int wtype, const void* wgt, int T, int F, int K, uint3
 
 cudaError_t launch_mmq_native(int wtype, const uint8_t* a8, const float2* as, const void* wgt, float* C, int32_t* sumi, int T,
                               int F, int K, int Tpad, int64_t ldc_t, int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t st,
-                              const PeerOut* peer, void* split_ws, size_t split_ws_bytes);
+                              const PeerOut* peer, void* split_ws, size_t split_ws_bytes, int tokn = 0);
+int mmq_native_tokn(int T, const PeerOut* peer, bool dump, uint32_t flags);
 
 template <int WT>
 static cudaError_t launch_mmq_t(const void* act, const void* wgt, float* C, int32_t* sumi, int T, int F, int K,
@@ -506,12 +513,13 @@ static cudaError_t launch_mmq_t(const void* act, const void* wgt, float* C, int3
         int ncount = 0;
         unsigned* counters = mmq_native_split_counters(T, F, K, flags, num_sms, ws_bytes > L.w8 ? base + L.w8 : nullptr,
                                                        ws_bytes > L.w8 ? ws_bytes - L.w8 : 0, sumi != nullptr, peer, &ncount);
+        const int tokn = mmq_native_tokn(T, peer, sumi != nullptr, flags);   // small batch: weight-major kernel form
         mmq_repack_act_kernel<<<act_blocks, 256, 0, st>>>((const uint8_t*)act, base + L.a8, (float2*)(base + L.as), T, L.Tpad,
-                                                          nb, nbp, coef, counters, ncount);
+                                                          nb, nbp, coef, counters, ncount, tokn != 0);
         note_launch();
         if (cudaError_t e = cudaGetLastError()) return e;
         return launch_mmq_native(WT, base + L.a8, (const float2*)(base + L.as), wgt, C, sumi, T, F, K, L.Tpad, ldc_t, ldc_f, flags,
-                                 num_sms, st, peer, ws_bytes > L.w8 ? base + L.w8 : nullptr, ws_bytes > L.w8 ? ws_bytes - L.w8 : 0);
+                                 num_sms, st, peer, ws_bytes > L.w8 ? base + L.w8 : nullptr, ws_bytes > L.w8 ? ws_bytes - L.w8 : 0, tokn);
     }
     if (flags & QGEMM_WEIGHTS_PREPACKED) {  // `wgt` is a qgemm_prepack_weights() buffer: nothing to unpack
         const MmqPack P = mmq_pack_layout(F, K);

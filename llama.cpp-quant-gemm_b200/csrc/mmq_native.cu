@@ -39,6 +39,10 @@
 #endif
 
 namespace qgemm {
+#ifndef QGEMM_NAT_EARLY_WEIGHTS
+#define QGEMM_NAT_EARLY_WEIGHTS 1
+#endif
+
 namespace nat {
 
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
@@ -94,6 +98,7 @@ struct Params {
     PeerOut peer;
     int tma_out;
 };
+
 
 // 2-D tensor load (TMA): box of the weight matrix viewed as [F][row bytes / 2] uint16 -> dense [128][box bytes] in smem
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
@@ -174,8 +179,20 @@ __device__ __forceinline__ void unpack_half_row(const uint8_t* raw_half, uint8_t
     unpack_one<WT, 3, NW>(y, tile_row, sw, ws, wm, row);
 }
 
-template <int WT, bool kDump, bool kRefSeq>
+// kTokN = 0: tokens on the M side of the MMA (TMEM lanes), 128 weight rows on N (columns).  kTokN = 32 / 64 (small
+// batches): the operands change places -- 128 weight rows on M, kTokN tokens on N -- so the fold, which bounds the kernel,
+// shrinks with the batch instead of being paid for 128 padded tokens; a thread then owns one weight row and kTokN / 4
+// tokens, d_w / m_w are per lane and (d_a, c_a) per column (the prepass writes them pair-wise for that, Params::as).
+template <int WT, bool kDump, bool kRefSeq, int kTokN = 0>
 __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p, const __grid_constant__ CUtensorMap wmap) {
+    // warp roles: 16 epilogue warps, 2 unpack warps in both forms.  (Weight-major with kTokN / 8 epilogue warps of 32 token
+    // columns each and 4 unpack warps was measured and is slower -- 32 x 11008 x 4096: 44 vs 34 us: one epilogue warp per
+    // sub-partition cannot hide the TMEM-load and barrier latencies.)
+    constexpr int kEW = kEpiWarps;
+    constexpr int kUW = kUnpackWarps;
+    constexpr int kWU = kEW, kWM = kWU + kUW, kWP = kWM + 1;
+    constexpr int kUTl = kUW * 32, kRPT = kBN / kUTl;
+    if (kTokN && threadIdx.x >= (kWP + 1) * 32) return;   // launched with exactly (kWP + 1) warps; a guard, not a path
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -223,27 +240,30 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
         return false;
     };
 
-    if (threadIdx.x == kWarpProd * 32) {
+    if (threadIdx.x == kWP * 32) {
         for (int s = 0; s < kMaxStages; s++) {
-            ptx::mbar_init(&full[s], 1 + kUnpackWarps);
-            ptx::mbar_init(&empty[s], 1 + kEpiWarps);
+            ptx::mbar_init(&full[s], 1 + kUW);
+            ptx::mbar_init(&empty[s], 1 + kEW);
         }
         for (int r = 0; r < kMaxRaw; r++) ptx::mbar_init(&rawfull[r], 1);
         for (int h = 0; h < 2; h++) {
             ptx::mbar_init(&tfull[h], 1);
-            ptx::mbar_init(&tempty[h], kEpiWarps);
+            ptx::mbar_init(&tempty[h], kEW);
         }
         ptx::fence_mbar_init();
         asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
     }
-    if (warp == kWarpMma) t5::alloc(tmem_slot, kTmemCols);
+    if (warp == kWM) t5::alloc(tmem_slot, kTmemCols);
     t5::fence_before();
     __syncthreads();
     t5::fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    ptx::griddep_wait();   // launched behind the activation prepass with programmatic serialization
+    // Launched behind the activation prepass with programmatic serialization.  Only what the prepass produces (operand
+    // tiles, scale slabs, cleared split counters) has to wait for it: the unpack warps start streaming and unpacking the
+    // weights at once (whatever wrote the weights ran before the prepass, which itself waited for it).
+    if (warp < kWU || warp >= kWU + kUW || QGEMM_NAT_EARLY_WEIGHTS == 0) ptx::griddep_wait();
 
-    if (warp == kWarpProd) {
+    if (warp == kWP) {
         // ===================== activation producer =====================
         if (lane == 0) {
             int s = 0;
@@ -266,11 +286,12 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
             if (blockIdx.x == 0 && (p.dbg & 32)) printf("producer: total %lld, waiting for empty %lld\n", clock64() - pf_t0, pf_wait);
 #endif
         }
-    } else if (warp == kWarpMma) {
+    } else if (warp == kWM) {
         // ===================== MMA issuer =====================
         // D[token, row] (s32) = A (s8 activations, M side) . B (u8 / s8 weights, N side)^T, both K-major
-        constexpr uint32_t idesc = (2u << 4) | (1u << 7) | ((Fmt<WT>::bits == 8 ? 1u : 0u) << 10) |
-                                   ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+        constexpr uint32_t wfmt = Fmt<WT>::bits == 8 ? 1u : 0u;   // s8 (q8_0) or u8
+        constexpr uint32_t idesc = kTokN == 0 ? (2u << 4) | (1u << 7) | (wfmt << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24)
+                                              : (2u << 4) | (wfmt << 7) | (1u << 10) | ((uint32_t)(kTokN >> 3) << 17) | ((uint32_t)(kBN >> 4) << 24);
         int s = 0;
         uint32_t ph = 0, tph = 0;
         PROF_DECL;
@@ -280,8 +301,9 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
             for (int kc = 0; kc < 2 * n; kc++) {
                 PROF_WAIT(pf_wait, ptx::mbar_wait_guarded(&full[s], ph));
                 t5::fence_after();
-                const uint64_t adesc = t5::smem_desc(ptx::smem_u32(stages + s * kStageBytes + kStageA));
-                const uint64_t bdesc = t5::smem_desc(ptx::smem_u32(stages + s * kStageBytes + kStageW));
+                // kTokN: the weight tile is the M-side operand, the first kTokN rows of the activation tile the N side
+                const uint64_t adesc = t5::smem_desc(ptx::smem_u32(stages + s * kStageBytes + (kTokN ? kStageW : kStageA)));
+                const uint64_t bdesc = t5::smem_desc(ptx::smem_u32(stages + s * kStageBytes + (kTokN ? kStageA : kStageW)));
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     PROF_WAIT(pf_wait2, ptx::mbar_wait_guarded(&tempty[h], tph ^ 1));
@@ -303,9 +325,9 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
 #ifdef QGEMM_MMQ_PROFILE
         if (blockIdx.x == 0 && lane == 0 && (p.dbg & 32)) printf("mma: total %lld, waiting for full %lld, for tempty %lld\n", clock64() - pf_t0, pf_wait, pf_wait2);
 #endif
-    } else if (warp >= kWarpUnpack) {
+    } else if (warp >= kWU) {
         // ===================== weight unpack =====================
-        const int u = threadIdx.x - kWarpUnpack * 32;   // this thread owns weight rows u, u + 64 of the tile
+        const int u = threadIdx.x - kWU * 32;   // this thread owns weight rows u, u + 64 of the tile
         constexpr int kRow = raw_row_bytes<WT>();
         constexpr int kHalf = kBPS * Fmt<WT>::bytes;
         int total = 0;                                    // raw stages of this CTA, units back to back
@@ -338,8 +360,8 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
             for (int h = 0; h < 2; h++) {
                 PROF_WAIT(pf_wait2, ptx::mbar_wait_guarded(&empty[s], ph ^ 1));
 #pragma unroll
-                for (int i = 0; i < kRowsPerThread; i++) {
-                    const int row = u + i * kUT;
+                for (int i = 0; i < kRPT; i++) {
+                    const int row = u + i * kUTl;
                     unpack_half_row<WT>(rslot + row * kRow + h * kHalf, stages + s * kStageBytes, row);
                 }
                 ptx::fence_proxy_async();                 // generic-proxy stores -> visible to the tensor core's reads
@@ -349,7 +371,7 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
             }
             if (++r == nraw) { r = 0; rph ^= 1; }
             if (issued < total) {
-                ptx::bar_sync(1, kUT);                    // both warps are done reading the slot
+                ptx::bar_sync(1, kUTl);                    // both warps are done reading the slot
                 issue();
             }
         }
@@ -360,10 +382,12 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
         // ===================== epilogue =====================
         const int ew = warp;
         const int quarter = warp & 3;           // TMEM lane quarter this warp may touch
-        const int cgrp = ew >> 2;               // which 32-column group
-        const int row = quarter * 32 + lane;    // token row inside the tile
-        const uint32_t tm = tmem_base + ((uint32_t)(quarter * 32) << 16) + cgrp * kEpiCols;
-        static_assert(kEpiCols == 32, "one tcgen05.ld.x32 per block per thread");
+        const int cgrp = ew >> 2;               // which column group
+        const int row = quarter * 32 + lane;    // TMEM lane = token row inside the tile (kTokN: weight row)
+        constexpr int NC = kTokN ? kTokN / 4 : kEpiCols;   // columns per thread
+        const uint32_t tm = tmem_base + ((uint32_t)(quarter * 32) << 16) + cgrp * NC;
+        static_assert(kEpiCols == 32 && (NC == 32 || NC == 16 || NC == 8), "one tcgen05.ld per block per thread");
+        static_assert(!(kDump && kTokN), "the block-sum dump uses the token-major form");
         int s = 0;
         uint32_t ph = 0, tph = 0;
         PROF_DECL;
@@ -375,9 +399,9 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
             long long pf_ts[6] = {0, 0, 0, 0, 0, 0};
             PROF_STAMP(0);
 #endif
-            uint64_t acc[kEpiCols / 2];  // fp32 accumulators as packed pairs (columns 2i, 2i+1)
+            uint64_t acc[NC / 2];  // fp32 accumulators as packed pairs (columns 2i, 2i+1)
 #pragma unroll
-            for (int i = 0; i < kEpiCols / 2; i++) acc[i] = 0ull;
+            for (int i = 0; i < NC / 2; i++) acc[i] = 0ull;
 #pragma unroll 1
             for (int kc = 2 * rs0; kc < 2 * (rs0 + n); kc++) {
                 PROF_WAIT(pf_wait, ptx::mbar_wait_guarded(&full[s], ph));  // scale slabs of this stage are visible
@@ -390,8 +414,8 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
 #pragma unroll
                     for (int jj = 0; jj < 2; jj++) {
                         const int j = 2 * h + jj;
-                        int x[kEpiCols];
-                        t5::ld32(tm + j * kBN, x);
+                        int x[NC];
+                        t5::ldn<NC>(tm + j * kBN, x);
                         t5::wait_ld();
                         if (jj == 1) {   // both blocks of this half are in registers: hand the half back to the tensor core
                             t5::fence_before();
@@ -406,6 +430,21 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
                                     const int f = nt * kBN + cgrp * kEpiCols + i;
                                     if (f < p.F) p.sumi[((size_t)t * p.F + f) * p.nb + b] = x[i];
                                 }
+                            }
+                        } else if constexpr (kTokN > 0) {
+                            // lane = weight row: its d_w (m_w) of this block; columns = tokens: (d_a, d_a'), (c_a, c_a') per pair
+                            const float dwf = reinterpret_cast<const float*>(st + kStageWS)[j * kBN + row];
+                            const uint64_t dw = pk(dwf, dwf);
+                            uint64_t mw = 0ull;
+                            if constexpr (Fmt<WT>::m >= 0) {
+                                const float mwf = reinterpret_cast<const float*>(st + kStageWM)[j * kBN + row];
+                                mw = pk(mwf, mwf);
+                            }
+                            const ulonglong2* sc = reinterpret_cast<const ulonglong2*>(st + kStageAS) + (j * kBM + cgrp * NC) / 2;
+#pragma unroll
+                            for (int i = 0; i < NC / 2; i++) {
+                                const ulonglong2 a = sc[i];   // broadcast read
+                                acc[i] = fold_pair<WT, kRefSeq>(acc[i], x[2 * i], x[2 * i + 1], dw, mw, a.x, a.y);
                             }
                         } else {
                             const float2 a = reinterpret_cast<const float2*>(st + kStageAS)[j * kBM + row];
@@ -439,17 +478,17 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
                     const bool final_unit = cu.w >= sk_w1;
                     // scratch layout of a partial tile: float4 (columns 4j .. 4j+3 of token `row`) at [j][row], so that the
                     // lanes of a warp (consecutive tokens) touch consecutive 16-byte words
-                    const size_t off = (size_t)(cgrp * (kEpiCols / 4)) * kBM + row;
+                    const size_t off = (size_t)(cgrp * (NC / 4)) * kBM + row;
                     float4* part = reinterpret_cast<float4*>(p.partial + ((size_t)seg * p.sk_ctas + blockIdx.x) * (kBM * kBN)) + off;
                     auto publish = [&]() {
 #pragma unroll
-                        for (int i = 0; i < kEpiCols / 4; i++) {
+                        for (int i = 0; i < NC / 4; i++) {
                             float4 v;
                             unpk(acc[2 * i], v.x, v.y);
                             unpk(acc[2 * i + 1], v.z, v.w);
                             __stcg(part + i * kBM, v);
                         }
-                        ptx::bar_sync(3, kEpiWarps * 32);
+                        ptx::bar_sync(3, kEW * 32);
                         if (threadIdx.x == 0) {
                             __threadfence();   // cumulative: covers the stores the barrier has ordered before this thread
                             atomicAdd(p.tile_count + 2 * ct + 1, 1u);
@@ -476,10 +515,10 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
                         }
                         split_info[0] = last; split_info[1] = c0; split_info[2] = c1;
                     }
-                    ptx::bar_sync(3, kEpiWarps * 32);
+                    ptx::bar_sync(3, kEW * 32);
                     const bool last = split_info[0] != 0;
                     const int c0 = split_info[1], c1 = split_info[2];
-                    ptx::bar_sync(3, kEpiWarps * 32);            // the words may be rewritten by the next unit
+                    ptx::bar_sync(3, kEW * 32);            // the words may be rewritten by the next unit
                     PROF_STAMP(2);
                     if (!last) {
                         if (final_unit) publish();
@@ -498,27 +537,27 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
                     const int me = final_unit ? (int)blockIdx.x : -1;
                     if (me >= 0 && me != c0) {
 #pragma unroll
-                        for (int i = 0; i < kEpiCols / 4; i++) {
+                        for (int i = 0; i < NC / 4; i++) {
                             float4 v;
                             unpk(acc[2 * i], v.x, v.y);
                             unpk(acc[2 * i + 1], v.z, v.w);
-                            own[i * (kEpiWarps * 32)] = v;
+                            own[i * (kEW * 32)] = v;
                         }
                     }
 #pragma unroll 1
                     for (int c = (me == c0 ? c0 + 1 : c0); c <= c1; c++) {
                         // CTA c's segment of this tile is its first cut unit unless its share began in the tile before
                         const float4* ps = reinterpret_cast<const float4*>(p.partial + ((size_t)(sk_begin(c) >= x0 ? 0 : 1) * p.sk_ctas + c) * (kBM * kBN)) + off;
-                        float4 in[kEpiCols / 4];
+                        float4 in[NC / 4];
                         if (c == me) {
 #pragma unroll
-                            for (int i = 0; i < kEpiCols / 4; i++) in[i] = own[i * (kEpiWarps * 32)];
+                            for (int i = 0; i < NC / 4; i++) in[i] = own[i * (kEW * 32)];
                         } else {
 #pragma unroll
-                            for (int i = 0; i < kEpiCols / 4; i++) in[i] = __ldcg(ps + i * kBM);
+                            for (int i = 0; i < NC / 4; i++) in[i] = __ldcg(ps + i * kBM);
                         }
 #pragma unroll
-                        for (int i = 0; i < kEpiCols / 4; i++) {
+                        for (int i = 0; i < NC / 4; i++) {
                             const float4 v = in[i];
                             if (c == c0) {
                                 acc[2 * i] = pk(v.x, v.y);
@@ -531,12 +570,27 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
                     }
                 }
                 PROF_STAMP(4);
+                if constexpr (kTokN > 0) {
+                    // row f of C, tokens cgrp * NC ..: contiguous along t in the ggml layout (ldc_t = 1)
+                    const int f = nt * kBN + row;
+                    if (f < p.F && !(p.dbg & 4)) {
+                        float* crow = p.C + (int64_t)f * p.ldc_f;
+#pragma unroll
+                        for (int i = 0; i < NC / 2; i++) {
+                            float v0, v1;
+                            unpk(acc[i], v0, v1);
+                            const int t0 = cgrp * NC + 2 * i;
+                            if (t0 < p.T) crow[(int64_t)t0 * p.ldc_t] = v0;
+                            if (t0 + 1 < p.T) crow[(int64_t)(t0 + 1) * p.ldc_t] = v1;
+                        }
+                    }
+                } else {
                 const int t = mt * kBM + row;
                 if (p.tma_out) {
                     // Fused all-gather, bulk variant (see mmq.cu): the tile is staged as [f][t] and carried to every rank's
                     // gathered C by the TMA engine, 512-byte rows, while the epilogue warps go on with the next tile.
                     if (lane == 0) ptx::bulk_wait_read();
-                    ptx::bar_sync(3, kEpiWarps * 32);
+                    ptx::bar_sync(3, kEW * 32);
 #pragma unroll
                     for (int i = 0; i < kEpiCols / 2; i++) {
                         float v0, v1;
@@ -545,13 +599,13 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
                         out_tile[(cgrp * kEpiCols + 2 * i + 1) * kBM + row] = v1;
                     }
                     ptx::fence_proxy_async();
-                    ptx::bar_sync(3, kEpiWarps * 32);
+                    ptx::bar_sync(3, kEW * 32);
                     if (lane == 0) {
                         const int t0 = mt * kBM;
                         const uint32_t bytes = (uint32_t)min(kBM, p.T - t0) * 4u;
-                        constexpr int kRowsPerWarp = kBN / kEpiWarps;
-#pragma unroll 1
+                        constexpr int kRowsPerWarp = kBN / kEW;
                         const int ndst = p.peer.mc ? 1 : p.peer.world;   // one store to the multicast mapping reaches every rank
+#pragma unroll 1
                         for (int q = 0; q < ndst; q++) {
                             int r = p.peer.rank + 1 + q;   // staggered start: the ranks target different receivers
                             if (r >= p.peer.world) r -= p.peer.world;
@@ -582,6 +636,7 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
                         }
                     }
                 }
+                }   // token-major store
 #ifdef QGEMM_MMQ_PROFILE
                 PROF_STAMP(5);
                 if (threadIdx.x == 0 && (p.dbg & 64) && blockIdx.x % 37 == 0)
@@ -602,7 +657,7 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
     }
     t5::fence_before();
     __syncthreads();
-    if (warp == kWarpMma) t5::dealloc(tmem_base, kTmemCols);
+    if (warp == kWM) t5::dealloc(tmem_base, kTmemCols);
     if constexpr (!kDump) {
         if (threadIdx.x == 0) peer_signal_done(p.peer, gridDim.x);  // the barrier above ordered every epilogue store
     }
@@ -640,7 +695,7 @@ static bool make_weight_map(CUtensorMap* map, const void* wgt, int F, int nb) {
 }
 
 template <int WT>
-static cudaError_t launch_t(Params p, const void* wgt, bool refseq, int num_sms, cudaStream_t st) {
+static cudaError_t launch_t(Params p, const void* wgt, bool refseq, int num_sms, cudaStream_t st, int tokn) {
     CUtensorMap wmap;
     if (!make_weight_map<WT>(&wmap, wgt, p.F, p.nb)) return cudaErrorNotSupported;
     // operand ring 3 deep (2 next to the peer staging tile), raw ring as deep as fits
@@ -652,11 +707,13 @@ static cudaError_t launch_t(Params p, const void* wgt, bool refseq, int num_sms,
     // q4_1 / q5_1 have a cheaper fold than the reference's operation sequence (tc05.cuh); refseq keeps the latter
     constexpr bool kHasM = Fmt<WT>::m >= 0;
     const bool fast = kHasM && !refseq;
-    const void* fn = p.sumi ? reinterpret_cast<const void*>(mmq_native_kernel<WT, true, true>)
-                     : fast ? reinterpret_cast<const void*>(mmq_native_kernel<WT, false, !kHasM>)
-                            : reinterpret_cast<const void*>(mmq_native_kernel<WT, false, true>);
-    if (cudaError_t e = smem_optin(fn, smem)) return e;
-    const int ntiles = p.tiles_m * p.tiles_n;
+    using KernelFn = void (*)(const Params, const CUtensorMap);
+    KernelFn kfn;
+    if (p.sumi) kfn = mmq_native_kernel<WT, true, true>;
+    else if (tokn == 32) kfn = fast ? mmq_native_kernel<WT, false, !kHasM, 32> : mmq_native_kernel<WT, false, true, 32>;
+    else if (tokn == 64) kfn = fast ? mmq_native_kernel<WT, false, !kHasM, 64> : mmq_native_kernel<WT, false, true, 64>;
+    else kfn = fast ? mmq_native_kernel<WT, false, !kHasM> : mmq_native_kernel<WT, false, true>;
+    if (cudaError_t e = smem_optin(reinterpret_cast<const void*>(kfn), smem)) return e;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(max(min(p.nfull, num_sms), p.sk_ctas));
     cfg.blockDim = dim3(kThreads);
@@ -667,9 +724,7 @@ static cudaError_t launch_t(Params p, const void* wgt, bool refseq, int num_sms,
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    cudaError_t e = p.sumi ? cudaLaunchKernelEx(&cfg, mmq_native_kernel<WT, true, true>, p, wmap)
-                    : fast ? cudaLaunchKernelEx(&cfg, mmq_native_kernel<WT, false, !kHasM>, p, wmap)
-                           : cudaLaunchKernelEx(&cfg, mmq_native_kernel<WT, false, true>, p, wmap);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kfn, p, wmap);
     note_launch();
     return e;
 }
@@ -730,11 +785,21 @@ unsigned* mmq_native_split_counters(int T, int F, int K, uint32_t flags, int num
     return (unsigned*)((char*)split_ws + (size_t)pl.sk_ctas * pl.slots * nat::kBM * nat::kBN * sizeof(float));
 }
 
+// Small batches take the kernel form with the weights on the M side and 32 / 64 tokens on the N side (0: the token-major
+// form).  The prepass must then write the (d_a, c_a) slabs pair-wise (see mmq_repack_act_kernel).  Not with peers (their
+// epilogue stores are token-major) and not for the block-sum dump.
+int mmq_native_tokn(int T, const PeerOut* peer, bool dump, uint32_t flags) {
+    (void)flags;
+    if (dump || (peer && peer->world > 1) || QGEMM_ENV("QGEMM_MMQ_NO_SWAP")) return 0;
+    return T <= 32 ? 32 : T <= 64 ? 64 : 0;
+}
+
 // a8 / as: the activation prepass of mmq.cu (Tpad tokens, nkc operand stages); split_ws: mmq_native_split_bytes() bytes whose
 // counters (mmq_native_split_counters) the caller has cleared on this stream
 cudaError_t launch_mmq_native(int wtype, const uint8_t* a8, const float2* as, const void* wgt, float* C, int32_t* sumi, int T,
                               int F, int K, int Tpad, int64_t ldc_t, int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t st,
-                              const PeerOut* peer, void* split_ws, size_t split_ws_bytes) {
+                              const PeerOut* peer, void* split_ws, size_t split_ws_bytes, int tokn) {
+    if (tokn != 0 && (tokn != mmq_native_tokn(T, peer, sumi != nullptr, flags))) return cudaErrorInvalidValue;
     nat::Params p;
     p.a8 = a8; p.as = as; p.C = C; p.sumi = sumi;
     p.T = T; p.F = F; p.nb = K / 32; p.nkc = K / nat::kKC; p.Tpad = Tpad;
@@ -765,11 +830,11 @@ cudaError_t launch_mmq_native(int wtype, const uint8_t* a8, const float2* as, co
         if (p.peer.mc && reinterpret_cast<uintptr_t>(p.peer.mc) % 16 != 0) p.tma_out = 0;
     }
     switch (wtype) {
-    case QGEMM_TYPE_Q4_0: return nat::launch_t<QGEMM_TYPE_Q4_0>(p, wgt, refseq, num_sms, st);
-    case QGEMM_TYPE_Q4_1: return nat::launch_t<QGEMM_TYPE_Q4_1>(p, wgt, refseq, num_sms, st);
-    case QGEMM_TYPE_Q5_0: return nat::launch_t<QGEMM_TYPE_Q5_0>(p, wgt, refseq, num_sms, st);
-    case QGEMM_TYPE_Q5_1: return nat::launch_t<QGEMM_TYPE_Q5_1>(p, wgt, refseq, num_sms, st);
-    case QGEMM_TYPE_Q8_0: return nat::launch_t<QGEMM_TYPE_Q8_0>(p, wgt, refseq, num_sms, st);
+    case QGEMM_TYPE_Q4_0: return nat::launch_t<QGEMM_TYPE_Q4_0>(p, wgt, refseq, num_sms, st, tokn);
+    case QGEMM_TYPE_Q4_1: return nat::launch_t<QGEMM_TYPE_Q4_1>(p, wgt, refseq, num_sms, st, tokn);
+    case QGEMM_TYPE_Q5_0: return nat::launch_t<QGEMM_TYPE_Q5_0>(p, wgt, refseq, num_sms, st, tokn);
+    case QGEMM_TYPE_Q5_1: return nat::launch_t<QGEMM_TYPE_Q5_1>(p, wgt, refseq, num_sms, st, tokn);
+    case QGEMM_TYPE_Q8_0: return nat::launch_t<QGEMM_TYPE_Q8_0>(p, wgt, refseq, num_sms, st, tokn);
     default: return cudaErrorInvalidValue;
     }
 }

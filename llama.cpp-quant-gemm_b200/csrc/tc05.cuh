@@ -49,6 +49,29 @@ __device__ __forceinline__ void ld32(uint32_t taddr, int (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+// narrower forms of the same load: 32 lanes x 16 / 8 consecutive columns
+__device__ __forceinline__ void ld16(uint32_t taddr, int (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void ld8(uint32_t taddr, int (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+template <int N>
+__device__ __forceinline__ void ldn(uint32_t taddr, int (&v)[N]) {
+    static_assert(N == 8 || N == 16 || N == 32, "tcgen05.ld widths in use");
+    if constexpr (N == 32) ld32(taddr, v);
+    else if constexpr (N == 16) ld16(taddr, v);
+    else ld8(taddr, v);
+}
 // K-major operand tile, 128-byte rows, SWIZZLE_128B, 8-row groups 1024 bytes apart
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)(1024u >> 4) << 32) | ((uint64_t)1 << 46) |
