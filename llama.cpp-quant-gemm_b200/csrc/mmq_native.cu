@@ -183,13 +183,15 @@ __device__ __forceinline__ void unpack_half_row(const uint8_t* raw_half, uint8_t
 // batches): the operands change places -- 128 weight rows on M, kTokN tokens on N -- so the fold, which bounds the kernel,
 // shrinks with the batch instead of being paid for 128 padded tokens; a thread then owns one weight row and kTokN / 4
 // tokens, d_w / m_w are per lane and (d_a, c_a) per column (the prepass writes them pair-wise for that, Params::as).
+constexpr int kSwapUnpackWarps = 2;   // four were measured: no gain (the unpack is 85 % busy with two, but not the limiter)
+constexpr int kSwapThreads = (kEpiWarps + kSwapUnpackWarps + 2) * 32;
 template <int WT, bool kDump, bool kRefSeq, int kTokN = 0>
-__global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p, const __grid_constant__ CUtensorMap wmap) {
+__global__ void __launch_bounds__(kTokN ? kSwapThreads : kThreads, 1) mmq_native_kernel(const Params p, const __grid_constant__ CUtensorMap wmap) {
     // warp roles: 16 epilogue warps, 2 unpack warps in both forms.  (Weight-major with kTokN / 8 epilogue warps of 32 token
     // columns each and 4 unpack warps was measured and is slower -- 32 x 11008 x 4096: 44 vs 34 us: one epilogue warp per
     // sub-partition cannot hide the TMEM-load and barrier latencies.)
     constexpr int kEW = kEpiWarps;
-    constexpr int kUW = kUnpackWarps;
+    constexpr int kUW = kTokN ? kSwapUnpackWarps : kUnpackWarps;
     constexpr int kWU = kEW, kWM = kWU + kUW, kWP = kWM + 1;
     constexpr int kUTl = kUW * 32, kRPT = kBN / kUTl;
     if (kTokN && threadIdx.x >= (kWP + 1) * 32) return;   // launched with exactly (kWP + 1) warps; a guard, not a path
@@ -202,9 +204,15 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);       // [kMaxStages] producer tx + 2 unpack warps
     uint64_t* empty = full + kMaxStages;                      // [kMaxStages] MMA commit + 16 epilogue warps
     uint64_t* rawfull = empty + kMaxStages;                   // [kMaxRaw]    tx of the tensor load
-    uint64_t* tfull = rawfull + kMaxRaw;                      // [2]          MMA commit per TMEM half
-    uint64_t* tempty = tfull + 2;                             // [2]          16 epilogue warps
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    // TMEM slots of two blocks each.  (Four slots in the weight-major form, whose blocks are only kTokN columns wide, were
+    // measured and change nothing: 32 x 11008 x 4096 29.3 us either way -- the operand-stage round trip, not the TMEM
+    // hand-off, is its floor.)
+    constexpr int kSlots = 2;
+    constexpr int kColStep = kTokN ? kTokN : kBN;             // TMEM columns between consecutive block buffers
+    static_assert(2 * kSlots * kColStep <= kTmemCols, "TMEM block buffers");
+    uint64_t* tfull = rawfull + kMaxRaw;                      // [kSlots]     MMA commit per TMEM slot
+    uint64_t* tempty = tfull + 4;                             // [kSlots]     16 epilogue warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 4);
     volatile int* split_info = reinterpret_cast<volatile int*>(tmem_slot + 1);   // [3]: this CTA completes the cut tile; its first / last CTA
     uint8_t* stages = smem + kBarBytes;
     uint8_t* raw_ring = stages + nstages * kStageBytes;
@@ -246,7 +254,7 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
             ptx::mbar_init(&empty[s], 1 + kEW);
         }
         for (int r = 0; r < kMaxRaw; r++) ptx::mbar_init(&rawfull[r], 1);
-        for (int h = 0; h < 2; h++) {
+        for (int h = 0; h < kSlots; h++) {
             ptx::mbar_init(&tfull[h], 1);
             ptx::mbar_init(&tempty[h], kEW);
         }
@@ -293,7 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
         constexpr uint32_t idesc = kTokN == 0 ? (2u << 4) | (1u << 7) | (wfmt << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24)
                                               : (2u << 4) | (wfmt << 7) | (1u << 10) | ((uint32_t)(kTokN >> 3) << 17) | ((uint32_t)(kBN >> 4) << 24);
         int s = 0;
-        uint32_t ph = 0, tph = 0;
+        uint32_t ph = 0, tq = 0;   // tq: TMEM slot uses so far (slot = tq % kSlots, parity = its use count)
         PROF_DECL;
         Cursor cu = cur0;
         int tile, rs0, n, seg;
@@ -305,20 +313,20 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
                 const uint64_t adesc = t5::smem_desc(ptx::smem_u32(stages + s * kStageBytes + (kTokN ? kStageW : kStageA)));
                 const uint64_t bdesc = t5::smem_desc(ptx::smem_u32(stages + s * kStageBytes + (kTokN ? kStageA : kStageW)));
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    PROF_WAIT(pf_wait2, ptx::mbar_wait_guarded(&tempty[h], tph ^ 1));
+                for (int h = 0; h < 2; h++, tq++) {
+                    const uint32_t q = tq % kSlots, qph = (tq / kSlots) & 1u;
+                    PROF_WAIT(pf_wait2, ptx::mbar_wait_guarded(&tempty[q], qph ^ 1));
                     t5::fence_after();
                     if (lane == 0) {
                         // one instruction = one quantization block (32 bytes of K = +2 in the >>4 address field)
-                        t5::mma_i8(tmem_base + (2 * h) * kBN, adesc + 2 * (2 * h), bdesc + 2 * (2 * h), idesc, 0u);
-                        t5::mma_i8(tmem_base + (2 * h + 1) * kBN, adesc + 2 * (2 * h + 1), bdesc + 2 * (2 * h + 1), idesc, 0u);
-                        t5::commit(&tfull[h]);
+                        t5::mma_i8(tmem_base + (2 * q) * kColStep, adesc + 2 * (2 * h), bdesc + 2 * (2 * h), idesc, 0u);
+                        t5::mma_i8(tmem_base + (2 * q + 1) * kColStep, adesc + 2 * (2 * h + 1), bdesc + 2 * (2 * h + 1), idesc, 0u);
+                        t5::commit(&tfull[q]);
                     }
                     __syncwarp();
                 }
                 if (lane == 0) t5::commit(&empty[s]);   // operand tiles consumed once these MMAs retire
                 __syncwarp();
-                tph ^= 1;
                 if (++s == nstages) { s = 0; ph ^= 1; }
             }
         }
@@ -389,7 +397,7 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
         static_assert(kEpiCols == 32 && (NC == 32 || NC == 16 || NC == 8), "one tcgen05.ld per block per thread");
         static_assert(!(kDump && kTokN), "the block-sum dump uses the token-major form");
         int s = 0;
-        uint32_t ph = 0, tph = 0;
+        uint32_t ph = 0, tq = 0;
         PROF_DECL;
         Cursor cu = cur0;
         int tile, rs0, n, seg;
@@ -407,20 +415,21 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
                 PROF_WAIT(pf_wait, ptx::mbar_wait_guarded(&full[s], ph));  // scale slabs of this stage are visible
                 const uint8_t* st = stages + s * kStageBytes;
 #pragma unroll 1
-                for (int h = 0; h < 2; h++) {   // one TMEM half = two blocks per iteration; not unrolled further so that the
-                                                // accumulators keep their registers
-                    PROF_WAIT(pf_wait2, ptx::mbar_wait_guarded(&tfull[h], tph));
+                for (int h = 0; h < 2; h++, tq++) {   // one TMEM slot = two blocks per iteration; not unrolled further so that
+                                                      // the accumulators keep their registers
+                    const uint32_t q = tq % kSlots, qph = (tq / kSlots) & 1u;
+                    PROF_WAIT(pf_wait2, ptx::mbar_wait_guarded(&tfull[q], qph));
                     t5::fence_after();
 #pragma unroll
                     for (int jj = 0; jj < 2; jj++) {
                         const int j = 2 * h + jj;
                         int x[NC];
-                        t5::ldn<NC>(tm + j * kBN, x);
+                        t5::ldn<NC>(tm + (2 * q + jj) * kColStep, x);
                         t5::wait_ld();
-                        if (jj == 1) {   // both blocks of this half are in registers: hand the half back to the tensor core
+                        if (jj == 1) {   // both blocks of this slot are in registers: hand it back to the tensor core
                             t5::fence_before();
                             __syncwarp();
-                            if (lane == 0) ptx::mbar_arrive(&tempty[h]);
+                            if (lane == 0) ptx::mbar_arrive(&tempty[q]);
                         }
                         if constexpr (kDump) {
                             const int t = mt * kBM + row, b = kc * kBPS + j;
@@ -464,7 +473,6 @@ __global__ void __launch_bounds__(kThreads, 1) mmq_native_kernel(const Params p,
                 }
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&empty[s]);  // scale slabs consumed
-                tph ^= 1;
                 if (++s == nstages) { s = 0; ph ^= 1; }
             }
             if constexpr (!kDump) {
@@ -716,7 +724,7 @@ static cudaError_t launch_t(Params p, const void* wgt, bool refseq, int num_sms,
     if (cudaError_t e = smem_optin(reinterpret_cast<const void*>(kfn), smem)) return e;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(max(min(p.nfull, num_sms), p.sk_ctas));
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(tokn ? kSwapThreads : kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute at[1];

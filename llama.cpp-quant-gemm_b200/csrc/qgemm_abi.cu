@@ -51,14 +51,15 @@ constexpr int kMmaMinTokens = 2;   // dp4a GEMV for a single token, mma.sync ski
 constexpr int kMmqMinTokens = 96;  // AUTO always takes the tcgen05 path from here on (a call without scratch is refused)
 
 // Below kMmqMinTokens AUTO takes the tcgen05 path only when scratch is at hand, from the measured crossover against the
-// mma.sync passes (profiles/r02_small_batch_crossover.md; the tcgen05 call costs the same for any T <= 128): T = 64 at
-// 4096 x 4096 28.0 -> 25.5 us, T = 64 at 11008 x 4096 49.6 -> 47 us; rows of other lengths than 4096 / 8192 have no wide
-// mma.sync variant and cross over at T = 24 (4096 x 11008: T = 32 61 -> 46 us, T = 95 183 -> 46 us).
+// mma.sync passes (profiles/r02_small_batch_crossover.md).  Up to 64 tokens the kernel runs weight-major (tokens on the N
+// side of the MMA, mmq_native.cu), so its time shrinks with the batch: 11008 x 4096 T = 48 40.4 -> 38.4 us, T = 64
+// 49.6 -> 39.3 us; 4096 x 4096 T = 64 28.0 -> 24.8 us.  Rows of other lengths than 4096 / 8192 have no wide mma.sync
+// variant and cross over at T = 16 (4096 x 11008: T = 16 31.9 -> 29.1 us, T = 32 61 -> 30 us, T = 95 183 -> 46 us).
 bool mmq_native_supported(int wtype, const void* wgt, int T, int F, int K);
 static int mmq_min_tokens(int wtype, const void* wgt, int T, int F, int K) {
     if (!mmq_native_supported(wtype, wgt, T, F, K)) return kMmqMinTokens;
     (void)F;
-    return (K == 4096 || K == 8192) ? 64 : 24;
+    return (K == 4096 || K == 8192) ? 48 : 16;
 }
 
 static std::atomic<int64_t> g_launches{0};

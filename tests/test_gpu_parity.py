@@ -298,7 +298,9 @@ def test_full_size_decode_properties(qg, O):
 # ------------------------------------------------------------------------------------------
 PATHS["tcgen05"] = 0x400
 FOLD_REFSEQ = 0x1000   # QGEMM_FOLD_REFSEQ
-MMQ_SHAPES = [(128, 128, 128), (64, 256, 4096), (200, 300, 1056), (130, 129, 32), (512, 384, 2048)]
+MMQ_SHAPES = [(128, 128, 128), (64, 256, 4096), (200, 300, 1056), (130, 129, 32), (512, 384, 2048),
+              # small batches on the native kernel run weight-major (tokens on the N side of the MMA: 32 or 64 columns)
+              (17, 200, 1024), (32, 129, 512), (48, 384, 2048), (9, 130, 256), (33, 1000, 4096)]
 
 
 @pytest.mark.parametrize("wt", qo.WEIGHT_TYPES)
@@ -628,9 +630,9 @@ def test_mma_wide_small_batch_vs_oracle(qg, O, wt, T, F, K):
     assert qg.last_path() == 0x300
     check_c(c, O.gemm(wt, aq, wq, layout="FT"), f"mma wide {qo.TYPE_NAMES[wt]} {T}x{F}x{K}")
     c_auto = run_gemm(qg, wt, aq, wq, "auto")
-    if T < 64:
+    if T < 48:
         assert qg.last_path() == 0x300 and (bits(c_auto) == bits(c)).all()
-    else:   # with scratch at hand AUTO takes the tcgen05 path from the measured crossover (T = 64 for these shapes)
+    else:   # with scratch at hand AUTO takes the tcgen05 path from the measured crossover (T = 48 for these shapes)
         assert qg.last_path() == 0x400
         check_c(c_auto, O.gemm(wt, aq, wq, layout="FT"), f"auto small batch {qo.TYPE_NAMES[wt]} {T}x{F}x{K}")
     # include/ convention (C[T,F]) through the same kernel
@@ -651,7 +653,7 @@ def test_mma_skinny_fuzz_and_auto(qg, O, wt):
     for fl in (0, qo.GEMM_MS_EXACT):
         check_c(run_gemm(qg, wt, aq, wq, "mma", flags=fl), O.gemm(wt, aq, wq, layout="FT", flags=fl), "mma fuzz")
     run_gemm(qg, wt, aq, wq, "auto")
-    assert qg.last_path() == 0x300        # AUTO: dp4a GEMV for T = 1, mma.sync from 2, tcgen05 from 24 .. 96 (shape dependent)
+    assert qg.last_path() == 0x300        # AUTO: dp4a GEMV for T = 1, mma.sync from 2, tcgen05 from 16 .. 96 (shape dependent)
     run_gemm(qg, wt, aq[:1], wq, "auto")
     assert qg.last_path() == 0x200
 
