@@ -120,6 +120,15 @@ QGEMM_API const char *qgemm_last_error_detail(void);
 QGEMM_API int qgemm_quantize_q8_1(const float *x, void *y, int64_t rows, int64_t K, uint32_t flags, void *stream);
 
 /*
+ * y = quantize_q8_1(silu(x) * gate): the SwiGLU neighbour of the FFN down projection folded into its quantizer
+ * (SURVEY 8 f.3).  Replaces silu_mul_forward_f32() (kernels/activation/silu.cuh:97-108, 162-175: y = x / (1 + expf(-x))
+ * * gate, same operation sequence, bit-identical intermediate values on the GPU) followed by quantize_q8_1_cuda();
+ * x, gate: [rows][K] fp32; flags as for qgemm_quantize_q8_1.  One pass: 9.1 instead of 17.1 bytes per element.
+ */
+QGEMM_API int qgemm_quantize_q8_1_silu_mul(const float *x, const float *gate, void *y, int64_t rows, int64_t K, uint32_t flags,
+                                           void *stream);
+
+/*
  * Weight quantizers (test-data producers): x[rows][K] fp32 -> y[rows][K/32] blocks.
  * q4_0/q8_0 replace quantize_q4_0_cuda()/quantize_q8_0_cuda()
  * (include/quantize.h:343-359) and python quantize_q4_0 (gemm_ops.cu:146-173);

@@ -41,6 +41,7 @@ cudaError_t launch_gemm_f32act_sequential(int wtype, const float* act, const voi
 bool mmq_supported(int wtype, const void* act, const void* wgt, int T, int F, int K);
 size_t mmq_workspace_bytes(int wtype, int T, int F, int K);
 size_t mmq_workspace_need(int wtype, const void* wgt, int T, int F, int K, uint32_t flags);
+cudaError_t launch_quantize_q8_1_silu_mul(const float* x, const float* gate, void* y, int64_t nblocks, uint32_t flags, cudaStream_t st);
 cudaError_t launch_mmq_f32act(int wtype, const float* act_f32, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
                               int64_t ldc_f, uint32_t flags, uint32_t qflags, void* ws, size_t ws_bytes, int num_sms, cudaStream_t st);
 cudaError_t launch_mmq(int wtype, const void* act, const void* wgt, float* C, int32_t* sumi_out, int T, int F, int K,
@@ -288,6 +289,17 @@ int64_t qgemm_launch_count(void) { return g_launches.load(std::memory_order_rela
 void qgemm_reset_launch_count(void) { g_launches.store(0, std::memory_order_relaxed); }
 uint32_t qgemm_last_path(void) { return t_last_path; }
 const char* qgemm_last_error_detail(void) { return t_detail; }
+
+int qgemm_quantize_q8_1_silu_mul(const float* x, const float* gate, void* y, int64_t rows, int64_t K, uint32_t flags, void* stream) {
+    if (rows < 0 || K < 0 || (K % kQK) != 0) return QGEMM_E_BADARG;
+    if (rows == 0 || K == 0) return QGEMM_OK;
+    if (!x || !gate || !y) return QGEMM_E_BADARG;
+    if (!aligned(x, 4) || !aligned(gate, 4) || !aligned(y, 4)) return QGEMM_E_ALIGN;
+    DeviceInfo dev;
+    if (int rc = device_check(&dev)) return rc;
+    const cudaError_t e = launch_quantize_q8_1_silu_mul(x, gate, y, rows * (K / kQK), flags, (cudaStream_t)stream);
+    return e == cudaSuccess ? QGEMM_OK : cuda_fail(e, "quantize_q8_1_silu_mul launch");
+}
 
 int qgemm_quantize_q8_1(const float* x, void* y, int64_t rows, int64_t K, uint32_t flags, void* stream) {
     if (rows < 0 || K < 0 || (K % kQK) != 0) return QGEMM_E_BADARG;

@@ -38,9 +38,13 @@ struct Q81Tiles {
     float coef;
     unsigned* zero;    // split-K arrival counters of the GEMM behind this kernel: cleared here
     int nzero;
+    const float* gate; // kSiluMul: the second operand of silu(x) * gate
 };
 
-template <bool kAlignedX, bool kTiles>
+// kSiluMul: the value that is quantized is silu(x) * gate, computed with the operation sequence of the reference's
+// silu_mul_f32_kernel (kernels/activation/silu.cuh:97-108): val / (1.0f + expf(-val)), then times gate -- the SwiGLU
+// neighbour of the FFN down projection folded into its quantizer, 9.1 instead of 17.1 bytes per element.
+template <bool kAlignedX, bool kTiles, bool kSiluMul = false>
 __global__ void __launch_bounds__(kQWarps * 32)
 quantize_q8_1_kernel(const float* __restrict__ x, uint32_t* __restrict__ y, int64_t nblocks, uint32_t flags, const Q81Tiles tl) {
     __shared__ float tile[kQWarps][32][33];
@@ -68,6 +72,19 @@ quantize_q8_1_kernel(const float* __restrict__ x, uint32_t* __restrict__ y, int6
                 v = __ldcs(reinterpret_cast<const float4*>(xb) + v4);
             } else {
                 v.x = xb[v4 * 4 + 0]; v.y = xb[v4 * 4 + 1]; v.z = xb[v4 * 4 + 2]; v.w = xb[v4 * 4 + 3];
+            }
+            if constexpr (kSiluMul) {
+                const float* gb = tl.gate + b0 * 32;
+                float4 g;
+                if constexpr (kAlignedX) {
+                    g = __ldcs(reinterpret_cast<const float4*>(gb) + v4);
+                } else {
+                    g.x = gb[v4 * 4 + 0]; g.y = gb[v4 * 4 + 1]; g.z = gb[v4 * 4 + 2]; g.w = gb[v4 * 4 + 3];
+                }
+                v.x = __fmul_rn(__fdiv_rn(v.x, __fadd_rn(1.0f, expf(-v.x))), g.x);
+                v.y = __fmul_rn(__fdiv_rn(v.y, __fadd_rn(1.0f, expf(-v.y))), g.y);
+                v.z = __fmul_rn(__fdiv_rn(v.z, __fadd_rn(1.0f, expf(-v.z))), g.z);
+                v.w = __fmul_rn(__fdiv_rn(v.w, __fadd_rn(1.0f, expf(-v.w))), g.w);
             }
         }
         tw[blk][j + 0] = v.x; tw[blk][j + 1] = v.y; tw[blk][j + 2] = v.z; tw[blk][j + 3] = v.w;
@@ -141,6 +158,20 @@ cudaError_t launch_quantize_q8_1(const float* x, void* y, int64_t nblocks, uint3
     return cudaGetLastError();
 }
 
+cudaError_t launch_quantize_q8_1_silu_mul(const float* x, const float* gate, void* y, int64_t nblocks, uint32_t flags, cudaStream_t st) {
+    if (nblocks == 0) return cudaSuccess;
+    const int64_t per_cta = (int64_t)kQWarps * 32;
+    const unsigned grid = (unsigned)((nblocks + per_cta - 1) / per_cta);
+    Q81Tiles tl{};
+    tl.gate = gate;
+    if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gate)) & 15) == 0)
+        quantize_q8_1_kernel<true, false, true><<<grid, kQWarps * 32, 0, st>>>(x, (uint32_t*)y, nblocks, flags, tl);
+    else
+        quantize_q8_1_kernel<false, false, true><<<grid, kQWarps * 32, 0, st>>>(x, (uint32_t*)y, nblocks, flags, tl);
+    note_launch();
+    return cudaGetLastError();
+}
+
 // fp32 x[T][K] -> operand tiles + slabs for the tensor-core kernels (K % 128 == 0).  The source has T rows; the tiles
 // have Tpad: the kernel runs over Tpad * nb blocks and reads zeros past row T.
 __global__ void zero_pad_rows_kernel(uint8_t* a8, float2* as, int T, int Tpad, int nb) {
@@ -168,7 +199,7 @@ cudaError_t launch_quantize_q8_1_tiles(const float* x, uint8_t* a8, float2* as, 
     const int64_t nblocks = (int64_t)T * nb;
     const int64_t per_cta = (int64_t)kQWarps * 32;
     const unsigned grid = (unsigned)((nblocks + per_cta - 1) / per_cta);
-    const Q81Tiles tl{a8, as, T, Tpad, nb, coef, zero, nzero};
+    const Q81Tiles tl{a8, as, T, Tpad, nb, coef, zero, nzero, nullptr};
     if ((reinterpret_cast<uintptr_t>(x) & 15) == 0)
         quantize_q8_1_kernel<true, true><<<grid, kQWarps * 32, 0, st>>>(x, nullptr, nblocks, flags, tl);
     else

@@ -94,6 +94,23 @@ def quantize_q8_1(x: torch.Tensor, flags: int = Q81_ROUND_AWAY) -> torch.Tensor:
     return _quantize(x, TYPE_Q8_1, flags)
 
 
+def quantize_q8_1_silu_mul(x: torch.Tensor, gate: torch.Tensor, flags: int = Q81_ROUND_AWAY) -> torch.Tensor:
+    """quantize_q8_1(silu(x) * gate) in one pass: the reference's silu_mul_forward_f32 (kernels/activation/silu.cuh:97-108,
+    162-175) folded into the quantizer that feeds the FFN down projection.  x, gate: FP32 [..., K] -> Q8_1 [..., K//32, 36]."""
+    _check(x.is_cuda and gate.is_cuda, "Inputs must be CUDA tensors")
+    _check(x.dtype == torch.float32 and gate.dtype == torch.float32, "Inputs must be float32")
+    _check(x.shape == gate.shape and x.dim() >= 1, "x and gate must have the same shape")
+    K = x.shape[-1]
+    _check(K % 32 == 0, f"Last dimension must be divisible by 32, got {K}")
+    x, gate = x.contiguous(), gate.contiguous()
+    rows = x.numel() // K if K else 0
+    out = torch.empty(*x.shape[:-1], K // 32, BLOCK_BYTES[TYPE_Q8_1], dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().qgemm_quantize_q8_1_silu_mul(x.data_ptr(), gate.data_ptr(), out.data_ptr(), rows, K, flags, _stream(x))
+    _lib.raise_on_error(rc, "quantize_q8_1_silu_mul")
+    return out
+
+
 def quantize_q4_1(x, flags: int = 0):
     return _quantize(x, TYPE_Q4_1, flags)
 
@@ -334,5 +351,6 @@ __all__ = [
     # supersets
     "quantize_q4_1", "quantize_q5_0", "quantize_q5_1", "quantize_q8_0", "dequantize",
     "gemm", "gemm_q4_1_q8_1", "gemm_q5_0_q8_1", "gemm_q5_1_q8_1", "gemm_q8_0_q8_1", "gemm_w4a8",
+    "gemm_a16", "gemm_q4_0_fp32", "quantize_q8_1_silu_mul",
     "gemm_group", "prepack_weights", "block_sumi", "launch_count", "reset_launch_count", "last_path", "hint_next_weights",
 ]

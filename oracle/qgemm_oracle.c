@@ -119,6 +119,19 @@ static void st32(uint8_t *p, uint32_t v)
  * __float2int_rn semantics (include/quantize.h:335). */
 static int rn_even(float v) { return (int)nearbyintf(v); /* default FE_TONEAREST */ }
 
+/* silu(x) * gate, element by element, in the operation order of silu_mul_f32_kernel (kernels/activation/silu.cuh:97-108;
+ * CPU form of the silu part: silu_cpu_f32, silu.cuh:23-27): val / (1.0f + expf(-val)), then times gate.  expf is libm's
+ * here and CUDA's on the device: both are faithful to well under one unit in the last place of the result, they are not
+ * guaranteed to agree in the last bit, so tests compare the quantized bytes with a one-step allowance. */
+void qo_silu_mul(const float *x, const float *gate, float *y, int64_t n)
+{
+    for (int64_t i = 0; i < n; i++) {
+        const float val = x[i];
+        const float silu = val / (1.0f + expf(-val));
+        y[i] = silu * gate[i];
+    }
+}
+
 void qo_quantize_q8_1(const float *x, void *y, int64_t n, unsigned flags)
 {
     /* include/quantize.h:165-193 (CPU), :302-337 (GPU kernel),

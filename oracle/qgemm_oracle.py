@@ -72,6 +72,7 @@ class Oracle:
         L.qo_fp16_to_fp32.restype = _f
         L.qo_fp16_to_fp32.argtypes = [C.c_uint16]
         L.qo_quantize_q8_1.argtypes = [_p, _p, _i64, _u]
+        L.qo_silu_mul.argtypes = [_p, _p, _p, _i64]
         for n in ("qo_quantize_q4_0_ref", "qo_quantize_q8_0_ref", "qo_to_q4_0", "qo_to_q4_1",
                   "qo_to_q5_0", "qo_to_q5_1", "qo_to_q8_0"):
             getattr(L, n).argtypes = [_p, _p, _i64]
@@ -101,6 +102,15 @@ class Oracle:
 
     def quantize_q8_1(self, x, flags: int = Q81_ROUND_AWAY):
         return self._quant(self.lib.qo_quantize_q8_1, x, 36, flags)
+
+    def silu_mul(self, x, gate) -> np.ndarray:
+        """silu(x) * gate in fp32, operation order of kernels/activation/silu.cuh:97-108."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        gate = np.ascontiguousarray(gate, dtype=np.float32)
+        assert x.shape == gate.shape
+        out = np.empty_like(x)
+        self.lib.qo_silu_mul(_ptr(x), _ptr(gate), _ptr(out), x.size)
+        return out
 
     def quantize_weight(self, wtype: int, x, flavour: str = "framework"):
         """flavour 'include' = include/quantize.h (q4_0/q8_0 only), 'framework' = tests/framework."""
@@ -212,6 +222,9 @@ class Reference:
         for n in ("ref_gpu_gemm_w4a16_naive", "ref_gpu_gemm_w8a16_naive"):
             if hasattr(L, n):
                 getattr(L, n).argtypes = [_p, _p, _p, _i, _i, _i, _p]
+        if hasattr(L, "ref_gpu_silu_mul_f32"):   # kernels/activation/silu.cuh (added with the fused SwiGLU quantizer)
+            L.ref_gpu_silu_mul_f32.argtypes = [_p, _p, _p, _i, _p]
+            L.ref_cpu_silu_f32.argtypes = [_p, _p, _i]
         L.ref_vec_dot_q4_0_q8_1.restype = _f
         L.ref_vec_dot_q4_0_q8_1.argtypes = [_i, _p, _p]
         L.ref_vec_dot_q8_0_q8_1.restype = _f

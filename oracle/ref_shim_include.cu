@@ -16,6 +16,7 @@
 #include "gemm_reference.h"
 #include "gemm_cuda_naive.cuh"
 #include "gemm_cuda_dp4a.cuh"
+#include "kernels/activation/silu.cuh"
 
 extern "C" {
 
@@ -63,6 +64,10 @@ void ref_gpu_gemm_w4a16_naive(const float* A, const void* B, float* C, int M, in
 void ref_gpu_gemm_w8a16_naive(const float* A, const void* B, float* C, int M, int N, int K, void* stream) {
     gemm_w8a16_naive(A, (const block_q8_0*)B, C, M, N, K, (cudaStream_t)stream);
 }
+void ref_gpu_silu_mul_f32(const float* x, const float* gate, float* y, int n, void* stream) {
+    silu_mul_forward_f32(x, gate, y, n, (cudaStream_t)stream);
+}
+void ref_cpu_silu_f32(const float* x, float* y, int n) { silu_cpu_f32(x, y, n); }
 void ref_gpu_gemm_w4a8_tiled_dp4a(const void* A, const void* B, float* C, int M, int N, int K, void* stream) {
     gemm_w4a8_tiled_dp4a((const block_q8_1*)A, (const block_q4_0*)B, C, M, N, K, (cudaStream_t)stream);
 }

@@ -93,6 +93,41 @@ def test_quantize_q8_1_unaligned_and_empty(qg, O):
     assert qg.quantize_q8_1(torch.zeros((0, 64), device="cuda")).shape == (0, 2, 36)
 
 
+@pytest.mark.parametrize("shape", [(3, 256), (1, 11008), (130, 4096), (2, 5, 64)])
+def test_quantize_q8_1_silu_mul_fused(qg, O, shape):
+    """quantize_q8_1(silu(x) * gate) in one pass.  Against the oracle (libm expf on the host, CUDA expf on
+    the device: the fp32 products may differ in the last bit, so a quantized value may differ by one step and d / s by one
+    fp16 unit in a few blocks); and bit for bit against the reference's own silu_mul_forward_f32 run on this GPU followed
+    by the plain quantizer, when oracle/_ref is present."""
+    rng = np.random.default_rng(sum(shape))
+    x = (rng.standard_normal(shape) * 3).astype(np.float32)
+    g = rng.standard_normal(shape).astype(np.float32)
+    x.reshape(-1)[:32] = 0.0
+    got = host(qg.quantize_q8_1_silu_mul(dev(x), dev(g)))
+    want = O.quantize_q8_1(O.silu_mul(x, g))
+    assert got.shape == want.shape
+    gq, wq_ = got[..., 4:].view(np.int8).astype(np.int32), want[..., 4:].view(np.int8).astype(np.int32)
+    assert np.abs(gq - wq_).max() <= 1 and (gq != wq_).mean() < 2e-3
+    gd, wd = got[..., :4].copy().view(np.float16).astype(np.float32), want[..., :4].copy().view(np.float16).astype(np.float32)
+    assert np.allclose(gd, wd, rtol=2e-3, atol=1e-6)
+    # dequantized values agree with the fp32 product to within the quantization step
+    y = O.silu_mul(x, g).reshape(-1, 32)
+    deq = (gq.reshape(-1, 32) * gd.reshape(-1, 2)[:, :1])
+    assert np.abs(deq - y).max() <= 0.51 * np.abs(y).max(axis=1, keepdims=True).max() / 127 + 1e-6
+    if qo.have_ref():
+        R = qo.Reference()
+        fn = getattr(R.lib, "ref_gpu_silu_mul_f32", None)
+        if fn is not None:
+            dx, dg = dev(x), dev(g)
+            y_ref = torch.empty_like(dx)
+            torch.cuda.synchronize()
+            fn(dx.data_ptr(), dg.data_ptr(), y_ref.data_ptr(), dx.numel(), None)
+            torch.cuda.synchronize()
+            assert (host(qg.quantize_q8_1(y_ref)) == got).all()
+    with pytest.raises(RuntimeError):
+        qg.quantize_q8_1_silu_mul(dev(x), dev(g[..., :32]))
+
+
 @pytest.mark.parametrize("wt", qo.WEIGHT_TYPES)
 def test_weight_quantizers_and_dequantize(qg, O, wt):
     _, w = datagen.model_like(1, 9, 512, seed=wt)
