@@ -228,6 +228,16 @@ QGEMM_API int qgemm_gemm_f32act(int wtype, const float *act_f32, const void *wei
                       size_t workspace_bytes, void *stream);
 
 /*
+ * The FFN down projection with its SwiGLU neighbour: C = W . quantize_q8_1(silu(x) * gate).  Same contract as
+ * qgemm_gemm_f32act (workspace, flags, two launches at tensor-core sizes); x, gate: [T][K] fp32.  Replaces
+ * silu_mul_forward_f32 (kernels/activation/silu.cuh:162-175) + quantize_q8_1_cuda + gemm_*: bit-equal to
+ * qgemm_quantize_q8_1_silu_mul followed by qgemm_gemm.
+ */
+QGEMM_API int qgemm_gemm_f32act_silu_mul(int wtype, const float *x, const float *gate, const void *weight, float *C, int T, int F,
+                                         int K, int64_t ldc_t, int64_t ldc_f, uint32_t flags, void *workspace,
+                                         size_t workspace_bytes, void *stream);
+
+/*
  * W4A16 / W8A16: fp32 activations act_f32[T][K] against Q4_0 / Q8_0 weights with NO activation quantization,
  *     C[t*ldc_t + f*ldc_f] = sum_k act[t][k] * d_w * (q_w - 8)        (q8_0: d_w * q_w)
  * every product and sum in fp32.  Replaces gemm_w4a16_naive / gemm_w8a16_naive (include/gemm_cuda_naive.cuh:66-143,

@@ -574,13 +574,14 @@ static cudaError_t launch_mmq_t(const void* act, const void* wgt, float* C, int3
 }
 
 cudaError_t launch_quantize_q8_1_tiles(const float* x, uint8_t* a8, float2* as, int T, int Tpad, int K, float coef, uint32_t flags,
-                                       cudaStream_t st, unsigned* zero, int nzero);
+                                       cudaStream_t st, unsigned* zero, int nzero, const float* gate);
 
 // fp32 activations straight into the tensor-core path: quantize_q8_1 writes the operand tiles itself, then the
 // native-layout GEMM -- two launches, no block_q8_1 round trip (successor of kernels/gemm/gemm_fused.cuh:76-302).
 // Returns cudaErrorNotSupported where that pairing does not apply (the caller then chains the separate kernels).
 cudaError_t launch_mmq_f32act(int wtype, const float* act_f32, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
-                              int64_t ldc_f, uint32_t flags, uint32_t qflags, void* ws, size_t ws_bytes, int num_sms, cudaStream_t st) {
+                              int64_t ldc_f, uint32_t flags, uint32_t qflags, void* ws, size_t ws_bytes, int num_sms, cudaStream_t st,
+                              const float* gate) {
     if ((flags & QGEMM_WEIGHTS_PREPACKED) || K % 128 != 0 || !mmq_native_supported(wtype, wgt, T, F, K) || QGEMM_ENV("QGEMM_MMQ_LEGACY") ||
         QGEMM_ENV("QGEMM_NO_FUSED_QUANT"))
         return cudaErrorNotSupported;
@@ -594,7 +595,7 @@ cudaError_t launch_mmq_f32act(int wtype, const float* act_f32, const void* wgt, 
     int ncount = 0;
     unsigned* counters = mmq_native_split_counters(T, F, K, flags, num_sms, ws_bytes > L.w8 ? base + L.w8 : nullptr,
                                                    ws_bytes > L.w8 ? ws_bytes - L.w8 : 0, false, nullptr, &ncount);
-    if (cudaError_t e = launch_quantize_q8_1_tiles(act_f32, base + L.a8, (float2*)(base + L.as), T, L.Tpad, K, coef, qflags, st, counters, ncount))
+    if (cudaError_t e = launch_quantize_q8_1_tiles(act_f32, base + L.a8, (float2*)(base + L.as), T, L.Tpad, K, coef, qflags, st, counters, ncount, gate))
         return e;
     return launch_mmq_native(wtype, base + L.a8, (const float2*)(base + L.as), wgt, C, nullptr, T, F, K, L.Tpad, ldc_t, ldc_f, flags, num_sms,
                              st, nullptr, ws_bytes > L.w8 ? base + L.w8 : nullptr, ws_bytes > L.w8 ? ws_bytes - L.w8 : 0);

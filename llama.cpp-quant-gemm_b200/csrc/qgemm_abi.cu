@@ -43,7 +43,7 @@ size_t mmq_workspace_bytes(int wtype, int T, int F, int K);
 size_t mmq_workspace_need(int wtype, const void* wgt, int T, int F, int K, uint32_t flags);
 cudaError_t launch_quantize_q8_1_silu_mul(const float* x, const float* gate, void* y, int64_t nblocks, uint32_t flags, cudaStream_t st);
 cudaError_t launch_mmq_f32act(int wtype, const float* act_f32, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
-                              int64_t ldc_f, uint32_t flags, uint32_t qflags, void* ws, size_t ws_bytes, int num_sms, cudaStream_t st);
+                              int64_t ldc_f, uint32_t flags, uint32_t qflags, void* ws, size_t ws_bytes, int num_sms, cudaStream_t st, const float* gate = nullptr);
 cudaError_t launch_mmq(int wtype, const void* act, const void* wgt, float* C, int32_t* sumi_out, int T, int F, int K,
                        int64_t ldc_t, int64_t ldc_f, uint32_t flags, void* ws, size_t ws_bytes, int num_sms,
                        cudaStream_t, const PeerOut* peer = nullptr);
@@ -418,9 +418,24 @@ int qgemm_gemm(int wtype, const void* act_q8_1, const void* weight, float* C, in
                     (cudaStream_t)stream, dev);
 }
 
+static int gemm_f32act_impl(int wtype, const float* act_f32, const float* gate, const void* weight, float* C, int T, int F, int K,
+                           int64_t ldc_t, int64_t ldc_f, uint32_t flags, void* workspace, size_t workspace_bytes, void* stream);
+
 int qgemm_gemm_f32act(int wtype, const float* act_f32, const void* weight, float* C, int T, int F, int K,
                       int64_t ldc_t, int64_t ldc_f, uint32_t flags, void* workspace, size_t workspace_bytes,
                       void* stream) {
+    return gemm_f32act_impl(wtype, act_f32, nullptr, weight, C, T, F, K, ldc_t, ldc_f, flags, workspace, workspace_bytes, stream);
+}
+
+int qgemm_gemm_f32act_silu_mul(int wtype, const float* x, const float* gate, const void* weight, float* C, int T, int F, int K,
+                               int64_t ldc_t, int64_t ldc_f, uint32_t flags, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+    if (T > 0 && K > 0 && (!gate || !aligned(gate, 4))) return gate ? QGEMM_E_ALIGN : QGEMM_E_BADARG;
+    return gemm_f32act_impl(wtype, x, gate, weight, C, T, F, K, ldc_t, ldc_f, flags, workspace, workspace_bytes, stream);
+}
+
+static int gemm_f32act_impl(int wtype, const float* act_f32, const float* gate, const void* weight, float* C, int T, int F, int K,
+                           int64_t ldc_t, int64_t ldc_f, uint32_t flags, void* workspace, size_t workspace_bytes, void* stream) {
     if (int rc = check_gemm_args(wtype, act_f32, weight, C, T, F, K)) return rc;
     if (T == 0 || F == 0) return QGEMM_OK;
     DeviceInfo dev;
@@ -433,7 +448,7 @@ int qgemm_gemm_f32act(int wtype, const float* act_f32, const void* weight, float
         const bool tc = !(gflags & QGEMM_SEQUENTIAL) && (path == QGEMM_PATH_TCGEN05 || (path == QGEMM_PATH_AUTO && T >= mmq_min_tokens(wtype, weight, T, F, K)));
         if (tc && K > 0 && workspace_bytes > a_q) {
             const cudaError_t e = launch_mmq_f32act(wtype, act_f32, weight, C, T, F, K, ldc_t, ldc_f, gflags, (flags >> 16) & 0xffu,
-                                                    (char*)workspace + a_q, workspace_bytes - a_q, dev.sms, st);
+                                                    (char*)workspace + a_q, workspace_bytes - a_q, dev.sms, st, gate);
             if (e == cudaSuccess) {
                 t_last_path = QGEMM_PATH_TCGEN05;
                 return QGEMM_OK;
@@ -441,9 +456,11 @@ int qgemm_gemm_f32act(int wtype, const float* act_f32, const void* weight, float
             if (e != cudaErrorNotSupported) return cuda_fail(e, "gemm_f32act launch");
         }
     }
-    if (K > 0 &&
-        launch_quantize_q8_1(act_f32, workspace, (int64_t)T * (K / kQK), (flags >> 16) & 0xffu, st) != cudaSuccess)
-        return QGEMM_E_CUDA;
+    if (K > 0) {
+        const cudaError_t e = gate ? launch_quantize_q8_1_silu_mul(act_f32, gate, workspace, (int64_t)T * (K / kQK), (flags >> 16) & 0xffu, st)
+                                   : launch_quantize_q8_1(act_f32, workspace, (int64_t)T * (K / kQK), (flags >> 16) & 0xffu, st);
+        if (e != cudaSuccess) return cuda_fail(e, "gemm_f32act quantize launch");
+    }
     return run_gemm(wtype, workspace, weight, C, T, F, K, ldc_t, ldc_f, flags & 0xffffu, (char*)workspace + a_q,
                     workspace_bytes - a_q, st, dev);
 }

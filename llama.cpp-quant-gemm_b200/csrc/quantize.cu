@@ -188,7 +188,7 @@ __global__ void zero_pad_rows_kernel(uint8_t* a8, float2* as, int T, int Tpad, i
 }
 
 cudaError_t launch_quantize_q8_1_tiles(const float* x, uint8_t* a8, float2* as, int T, int Tpad, int K, float coef, uint32_t flags,
-                                       cudaStream_t st, unsigned* zero, int nzero) {
+                                       cudaStream_t st, unsigned* zero, int nzero, const float* gate) {
     const int nb = K / 32;
     if (T < 1 || nb < 4 || (nb & 3)) return cudaErrorInvalidValue;
     if (Tpad > T) {   // at most 127 rows: a sliver in front of the main pass (same stream, so ordered before the GEMM)
@@ -199,11 +199,16 @@ cudaError_t launch_quantize_q8_1_tiles(const float* x, uint8_t* a8, float2* as, 
     const int64_t nblocks = (int64_t)T * nb;
     const int64_t per_cta = (int64_t)kQWarps * 32;
     const unsigned grid = (unsigned)((nblocks + per_cta - 1) / per_cta);
-    const Q81Tiles tl{a8, as, T, Tpad, nb, coef, zero, nzero, nullptr};
-    if ((reinterpret_cast<uintptr_t>(x) & 15) == 0)
+    const Q81Tiles tl{a8, as, T, Tpad, nb, coef, zero, nzero, gate};
+    const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gate)) & 15) == 0;
+    if (gate) {   // silu(x) * gate is what gets quantized (the FFN down projection's input)
+        if (al) quantize_q8_1_kernel<true, true, true><<<grid, kQWarps * 32, 0, st>>>(x, nullptr, nblocks, flags, tl);
+        else quantize_q8_1_kernel<false, true, true><<<grid, kQWarps * 32, 0, st>>>(x, nullptr, nblocks, flags, tl);
+    } else if (al) {
         quantize_q8_1_kernel<true, true><<<grid, kQWarps * 32, 0, st>>>(x, nullptr, nblocks, flags, tl);
-    else
+    } else {
         quantize_q8_1_kernel<false, true><<<grid, kQWarps * 32, 0, st>>>(x, nullptr, nblocks, flags, tl);
+    }
     note_launch();
     return cudaGetLastError();
 }

@@ -260,11 +260,14 @@ def gemm_q8_0_q8_1(weight_q, activation_q, M, N, K, flags: int = 0):
 
 
 def gemm_w4a8(weight_q: torch.Tensor, activation: torch.Tensor, M: int, N: int, K: int,
-              wtype: int = TYPE_Q4_0, flags: int = 0, q81_flags: int = Q81_ROUND_AWAY) -> torch.Tensor:
+              wtype: int = TYPE_Q4_0, flags: int = 0, q81_flags: int = Q81_ROUND_AWAY,
+              gate: torch.Tensor | None = None) -> torch.Tensor:
     """One call: quantize_q8_1(activation fp32 [N,K]) then the GEMM -> [M, N].
 
     The reference designs this entry (docs/analysis/W4A8_DATAFLOW_ANALYSIS.md:93-160)
     but never wrote it; its FP16 precursor is kernels/gemm/gemm_fused.cuh:311-338.
+    With `gate` (same shape as `activation`) what is quantized is silu(activation) * gate: the FFN down projection
+    with its SwiGLU neighbour (kernels/activation/silu.cuh:97-108) folded in.
     """
     _check(weight_q.is_cuda and activation.is_cuda, "Inputs must be CUDA tensors")
     _check(weight_q.dtype == torch.uint8, "Weight must be uint8")
@@ -275,15 +278,20 @@ def gemm_w4a8(weight_q: torch.Tensor, activation: torch.Tensor, M: int, N: int, 
     _check(activation.numel() == N * K, "Activation shape mismatch")
     weight_q = weight_q.contiguous()
     activation = activation.contiguous()
+    if gate is not None:
+        _check(gate.is_cuda and gate.dtype == torch.float32 and gate.numel() == N * K, "Gate must match the activation")
+        gate = gate.contiguous()
     out = torch.empty((M, N), dtype=torch.float32, device=weight_q.device)
     L = _lib.lib()
     with torch.cuda.device(weight_q.device):
         ws_bytes = L.qgemm_workspace_bytes(wtype, N, M, K, flags)
         ws = _workspace(weight_q.device, ws_bytes)
-        rc = L.qgemm_gemm_f32act(wtype, activation.data_ptr(), weight_q.data_ptr(), out.data_ptr(), N, M, K,
-                                 1, N, (flags & 0xFFFF) | (q81_flags << 16),
-                                 ws.data_ptr() if ws is not None else None,
-                                 ws.numel() if ws is not None else 0, _stream(weight_q))
+        tail = (N, M, K, 1, N, (flags & 0xFFFF) | (q81_flags << 16), ws.data_ptr() if ws is not None else None,
+                ws.numel() if ws is not None else 0, _stream(weight_q))
+        if gate is None:
+            rc = L.qgemm_gemm_f32act(wtype, activation.data_ptr(), weight_q.data_ptr(), out.data_ptr(), *tail)
+        else:
+            rc = L.qgemm_gemm_f32act_silu_mul(wtype, activation.data_ptr(), gate.data_ptr(), weight_q.data_ptr(), out.data_ptr(), *tail)
     _lib.raise_on_error(rc, "gemm_w4a8")
     return out
 

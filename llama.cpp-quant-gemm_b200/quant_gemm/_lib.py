@@ -36,6 +36,7 @@ SYMBOLS = {
     "qgemm_workspace_bytes": (_sz, [_i, _i, _i, _i, _u32]),
     "qgemm_gemm": (_i, [_i, _p, _p, _p, _i, _i, _i, _i64, _i64, _u32, _p, _sz, _p]),
     "qgemm_gemm_f32act": (_i, [_i, _p, _p, _p, _i, _i, _i, _i64, _i64, _u32, _p, _sz, _p]),
+    "qgemm_gemm_f32act_silu_mul": (_i, [_i, _p, _p, _p, _p, _i, _i, _i, _i64, _i64, _u32, _p, _sz, _p]),
     "qgemm_gemm_a16": (_i, [_i, _p, _p, _p, _i, _i, _i, _i64, _i64, _u32, _p]),
     "qgemm_sumi": (_i, [_i, _p, _p, _p, _i, _i, _i, _u32, _p, _sz, _p]),
     "qgemm_shard_range": (_i, [_i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),

@@ -128,6 +128,26 @@ def test_quantize_q8_1_silu_mul_fused(qg, O, shape):
         qg.quantize_q8_1_silu_mul(dev(x), dev(g[..., :32]))
 
 
+@pytest.mark.parametrize("wt,T,F,K", [(qo.Q4_0, 1, 300, 1024), (qo.Q5_1, 6, 129, 512), (qo.Q4_0, 256, 1000, 2048), (qo.Q8_0, 40, 384, 1024)])
+def test_swiglu_down_projection_one_call(qg, O, wt, T, F, K):
+    """gemm_w4a8(..., gate=g) = W . quantize_q8_1(silu(x) * g): bit-equal to the fused quantizer followed by the GEMM on
+    every path (decode, small batch, tensor cores: there the quantizer writes the operand tiles itself, two launches)."""
+    rng = np.random.default_rng(T + F)
+    x = (rng.standard_normal((T, K)) * 2).astype(np.float32)
+    g = rng.standard_normal((T, K)).astype(np.float32)
+    _, w = datagen.model_like(1, F, K, seed=F)
+    wq = dev(O.quantize_weight(wt, w))
+    dx, dg = dev(x), dev(g)
+    qg.reset_launch_count()
+    c1 = qg.gemm_w4a8(wq, dx, F, T, K, wtype=wt, gate=dg)
+    n1 = qg.launch_count()
+    c2 = qg.gemm(wq, qg.quantize_q8_1_silu_mul(dx, dg), F, T, K, wt)
+    assert torch.equal(c1, c2)
+    assert n1 <= 3      # quantizer (+ the tile padding sliver when T % 128 != 0) + GEMM
+    aq = host(qg.quantize_q8_1_silu_mul(dx, dg))
+    check_c(host(c1), O.gemm(wt, aq, host(wq), layout="FT"), "swiglu down projection vs oracle on the GPU-quantized input")
+
+
 @pytest.mark.parametrize("wt", qo.WEIGHT_TYPES)
 def test_weight_quantizers_and_dequantize(qg, O, wt):
     _, w = datagen.model_like(1, 9, 512, seed=wt)
