@@ -125,6 +125,16 @@ QGEMM_API int qgemm_quantize_q8_1(const float *x, void *y, int64_t rows, int64_t
  * * gate, same operation sequence, bit-identical intermediate values on the GPU) followed by quantize_q8_1_cuda();
  * x, gate: [rows][K] fp32; flags as for qgemm_quantize_q8_1.  One pass: 9.1 instead of 17.1 bytes per element.
  */
+/*
+ * y = quantize_q8_1(rms_norm(x) * weight): the normalisation in front of the q/k/v and gate/up projections folded into
+ * their quantizer.  Replaces rms_norm_forward_f32() (kernels/normalization/rms_norm.cuh:249-272; arithmetic of
+ * rms_norm_cpu_f32, :32-58: sum of squares in double, 1 / sqrtf(mean + eps), then x * inv_rms * weight[i] in that
+ * order) followed by quantize_q8_1_cuda().  x: [rows][K] fp32, weight: [K] fp32 (16-byte aligned); row_scratch: `rows`
+ * floats of device scratch (1 / rms per row).  Two launches; the normalised fp32 tensor never exists in memory.
+ */
+QGEMM_API int qgemm_quantize_q8_1_rms_norm(const float *x, const float *weight, void *y, int64_t rows, int64_t K, float eps,
+                                           uint32_t flags, float *row_scratch, void *stream);
+
 QGEMM_API int qgemm_quantize_q8_1_silu_mul(const float *x, const float *gate, void *y, int64_t rows, int64_t K, uint32_t flags,
                                            void *stream);
 

@@ -42,6 +42,8 @@ bool mmq_supported(int wtype, const void* act, const void* wgt, int T, int F, in
 size_t mmq_workspace_bytes(int wtype, int T, int F, int K);
 size_t mmq_workspace_need(int wtype, const void* wgt, int T, int F, int K, uint32_t flags);
 cudaError_t launch_quantize_q8_1_silu_mul(const float* x, const float* gate, void* y, int64_t nblocks, uint32_t flags, cudaStream_t st);
+cudaError_t launch_quantize_q8_1_rms_norm(const float* x, const float* weight, float* inv_rms, void* y, int64_t rows, int K, float eps,
+                                          uint32_t flags, cudaStream_t st);
 cudaError_t launch_mmq_f32act(int wtype, const float* act_f32, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
                               int64_t ldc_f, uint32_t flags, uint32_t qflags, void* ws, size_t ws_bytes, int num_sms, cudaStream_t st, const float* gate = nullptr);
 cudaError_t launch_mmq(int wtype, const void* act, const void* wgt, float* C, int32_t* sumi_out, int T, int F, int K,
@@ -299,6 +301,19 @@ int qgemm_quantize_q8_1_silu_mul(const float* x, const float* gate, void* y, int
     if (int rc = device_check(&dev)) return rc;
     const cudaError_t e = launch_quantize_q8_1_silu_mul(x, gate, y, rows * (K / kQK), flags, (cudaStream_t)stream);
     return e == cudaSuccess ? QGEMM_OK : cuda_fail(e, "quantize_q8_1_silu_mul launch");
+}
+
+int qgemm_quantize_q8_1_rms_norm(const float* x, const float* weight, void* y, int64_t rows, int64_t K, float eps, uint32_t flags,
+                                 float* row_scratch, void* stream) {
+    if (rows < 0 || K < 0 || (K % kQK) != 0 || K > INT32_MAX || rows > INT32_MAX) return QGEMM_E_BADARG;
+    if (rows == 0 || K == 0) return QGEMM_OK;
+    if (!x || !weight || !y) return QGEMM_E_BADARG;
+    if (!row_scratch) return QGEMM_E_WORKSPACE;
+    if (!aligned(x, 4) || !aligned(weight, 16) || !aligned(y, 4) || !aligned(row_scratch, 4)) return QGEMM_E_ALIGN;
+    DeviceInfo dev;
+    if (int rc = device_check(&dev)) return rc;
+    const cudaError_t e = launch_quantize_q8_1_rms_norm(x, weight, row_scratch, y, rows, (int)K, eps, flags, (cudaStream_t)stream);
+    return e == cudaSuccess ? QGEMM_OK : cuda_fail(e, "quantize_q8_1_rms_norm launch");
 }
 
 int qgemm_quantize_q8_1(const float* x, void* y, int64_t rows, int64_t K, uint32_t flags, void* stream) {

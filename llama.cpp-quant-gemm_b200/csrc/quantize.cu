@@ -38,13 +38,17 @@ struct Q81Tiles {
     float coef;
     unsigned* zero;    // split-K arrival counters of the GEMM behind this kernel: cleared here
     int nzero;
-    const float* gate; // kSiluMul: the second operand of silu(x) * gate
+    const float* gate; // kPro == 1: the second operand of silu(x) * gate;  kPro == 2: the rms_norm weight [K]
+    const float* inv_rms; // kPro == 2: 1 / rms of every row (row_inv_rms_kernel)
+    int pro_nb;        // kPro == 2: blocks per row
 };
 
 // kSiluMul: the value that is quantized is silu(x) * gate, computed with the operation sequence of the reference's
 // silu_mul_f32_kernel (kernels/activation/silu.cuh:97-108): val / (1.0f + expf(-val)), then times gate -- the SwiGLU
 // neighbour of the FFN down projection folded into its quantizer, 9.1 instead of 17.1 bytes per element.
-template <bool kAlignedX, bool kTiles, bool kSiluMul = false>
+// kPro == 2: the value that is quantized is x * inv_rms[row] * weight[col], the operation order of the reference's
+// rms_norm kernels (kernels/normalization/rms_norm.cuh:54-56, 134-136), with 1 / rms from row_inv_rms_kernel below.
+template <bool kAlignedX, bool kTiles, int kPro = 0>
 __global__ void __launch_bounds__(kQWarps * 32)
 quantize_q8_1_kernel(const float* __restrict__ x, uint32_t* __restrict__ y, int64_t nblocks, uint32_t flags, const Q81Tiles tl) {
     __shared__ float tile[kQWarps][32][33];
@@ -73,7 +77,7 @@ quantize_q8_1_kernel(const float* __restrict__ x, uint32_t* __restrict__ y, int6
             } else {
                 v.x = xb[v4 * 4 + 0]; v.y = xb[v4 * 4 + 1]; v.z = xb[v4 * 4 + 2]; v.w = xb[v4 * 4 + 3];
             }
-            if constexpr (kSiluMul) {
+            if constexpr (kPro == 1) {
                 const float* gb = tl.gate + b0 * 32;
                 float4 g;
                 if constexpr (kAlignedX) {
@@ -85,6 +89,17 @@ quantize_q8_1_kernel(const float* __restrict__ x, uint32_t* __restrict__ y, int6
                 v.y = __fmul_rn(__fdiv_rn(v.y, __fadd_rn(1.0f, expf(-v.y))), g.y);
                 v.z = __fmul_rn(__fdiv_rn(v.z, __fadd_rn(1.0f, expf(-v.z))), g.z);
                 v.w = __fmul_rn(__fdiv_rn(v.w, __fadd_rn(1.0f, expf(-v.w))), g.w);
+            }
+            if constexpr (kPro == 2) {
+                const int64_t g = b0 + blk;                       // block index: row g / nb, columns (g % nb) * 32 + j ..
+                const int64_t r = g / tl.pro_nb;
+                const int col = (int)(g - r * tl.pro_nb) * 32 + j;
+                const float ir = __ldg(tl.inv_rms + r);
+                const float4 w = __ldg(reinterpret_cast<const float4*>(tl.gate + col));   // K % 32 == 0, weight 16-byte aligned
+                v.x = __fmul_rn(__fmul_rn(v.x, ir), w.x);
+                v.y = __fmul_rn(__fmul_rn(v.y, ir), w.y);
+                v.z = __fmul_rn(__fmul_rn(v.z, ir), w.z);
+                v.w = __fmul_rn(__fmul_rn(v.w, ir), w.w);
             }
         }
         tw[blk][j + 0] = v.x; tw[blk][j + 1] = v.y; tw[blk][j + 2] = v.z; tw[blk][j + 3] = v.w;
@@ -165,9 +180,54 @@ cudaError_t launch_quantize_q8_1_silu_mul(const float* x, const float* gate, voi
     Q81Tiles tl{};
     tl.gate = gate;
     if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gate)) & 15) == 0)
-        quantize_q8_1_kernel<true, false, true><<<grid, kQWarps * 32, 0, st>>>(x, (uint32_t*)y, nblocks, flags, tl);
+        quantize_q8_1_kernel<true, false, 1><<<grid, kQWarps * 32, 0, st>>>(x, (uint32_t*)y, nblocks, flags, tl);
     else
-        quantize_q8_1_kernel<false, false, true><<<grid, kQWarps * 32, 0, st>>>(x, (uint32_t*)y, nblocks, flags, tl);
+        quantize_q8_1_kernel<false, false, 1><<<grid, kQWarps * 32, 0, st>>>(x, (uint32_t*)y, nblocks, flags, tl);
+    note_launch();
+    return cudaGetLastError();
+}
+
+// 1 / rms of every row: inv_rms[r] = 1 / sqrtf((float)(sum_k x^2 / K) + eps), the sum of squares in double like
+// rms_norm_cpu_f32 (kernels/normalization/rms_norm.cuh:43-51).  One CTA per row, partial sums combined in a fixed order.
+__global__ void __launch_bounds__(256) row_inv_rms_kernel(const float* __restrict__ x, float* __restrict__ inv_rms, int K, float eps) {
+    __shared__ double part[256];
+    const float* xr = x + (size_t)blockIdx.x * K;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < K; i += 256) {
+        const double v = (double)xr[i];
+        acc += v * v;
+    }
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const float rms = sqrtf(__fadd_rn((float)(part[0] / (double)K), eps));
+        inv_rms[blockIdx.x] = __fdiv_rn(1.0f, rms);
+    }
+}
+
+// y = quantize_q8_1(x * inv_rms[row] * weight): two launches (row statistics, then the quantizer reads x again, from L2
+// for the sizes a decode or prefill step has).  inv_rms: `rows` floats of scratch.
+cudaError_t launch_quantize_q8_1_rms_norm(const float* x, const float* weight, float* inv_rms, void* y, int64_t rows, int K, float eps,
+                                          uint32_t flags, cudaStream_t st) {
+    if (rows == 0 || K == 0) return cudaSuccess;
+    row_inv_rms_kernel<<<(unsigned)rows, 256, 0, st>>>(x, inv_rms, K, eps);
+    note_launch();
+    if (cudaError_t e = cudaGetLastError()) return e;
+    const int64_t nblocks = rows * (K / 32);
+    const int64_t per_cta = (int64_t)kQWarps * 32;
+    const unsigned grid = (unsigned)((nblocks + per_cta - 1) / per_cta);
+    Q81Tiles tl{};
+    tl.gate = weight;
+    tl.inv_rms = inv_rms;
+    tl.pro_nb = K / 32;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) == 0)
+        quantize_q8_1_kernel<true, false, 2><<<grid, kQWarps * 32, 0, st>>>(x, (uint32_t*)y, nblocks, flags, tl);
+    else
+        quantize_q8_1_kernel<false, false, 2><<<grid, kQWarps * 32, 0, st>>>(x, (uint32_t*)y, nblocks, flags, tl);
     note_launch();
     return cudaGetLastError();
 }
@@ -199,11 +259,11 @@ cudaError_t launch_quantize_q8_1_tiles(const float* x, uint8_t* a8, float2* as, 
     const int64_t nblocks = (int64_t)T * nb;
     const int64_t per_cta = (int64_t)kQWarps * 32;
     const unsigned grid = (unsigned)((nblocks + per_cta - 1) / per_cta);
-    const Q81Tiles tl{a8, as, T, Tpad, nb, coef, zero, nzero, gate};
+    const Q81Tiles tl{a8, as, T, Tpad, nb, coef, zero, nzero, gate, nullptr, 0};
     const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gate)) & 15) == 0;
     if (gate) {   // silu(x) * gate is what gets quantized (the FFN down projection's input)
-        if (al) quantize_q8_1_kernel<true, true, true><<<grid, kQWarps * 32, 0, st>>>(x, nullptr, nblocks, flags, tl);
-        else quantize_q8_1_kernel<false, true, true><<<grid, kQWarps * 32, 0, st>>>(x, nullptr, nblocks, flags, tl);
+        if (al) quantize_q8_1_kernel<true, true, 1><<<grid, kQWarps * 32, 0, st>>>(x, nullptr, nblocks, flags, tl);
+        else quantize_q8_1_kernel<false, true, 1><<<grid, kQWarps * 32, 0, st>>>(x, nullptr, nblocks, flags, tl);
     } else if (al) {
         quantize_q8_1_kernel<true, true><<<grid, kQWarps * 32, 0, st>>>(x, nullptr, nblocks, flags, tl);
     } else {

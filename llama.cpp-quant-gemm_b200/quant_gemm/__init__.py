@@ -111,6 +111,25 @@ def quantize_q8_1_silu_mul(x: torch.Tensor, gate: torch.Tensor, flags: int = Q81
     return out
 
 
+def quantize_q8_1_rms_norm(x: torch.Tensor, weight: torch.Tensor, eps: float = 1e-5, flags: int = Q81_ROUND_AWAY) -> torch.Tensor:
+    """quantize_q8_1(rms_norm(x) * weight): the reference's rms_norm_forward_f32 (kernels/normalization/rms_norm.cuh:249-272)
+    folded into the quantizer in front of the q/k/v and gate/up projections.  x: FP32 [..., K], weight: FP32 [K]."""
+    _check(x.is_cuda and weight.is_cuda, "Inputs must be CUDA tensors")
+    _check(x.dtype == torch.float32 and weight.dtype == torch.float32, "Inputs must be float32")
+    K = x.shape[-1]
+    _check(K % 32 == 0, f"Last dimension must be divisible by 32, got {K}")
+    _check(weight.numel() == K, "Weight must have K elements")
+    x, weight = x.contiguous(), weight.contiguous()
+    rows = x.numel() // K if K else 0
+    out = torch.empty(*x.shape[:-1], K // 32, BLOCK_BYTES[TYPE_Q8_1], dtype=torch.uint8, device=x.device)
+    scratch = torch.empty(max(rows, 1), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().qgemm_quantize_q8_1_rms_norm(x.data_ptr(), weight.data_ptr(), out.data_ptr(), rows, K, float(eps), flags,
+                                                     scratch.data_ptr(), _stream(x))
+    _lib.raise_on_error(rc, "quantize_q8_1_rms_norm")
+    return out
+
+
 def quantize_q4_1(x, flags: int = 0):
     return _quantize(x, TYPE_Q4_1, flags)
 
@@ -359,6 +378,6 @@ __all__ = [
     # supersets
     "quantize_q4_1", "quantize_q5_0", "quantize_q5_1", "quantize_q8_0", "dequantize",
     "gemm", "gemm_q4_1_q8_1", "gemm_q5_0_q8_1", "gemm_q5_1_q8_1", "gemm_q8_0_q8_1", "gemm_w4a8",
-    "gemm_a16", "gemm_q4_0_fp32", "quantize_q8_1_silu_mul",
+    "gemm_a16", "gemm_q4_0_fp32", "quantize_q8_1_silu_mul", "quantize_q8_1_rms_norm",
     "gemm_group", "prepack_weights", "block_sumi", "launch_count", "reset_launch_count", "last_path", "hint_next_weights",
 ]

@@ -26,6 +26,7 @@ SYMBOLS = {
     "qgemm_last_error_detail": (C.c_char_p, []),
     "qgemm_quantize_q8_1": (_i, [_p, _p, _i64, _i64, _u32, _p]),
     "qgemm_quantize_q8_1_silu_mul": (_i, [_p, _p, _p, _i64, _i64, _u32, _p]),
+    "qgemm_quantize_q8_1_rms_norm": (_i, [_p, _p, _p, _i64, _i64, C.c_float, _u32, _p, _p]),
     "qgemm_quantize_weight": (_i, [_i, _p, _p, _i64, _i64, _u32, _p]),
     "qgemm_dequantize": (_i, [_i, _p, _p, _i64, _i64, _p]),
     "qgemm_set_default_workspace": (_i, [_p, _sz]),

@@ -132,6 +132,21 @@ void qo_silu_mul(const float *x, const float *gate, float *y, int64_t n)
     }
 }
 
+/* rms_norm(x) * weight, row by row: rms_norm_cpu_f32 (kernels/normalization/rms_norm.cuh:32-58) -- the sum of squares
+ * in double, rms = sqrtf((float)(sum / n_cols) + eps), inv_rms = 1.0f / rms, y = x * inv_rms * weight in that order. */
+void qo_rms_norm(const float *x, const float *weight, float *y, int64_t n_rows, int64_t n_cols, float eps)
+{
+    for (int64_t row = 0; row < n_rows; row++) {
+        const float *xr = x + row * n_cols;
+        float *yr = y + row * n_cols;
+        double sum_sq = 0.0;
+        for (int64_t i = 0; i < n_cols; i++) sum_sq += (double)xr[i] * xr[i];
+        const float rms = sqrtf((float)(sum_sq / (double)n_cols) + eps);
+        const float inv_rms = 1.0f / rms;
+        for (int64_t i = 0; i < n_cols; i++) yr[i] = xr[i] * inv_rms * weight[i];
+    }
+}
+
 void qo_quantize_q8_1(const float *x, void *y, int64_t n, unsigned flags)
 {
     /* include/quantize.h:165-193 (CPU), :302-337 (GPU kernel),

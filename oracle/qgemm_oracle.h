@@ -58,6 +58,7 @@ size_t qo_block_bytes(int type);
 /* ---- quantizers --------------------------------------------------------- */
 /* x[rows*k] fp32 -> y[rows*k/32] block_q8_1 (36 B each). */
 void qo_silu_mul(const float *x, const float *gate, float *y, int64_t n);
+void qo_rms_norm(const float *x, const float *weight, float *y, int64_t n_rows, int64_t n_cols, float eps);
 void qo_quantize_q8_1(const float *x, void *y, int64_t n, unsigned flags);
 
 /* include/quantize.h flavours (weights as test data) */

@@ -73,6 +73,7 @@ class Oracle:
         L.qo_fp16_to_fp32.argtypes = [C.c_uint16]
         L.qo_quantize_q8_1.argtypes = [_p, _p, _i64, _u]
         L.qo_silu_mul.argtypes = [_p, _p, _p, _i64]
+        L.qo_rms_norm.argtypes = [_p, _p, _p, _i64, _i64, _f]
         for n in ("qo_quantize_q4_0_ref", "qo_quantize_q8_0_ref", "qo_to_q4_0", "qo_to_q4_1",
                   "qo_to_q5_0", "qo_to_q5_1", "qo_to_q8_0"):
             getattr(L, n).argtypes = [_p, _p, _i64]
@@ -110,6 +111,15 @@ class Oracle:
         assert x.shape == gate.shape
         out = np.empty_like(x)
         self.lib.qo_silu_mul(_ptr(x), _ptr(gate), _ptr(out), x.size)
+        return out
+
+    def rms_norm(self, x, weight, eps: float = 1e-5) -> np.ndarray:
+        """rms_norm(x) * weight over the last axis, arithmetic of kernels/normalization/rms_norm.cuh:32-58."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        weight = np.ascontiguousarray(weight, dtype=np.float32)
+        assert weight.size == x.shape[-1]
+        out = np.empty_like(x)
+        self.lib.qo_rms_norm(_ptr(x), _ptr(weight), _ptr(out), x.size // x.shape[-1], x.shape[-1], eps)
         return out
 
     def quantize_weight(self, wtype: int, x, flavour: str = "framework"):
@@ -225,6 +235,9 @@ class Reference:
         if hasattr(L, "ref_gpu_silu_mul_f32"):   # kernels/activation/silu.cuh (added with the fused SwiGLU quantizer)
             L.ref_gpu_silu_mul_f32.argtypes = [_p, _p, _p, _i, _p]
             L.ref_cpu_silu_f32.argtypes = [_p, _p, _i]
+        if hasattr(L, "ref_cpu_rms_norm_f32"):   # kernels/normalization/rms_norm.cuh
+            L.ref_cpu_rms_norm_f32.argtypes = [_p, _p, _p, _i, _i, _f]
+            L.ref_gpu_rms_norm_f32.argtypes = [_p, _p, _p, _i, _i, _f, _p]
         L.ref_vec_dot_q4_0_q8_1.restype = _f
         L.ref_vec_dot_q4_0_q8_1.argtypes = [_i, _p, _p]
         L.ref_vec_dot_q8_0_q8_1.restype = _f

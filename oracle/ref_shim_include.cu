@@ -17,6 +17,7 @@
 #include "gemm_cuda_naive.cuh"
 #include "gemm_cuda_dp4a.cuh"
 #include "kernels/activation/silu.cuh"
+#include "kernels/normalization/rms_norm.cuh"
 
 extern "C" {
 
@@ -68,6 +69,10 @@ void ref_gpu_silu_mul_f32(const float* x, const float* gate, float* y, int n, vo
     silu_mul_forward_f32(x, gate, y, n, (cudaStream_t)stream);
 }
 void ref_cpu_silu_f32(const float* x, float* y, int n) { silu_cpu_f32(x, y, n); }
+void ref_cpu_rms_norm_f32(const float* x, const float* w, float* y, int rows, int cols, float eps) { rms_norm_cpu_f32(x, w, y, rows, cols, eps); }
+void ref_gpu_rms_norm_f32(const float* x, const float* w, float* y, int rows, int cols, float eps, void* stream) {
+    rms_norm_forward_f32(x, w, y, rows, cols, eps, (cudaStream_t)stream);
+}
 void ref_gpu_gemm_w4a8_tiled_dp4a(const void* A, const void* B, float* C, int M, int N, int K, void* stream) {
     gemm_w4a8_tiled_dp4a((const block_q8_1*)A, (const block_q4_0*)B, C, M, N, K, (cudaStream_t)stream);
 }

@@ -128,6 +128,37 @@ def test_quantize_q8_1_silu_mul_fused(qg, O, shape):
         qg.quantize_q8_1_silu_mul(dev(x), dev(g[..., :32]))
 
 
+@pytest.mark.parametrize("shape", [(1, 4096), (5, 11008), (300, 1024), (2, 3, 64)])
+def test_quantize_q8_1_rms_norm_fused(qg, O, shape):
+    """quantize_q8_1(rms_norm(x) * weight) without the fp32 intermediate: against the oracle's restatement of
+    rms_norm_cpu_f32 followed by the quantizer.  1 / rms comes from a double-precision sum of squares on both sides (other
+    summation order on the GPU, same value after rounding to fp32 except in rare ties), so bytes agree up to one
+    quantization step in a few elements; and within that of the reference's GPU kernel followed by the quantizer."""
+    rng = np.random.default_rng(sum(shape))
+    x = (rng.standard_normal(shape) * rng.choice([1e-2, 1.0, 20.0], size=shape[:-1] + (1,))).astype(np.float32)
+    w = (1.0 + 0.2 * rng.standard_normal(shape[-1])).astype(np.float32)
+    got = host(qg.quantize_q8_1_rms_norm(dev(x), dev(w), 1e-5))
+    want = O.quantize_q8_1(O.rms_norm(x, w, 1e-5))
+    assert got.shape == want.shape
+    gq, wq_ = got[..., 4:].view(np.int8).astype(np.int32), want[..., 4:].view(np.int8).astype(np.int32)
+    assert np.abs(gq - wq_).max() <= 1 and (gq != wq_).mean() < 2e-3
+    gd, wd = got[..., :4].copy().view(np.float16).astype(np.float32), want[..., :4].copy().view(np.float16).astype(np.float32)
+    assert np.allclose(gd, wd, rtol=2e-3, atol=1e-6)
+    if qo.have_ref():
+        R = qo.Reference()
+        fn = getattr(R.lib, "ref_gpu_rms_norm_f32", None)
+        if fn is not None:
+            dx, dw = dev(x.reshape(-1, shape[-1])), dev(w)
+            y_ref = torch.empty_like(dx)
+            torch.cuda.synchronize()
+            fn(dx.data_ptr(), dw.data_ptr(), y_ref.data_ptr(), dx.shape[0], dx.shape[1], 1e-5, None)
+            torch.cuda.synchronize()
+            rq = host(qg.quantize_q8_1(y_ref)).reshape(got.shape)[..., 4:].view(np.int8).astype(np.int32)
+            assert np.abs(gq - rq).max() <= 1 and (gq != rq).mean() < 5e-3   # its sum of squares is fp32, block-reduced
+    with pytest.raises(RuntimeError):
+        qg.quantize_q8_1_rms_norm(dev(x), dev(w[:32]))
+
+
 @pytest.mark.parametrize("wt,T,F,K", [(qo.Q4_0, 1, 300, 1024), (qo.Q5_1, 6, 129, 512), (qo.Q4_0, 256, 1000, 2048), (qo.Q8_0, 40, 384, 1024)])
 def test_swiglu_down_projection_one_call(qg, O, wt, T, F, K):
     """gemm_w4a8(..., gate=g) = W . quantize_q8_1(silu(x) * g): bit-equal to the fused quantizer followed by the GEMM on
