@@ -55,7 +55,7 @@ def algorithmic_bytes(wtype, T, F, K):
 
 def load_traffic():
     """Per-launch DRAM bytes of the dominant kernel from the committed ncu --set full capture."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(p):
         d = json.load(open(p))
         return d["dram_bytes_per_launch_bench_average"], d["source"]

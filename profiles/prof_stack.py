@@ -1,27 +1,48 @@
-"""ncu driver: the four launches of one layer of the bench workload (q4_0, M=1, grouped like bench.py:
-[wq wk wv], wo, [gate up], down; each hinting the next one's weights), cold weights, 3 layers."""
+"""ncu driver: the bench workload's launch sequence (q4_0, M=1, grouped like bench.py: [wq wk wv], wo, [gate up], down; the
+weights back to back in one allocation, every launch hinting the next 12 MB of it into L2), cold weights, 8 layers."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [os.path.join(ROOT, "llama.cpp-quant-gemm_b200"), ROOT]
-import torch, quant_gemm, bench_detail
+import torch, quant_gemm
 dev = torch.device("cuda")
 LAYERS = 8
-sq = bench_detail.make_weights(torch, 2, 4096, 4096, 4 * LAYERS, dev)
-up = bench_detail.make_weights(torch, 2, 11008, 4096, 2 * LAYERS, dev)
-dn = bench_detail.make_weights(torch, 2, 4096, 11008, LAYERS, dev)
+WINDOW = 12 << 20
+SHAPES = [(4096, 4096)] * 4 + [(11008, 4096)] * 2 + [(4096, 11008)]
+g = torch.Generator(device=dev)
+g.manual_seed(1)
+sizes = [F * (K // 32) * 18 for _ in range(LAYERS) for F, K in SHAPES]
+arena = torch.empty(sum((n + 255) // 256 * 256 for n in sizes), dtype=torch.uint8, device=dev)
+mats, off = [], 0
+for _ in range(LAYERS):
+    for F, K in SHAPES:
+        nb = K // 32
+        w = arena[off:off + F * nb * 18].view(F, nb, 18)
+        off += (F * nb * 18 + 255) // 256 * 256
+        w.copy_(torch.randint(0, 256, (F, nb, 18), dtype=torch.uint8, device=dev, generator=g))
+        d = (torch.rand((F, nb), device=dev, generator=g) * 0.02 + 0.001).to(torch.float16)
+        w[:, :, 0:2] = d.view(torch.uint8).view(F, nb, 2)
+        mats.append(w)
+end = arena.data_ptr() + arena.numel()
 aq = {K: quant_gemm.quantize_q8_1(torch.randn((1, K), device=dev)) for K in (4096, 11008)}
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 flush.zero_()
 torch.cuda.synchronize()
+
+
+def hint(w):
+    quant_gemm.hint_next_weights(w, min(WINDOW, end - w.data_ptr()))
+
+
 for l in range(LAYERS):
-    q = sq[4 * l:4 * l + 4]
-    quant_gemm.hint_next_weights(q[3])
-    quant_gemm.gemm_group([q[0], q[1], q[2]], aq[4096], [4096] * 3, 1, 4096, 2, 0x10)
-    quant_gemm.hint_next_weights(up[2 * l])
-    quant_gemm.gemm(q[3], aq[4096], 4096, 1, 4096, 2, 0x10)
-    quant_gemm.hint_next_weights(dn[l])
-    quant_gemm.gemm_group([up[2 * l], up[2 * l + 1]], aq[4096], [11008] * 2, 1, 4096, 2, 0x10)
-    quant_gemm.hint_next_weights(sq[(4 * l + 4) % (4 * LAYERS)])
-    quant_gemm.gemm(dn[l], aq[11008], 4096, 1, 11008, 2, 0x10)
+    m = mats[7 * l:7 * l + 7]
+    nxt = mats[(7 * l + 7) % len(mats)]
+    hint(m[3])
+    quant_gemm.gemm_group([m[0], m[1], m[2]], aq[4096], [4096] * 3, 1, 4096, 2, 0x10)
+    hint(m[4])
+    quant_gemm.gemm(m[3], aq[4096], 4096, 1, 4096, 2, 0x10)
+    hint(m[6])
+    quant_gemm.gemm_group([m[4], m[5]], aq[4096], [11008] * 2, 1, 4096, 2, 0x10)
+    hint(nxt)
+    quant_gemm.gemm(m[6], aq[11008], 4096, 1, 11008, 2, 0x10)
 torch.cuda.synchronize()
 print("ok")
