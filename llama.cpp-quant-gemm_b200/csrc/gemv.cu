@@ -172,7 +172,26 @@ struct GemvParams {
     const uint8_t* wgt_m[kGemvMaxGroup];
     float* C_m[kGemvMaxGroup];
     int fstart[kGemvMaxGroup + 1];
+    float skew;           // uneven row shares (see the kernel): 0 = equal
+#ifdef QGEMM_GEMV_TRACE
+    int trace_slot;       // timeline build only (profiles/microbench/decode_trace.cu)
+#endif
 };
+
+#ifdef QGEMM_GEMV_TRACE
+// Timeline build: per launch slot and CTA, %globaltimer at kernel entry, after the dependency wait, after the activations
+// are in registers, and after the last store.  Never compiled into the product library.
+constexpr int kTraceSlots = 256, kTraceCtas = 304;
+__device__ unsigned long long g_gemv_trace[kTraceSlots][kTraceCtas][4];
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define GEMV_TRACE(i) do { if (threadIdx.x == 0 && blockIdx.x < kTraceCtas) g_gemv_trace[p.trace_slot][blockIdx.x][i] = gtimer(); } while (0)
+#else
+#define GEMV_TRACE(i)
+#endif
 
 // tile that starts at group row r0: rows until the tile size, the CTA's span or the matrix ends
 struct TileRef { int m, local, rows; };
@@ -209,9 +228,17 @@ __global__ void __launch_bounds__(kGemvThreads, kGemvCtasPerSm) gemv_kernel(cons
     const uint32_t act_bytes = (PPL > 0) ? (uint32_t)TT * nb * 36u : (uint32_t)TT * nb * 40u;
     uint8_t* stage0 = smem + (((uint32_t)kGemvActOff + act_bytes + 127u) & ~127u);
 
-    // ---- this CTA's contiguous span of weight rows
-    const int r_begin = (int)(((int64_t)p.F * blockIdx.x) / gridDim.x);
-    const int r_end = (int)(((int64_t)p.F * (blockIdx.x + 1)) / gridDim.x);
+    // ---- this CTA's contiguous span of weight rows.  Not quite equal shares: CTAs with low indices come in first and find
+    // the head of the weights in L2 (the previous launch's hint), and the timeline (profiles/r02_decode_timeline.md) has them
+    // finish 0.5-0.8 us before the others, so they get linearly more rows (density 1 + skew * (1/2 - x) over x = index / grid).
+    auto span_at = [&](unsigned c) -> int {
+        if (c >= gridDim.x) return p.F;
+        const float x = (float)c / (float)gridDim.x;
+        const float g = x * (1.0f + 0.5f * p.skew) - 0.5f * p.skew * x * x;
+        return min(p.F, (int)((float)p.F * g + 0.5f));
+    };
+    const int r_begin = p.skew == 0.0f ? (int)(((int64_t)p.F * blockIdx.x) / gridDim.x) : span_at(blockIdx.x);
+    const int r_end = p.skew == 0.0f ? (int)(((int64_t)p.F * (blockIdx.x + 1)) / gridDim.x) : span_at(blockIdx.x + 1);
     const size_t rowbytes = (size_t)nb * Fm::bytes;
 
     uint64_t* abar = reinterpret_cast<uint64_t*>(smem + kGemvAbarOff);  // activation copy: own 8 bytes in front of a_raw
@@ -254,7 +281,9 @@ __global__ void __launch_bounds__(kGemvThreads, kGemvCtasPerSm) gemv_kernel(cons
     }
 
     // ================= consumer warps =================
+    GEMV_TRACE(0);
     if (p.pdl == 1) ptx::griddep_wait();  // activations / C may belong to the previous launch
+    GEMV_TRACE(1);
     if (p.peer.world > 1) {          // ... or to an earlier launch of a peer GPU
         if (tid == 0) peer_wait_prior(p.peer);
         ptx::bar_sync(1, kGemvWarps * 32);
@@ -321,6 +350,7 @@ __global__ void __launch_bounds__(kGemvThreads, kGemvCtasPerSm) gemv_kernel(cons
         ptx::bar_sync(1, kGemvWarps * 32);
     }
 
+    GEMV_TRACE(2);
     int s = 0, spar = 0;
     uint32_t ph = 0;
     const int npl = (PPL > 0) ? PPL : (np + WPR * 32 - 1) / (WPR * 32);  // pairs per lane
@@ -414,6 +444,7 @@ __global__ void __launch_bounds__(kGemvThreads, kGemvCtasPerSm) gemv_kernel(cons
         if (lane == 0) ptx::mbar_arrive(&empty[s]);
         if (++s == p.stages) { s = 0; ph ^= 1; }
     }
+    GEMV_TRACE(3);
     if (p.peer.world > 1) {
         if (!(p.peer.dbg & 4)) __threadfence();  // this thread's peer stores are ordered before the CTA barrier
         ptx::bar_sync(1, kGemvWarps * 32);
@@ -572,6 +603,15 @@ cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, i
                       !QGEMM_ENV("QGEMM_GEMV_NO_ACT_BULK")) ? 1 : 0;
         p.pf_ptr = (t0 + pl.tt >= T && reinterpret_cast<uintptr_t>(pf_ptr) % 16 == 0) ? (const uint8_t*)pf_ptr : nullptr;
         p.pf_bytes = pf_bytes;
+        // measured on the decode stack (profiles/r02_decode_timeline.md): 0 -> 881, 0.1 -> 875, 0.2 -> 866, 0.25 / 0.3 -> 860,
+        // 0.35 -> 879, 0.4 -> 893 us per 128-launch step
+        p.skew = QGEMM_ENV("QGEMM_GEMV_SKEW") ? (float)atof(QGEMM_ENV("QGEMM_GEMV_SKEW")) : (F >= 8 * grid ? 0.28f : 0.0f);
+#ifdef QGEMM_GEMV_TRACE
+        {
+            static int seq = 0;
+            p.trace_slot = seq++ % kTraceSlots;
+        }
+#endif
         p.nmat = 0;
         if (group) {
             p.nmat = group->nmat;
@@ -602,3 +642,9 @@ cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, i
 }
 
 }  // namespace qgemm
+
+#ifdef QGEMM_GEMV_TRACE
+extern "C" __attribute__((visibility("default"))) int qgemm_debug_read_gemv_trace(unsigned long long* dst, size_t bytes) {
+    return (int)cudaMemcpyFromSymbol(dst, qgemm::g_gemv_trace, bytes < sizeof(qgemm::g_gemv_trace) ? bytes : sizeof(qgemm::g_gemv_trace));
+}
+#endif
