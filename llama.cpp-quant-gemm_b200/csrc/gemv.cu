@@ -182,7 +182,7 @@ struct GemvParams {
 // Timeline build: per launch slot and CTA, %globaltimer at kernel entry, after the dependency wait, after the activations
 // are in registers, and after the last store.  Never compiled into the product library.
 constexpr int kTraceSlots = 256, kTraceCtas = 304;
-__device__ unsigned long long g_gemv_trace[kTraceSlots][kTraceCtas][4];
+__device__ unsigned long long g_gemv_trace[kTraceSlots][kTraceCtas][6];
 __device__ __forceinline__ unsigned long long gtimer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -305,6 +305,7 @@ __global__ void __launch_bounds__(kGemvThreads, kGemvCtasPerSm) gemv_kernel(cons
                 ptx::bulk_g2s(a_raw, p.act, (uint32_t)total * 4u, abar);
             }
             ptx::mbar_wait(abar, 0);
+            GEMV_TRACE(4);
         } else {
             for (int i = tid; i < total; i += kGemvWarps * 32) dst[i] = __ldg(a32 + i);
             ptx::bar_sync(1, kGemvWarps * 32);

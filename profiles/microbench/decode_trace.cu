@@ -66,12 +66,12 @@ int main() {
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
     printf("one step (128 launches): %.1f us\n", ms * 1e3);
     const int slots = 256, ctas = 304, nl = layers * 4;
-    std::vector<unsigned long long> tr((size_t)slots * ctas * 4);
+    std::vector<unsigned long long> tr((size_t)slots * ctas * 6);
     if (rd(tr.data(), tr.size() * 8)) { printf("trace read failed\n"); return 1; }
     // the capture pass used slots 0..127, the graph nodes keep those slot numbers: the last replay is what is in them
-    auto T = [&](int l, int c, int i) { return tr[((size_t)(l % slots) * ctas + c) * 4 + i]; };
+    auto T = [&](int l, int c, int i) { return tr[((size_t)(l % slots) * ctas + c) * 6 + i]; };
     const int grid = 296;
-    double sum_gap = 0, sum_skew = 0, sum_startskew = 0, sum_wait2act = 0, sum_len = 0, sum_period = 0;
+    double sum_wait2bulk = 0, sum_wait2bulk_mean = 0, sum_gap = 0, sum_skew = 0, sum_startskew = 0, sum_wait2act = 0, sum_len = 0, sum_period = 0;
     int cnt = 0;
     unsigned long long t0 = ~0ull;
     for (int c = 0; c < grid; c++) t0 = std::min(t0, T(0, c, 0));
@@ -94,6 +94,7 @@ int main() {
             sum_skew += (double)e_max - (double)e_min;
             sum_startskew += (double)w_max - (double)w_min;
             sum_wait2act += (double)a_max - (double)w_max;
+            { unsigned long long b_max = 0; double m = 0; for (int c = 0; c < grid; c++) { b_max = std::max(b_max, T(l, c, 4)); m += (double)T(l, c, 4) - (double)T(l, c, 1); } sum_wait2bulk += (double)b_max - (double)w_max; sum_wait2bulk_mean += m / grid; }
             sum_len += (double)e_max - (double)w_min;
             sum_period += (double)ne_max - (double)e_max;
             cnt++;
@@ -112,6 +113,7 @@ int main() {
         printf("launch %d: mean end time by start-time quartile (earliest starters first): %.2f %.2f %.2f %.2f us | by block index half: %.2f %.2f\n", l, q[0], q[1], q[2], q[3],
                elo / lo, ehi / hi);
     }
+    printf("wait passed -> activation bulk copy complete: last CTA %.2f us, mean over CTAs %.2f us\n", sum_wait2bulk / cnt * 1e-3, sum_wait2bulk_mean / cnt * 1e-3);
     printf("averages over %d launches (us): period %.2f | wait passed -> last store %.2f | last store -> next launch past its wait %.2f | "
            "skew of the waits %.2f | last wait -> activations in registers %.2f | skew of the last stores %.2f\n",
            cnt, sum_period / cnt * 1e-3, sum_len / cnt * 1e-3, sum_gap / cnt * 1e-3, sum_startskew / cnt * 1e-3, sum_wait2act / cnt * 1e-3, sum_skew / cnt * 1e-3);
