@@ -316,6 +316,15 @@ def main():
     ap.add_argument("--layers", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--group", type=int, default=1, help="1 GPU: fuse q/k/v and gate/up into grouped launches")
+    ap.add_argument("--chain", type=int, default=0,
+                    help="1 GPU: layers per persistent chained launch (qgemm_gemv_chain: the grouped projections of `chain` layers "
+                         "walked by one launch with device-side dependencies; every step still waits for its predecessor to "
+                         "complete on the whole device).  0 (default): one launch per grouped projection -- measured faster: a "
+                         "programmatic dependent launch costs less than a device-wide barrier inside a kernel "
+                         "(profiles/r02_chain.md); the chained form is timed as extra.chained_launch_form")
+    ap.add_argument("--d2h-chunk-layers", type=int, default=4,
+                    help="e2e: copy the outputs back to the host every this many layers on a side stream, overlapped with the "
+                         "following layers (0: one copy at the end of the step)")
     ap.add_argument("--prefetch", type=int, default=1, help="1: hint each GEMV with the next one's weights (L2 prefetch)")
     ap.add_argument("--prefetch-mb", type=int, default=12,
                     help="L2 prefetch window in MB, starting at the next launch's first matrix (0: exactly that matrix). "
@@ -441,7 +450,25 @@ def main():
             b = 7 * l
             groups += [[b, b + 1, b + 2], [b + 3], [b + 4, b + 5], [b + 6]]
 
-    def gemv_all():
+    chains = []
+    if groups and args.chain > 0:
+        per = 4 * args.chain
+        for c0 in range(0, len(groups), per):
+            steps = []
+            for g in groups[c0:c0 + per]:
+                K = mats[g[0]][1]
+                # stream-order semantics: no step is marked `ready`, each waits until its predecessor has completed
+                steps.append({"weights": [mats[i][2] for i in g], "Ms": [mats[i][0] for i in g], "K": K,
+                              "act_q": acts_q[K], "outs": [outs[i] for i in g]})
+            chains.append((quant_gemm.GemvChain(steps, WTYPE, GEMV_FLAGS), mats[groups[c0][0]][2]))
+
+    def gemv_all(after_layer=None):
+        if chains:
+            for ci, (ch, _) in enumerate(chains):
+                if args.prefetch:   # the head of the next chain's weights
+                    hint(chains[(ci + 1) % len(chains)][1])
+                ch()
+            return
         if plan is not None and args.group:
             for oi, (op, K, g) in enumerate(ops):
                 if args.prefetch:
@@ -460,6 +487,8 @@ def main():
                 else:
                     quant_gemm.gemm_group([mats[i][2] for i in g], acts_q[K], [mats[i][0] for i in g], 1, K, WTYPE,
                                           GEMV_FLAGS, outs=[outs[i] for i in g])
+                if after_layer is not None and gi % 4 == 3:
+                    after_layer(gi // 4)
             return
         # a decode runtime knows its layer order: each launch pulls the next GEMV's weights into L2
         n = len(mats)
@@ -478,7 +507,25 @@ def main():
     def e2e_step():
         for K in acts_host:
             acts_dev[K].copy_(acts_host[K], non_blocking=True)
-            acts_q[K] = quant_gemm.quantize_q8_1(acts_dev[K])
+            quant_gemm.quantize_q8_1(acts_dev[K], out=acts_q[K])   # the decode runtime's fixed activation buffers
+        if groups and not chains and plan is None and args.d2h_chunk_layers > 0:
+            # the step's results go back to the host as they are produced: every few layers a side stream copies the finished
+            # slice of the output buffer while the next layers compute (same bytes, same pinned destination); the step ends
+            # when the last slice has landed
+            main = torch.cuda.current_stream()
+            per_layer = sum(F for _, F, _ in LLAMA7B)
+            sent = [0]
+
+            def after_layer(l):
+                if (l + 1) % args.d2h_chunk_layers == 0 or l == args.layers - 1:
+                    lo, hi = sent[0], (l + 1) * per_layer
+                    sent[0] = hi
+                    d2h_stream.wait_stream(main)
+                    with torch.cuda.stream(d2h_stream):
+                        out_host[lo:hi].copy_(out_all[lo:hi], non_blocking=True)
+            gemv_all(after_layer)
+            main.wait_stream(d2h_stream)
+            return
         gemv_all()
         if plan is not None:   # fused all-gather: the gathered outputs live in the symmetric pool
             out_host[:plan.cursor].copy_(plan.pool[:plan.cursor], non_blocking=True)
@@ -486,6 +533,7 @@ def main():
             out_host[:total_out].copy_(out_all, non_blocking=True)
 
     stream = torch.cuda.Stream(device=dev)
+    d2h_stream = torch.cuda.Stream(device=dev)
     with torch.cuda.stream(stream):
         gemv_all()  # warm: cudaFuncSetAttribute, NCCL channels
         e2e_step()
@@ -563,6 +611,33 @@ def main():
         extra["prefill_q5_1_M2048_N14336_K4096_incl_quantize"] = {
             "us": r["us"], "tops": r["tops"], "path": r["path"], "frac_of_nominal_int8_4500_tops": r["tops"] / 4500.0,
             "note": "BASELINE configs[3]; fp32 activations in, quantize_q8_1 inside the call (two launches), L2 flushed between reps"}
+        if groups and not chains:
+            # the same step as persistent chained launches (the last review's suggestion), for the record: it is slower
+            try:
+                forms = {}
+                for L in (1, args.layers):
+                    cs = []
+                    for c0 in range(0, len(groups), 4 * L):
+                        steps = [{"weights": [mats[i][2] for i in g], "Ms": [mats[i][0] for i in g], "K": mats[g[0]][1],
+                                  "act_q": acts_q[mats[g[0]][1]], "outs": [outs[i] for i in g]} for g in groups[c0:c0 + 4 * L]]
+                        cs.append(quant_gemm.GemvChain(steps, WTYPE, GEMV_FLAGS))
+                    with torch.cuda.stream(stream):
+                        for ch in cs:
+                            ch()
+                        stream.synchronize()
+                        gch = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(gch, stream=stream):
+                            for ch in cs:
+                                ch()
+                    ms = timed(gch, 10, 3)
+                    forms[f"{L}_layer(s)_per_launch"] = {"ms_per_step": ms / 10, "gbs": step_bytes * 10 / (ms * 1e-3) / 1e9,
+                                                         "launches_per_step": len(cs)}
+                    del gch
+                extra["chained_launch_form"] = dict(forms, note="qgemm_gemv_chain: one persistent launch walks the grouped projections "
+                                                    "with device-side dependencies (stream-order semantics kept); bit-identical "
+                                                    "outputs; slower than one PDL launch per projection, see profiles/r02_chain.md")
+            except Exception as ex:  # noqa: BLE001 -- an extra, the headline stands
+                extra["chained_launch_form"] = {"error": repr(ex)[:300]}
         extra["prefill_ceiling_note"] = ("the per-block scale fold runs on the CUDA cores: one I2FP + two packed FMAs per output pair and "
                                          "quantization block; profiles/microbench/epi_probe.cu measures 469 cycles per 128x128 block for "
                                          "that sequence alone (13.6 % of the int8 MMA rate), profiles/r02_prefill_knockouts.md")
@@ -571,17 +646,23 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u4 x s8 -> s32 (dp4a), fp32 fold", "data": "synthetic",
-        "config": workload_config(world, tp),
+        "config": dict(workload_config(world, tp), launch_form=(
+            f"{len(chains)} persistent chained launches per step ({args.chain} layer(s) = {4 * args.chain} grouped projections each, "
+            "qgemm_gemv_chain); every projection waits for its predecessor to complete on the whole device" if chains else
+            f"{launches_per_step} launches per step, one per (grouped) projection")),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT,
                 "h2d_bytes_per_step": sum(v.numel() * 4 for v in acts_host.values()),
                 "d2h_bytes_per_step": total_out * 4, "ms_per_step": ms_e2e / args.steps,
+                "d2h": (f"every {args.d2h_chunk_layers} layers on a side stream, overlapped with the following layers; the step "
+                        "ends when the last slice has landed") if (groups and not chains and plan is None and args.d2h_chunk_layers > 0)
+                       else "one copy at the end of the step",
                 "api": "quant_gemm.quantize_q8_1 + quant_gemm.gemm (python mirror of the reference extension) "
                        "-> C ABI; weights resident in HBM like the reference API (device pointers)"},
         "gpu_launches": int(launches_per_step * args.steps),
         "gpu_launches_e2e": int(launches_per_e2e * args.steps),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "traffic_source": traffic_src, "kernel": "gemv_kernel<Q4_0,1>", "peak_source": peak_src,
+                     "traffic": traffic, "traffic_source": traffic_src, "kernel": "gemv_chain_kernel<Q4_0>" if chains else "gemv_kernel<Q4_0,1>", "peak_source": peak_src,
                      "avg_launch_us": per_launch_us, "algorithmic_bytes_per_launch": per_launch_bytes,
                      "frac_of_nominal_8000": achieved / 8000.0},
         "oracle_check_max_norm_err": check,

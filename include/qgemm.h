@@ -60,6 +60,11 @@ extern "C" {
 #define QGEMM_Q81_ROUND_EVEN 1u  /* __float2int_rn(): include/quantize.h:302-337 GPU kernel   */
 #define QGEMM_Q81_S_FROM_QSUM 2u /* s = half(sum(q) * d): tests/framework/test_framework.cuh:195-225 */
 #define QGEMM_Q81_CLAMP127 4u    /* clamp q to [-127,127]: python ext gemm_ops.cu:75-110, framework */
+#define QGEMM_Q81_TREE_SUM 8u    /* s = pairwise tree sum (i,i+16),(i,i+8)..: kernels/gemm/gemm_fused.cuh:96-127  */
+#define QGEMM_Q81_ID_FROM_HALF_D 16u /* 1/d from the fp16-rounded d, int8 narrowing before the clamp: gemm_fused.cuh:131-140 */
+#define QGEMM_Q81_ZERO_D1 32u    /* all-zero block stores d = 1.0: schemas/definitions/quantization/quantize_q8_1.json */
+/* quantize_fp16_to_q8_1_smem(), the in-kernel quantizer of gemm_q4_0_fp16_fused (gemm_fused.cuh:76-143), bit for bit: */
+#define QGEMM_Q81_FUSED_F16 (QGEMM_Q81_TREE_SUM | QGEMM_Q81_ID_FROM_HALF_D | QGEMM_Q81_CLAMP127)
 
 /* ---- GEMM flags ----------------------------------------------------------- */
 #define QGEMM_MS_EXACT 0x1u     /* q4_1/q5_1: + m*s (llama.cpp-true) instead of the
@@ -118,6 +123,12 @@ QGEMM_API const char *qgemm_last_error_detail(void);
  * Default flags reproduce quantize_row_q8_1_ref() byte for byte.
  */
 QGEMM_API int qgemm_quantize_q8_1(const float *x, void *y, int64_t rows, int64_t K, uint32_t flags, void *stream);
+/*
+ * Same from fp16 input x_f16[rows][K] (2-byte aligned): every element enters as __half2float(x), then exactly the
+ * arithmetic `flags` selects.  With QGEMM_Q81_FUSED_F16 the bytes are those quantize_fp16_to_q8_1_smem() writes
+ * (kernels/gemm/gemm_fused.cuh:76-143), so quantize_q8_1_f16 + qgemm_gemm reproduces gemm_q4_0_fp16_fused (:157-338).
+ */
+QGEMM_API int qgemm_quantize_q8_1_f16(const void *x_f16, void *y, int64_t rows, int64_t K, uint32_t flags, void *stream);
 
 /*
  * y = quantize_q8_1(silu(x) * gate): the SwiGLU neighbour of the FFN down projection folded into its quantizer
@@ -216,6 +227,50 @@ QGEMM_API int qgemm_prepack_weights(int wtype, const void *weight, int F, int K,
  */
 QGEMM_API int qgemm_gemm_group(int wtype, const void *act_q8_1, int nmat, const void *const *weights, float *const *Cs,
                                const int *Fs, int T, int K, int64_t ldc_t, int64_t ldc_f, uint32_t flags, void *stream);
+
+/*
+ * Chained decode GEMVs (one token): `nsteps` grouped GEMVs executed in order by ONE persistent launch, with the
+ * dependencies between them resolved on the device.  Equivalent to nsteps qgemm_gemm_group() calls (T = 1,
+ * ldc_t ignored) issued back to back on `stream`, and to the launches the reference would issue for them
+ * (kernels/gemm/gemm_warp_optimized.cuh:377-1210, one launch per projection): same sums, same order, same bits.
+ * What changes is the cost of the boundaries: the weight stream of step k+1 is already running while step k drains
+ * and while the activations of step k+1 are fetched.
+ *
+ * A step's activations are either
+ *   - act_q8_1: ready-made block_q8_1[K/32], or
+ *   - act_f32 (act_q8_1 == NULL): K floats that the kernel quantizes itself with quantize_q8_1's default arithmetic
+ *     (include/quantize.h:165-193) -- typically the C of an EARLIER step of the same chain, so the quantize launch
+ *     between two projections disappears; with gate_f32 != NULL the quantized value is silu(act_f32[i]) * gate_f32[i]
+ *     (kernels/activation/silu.cuh:97-108), the SwiGLU in front of the down projection.
+ * Step flags: QGEMM_INPUTS_READY = this step's activations are not produced by an earlier step of the chain (nor by
+ * work still in flight when the chain starts computing): it may begin before the earlier steps have finished.  Without
+ * it a step starts when every earlier step has completed on the whole device (stream-order semantics).
+ *
+ * sync: qgemm_gemv_chain_sync_bytes(nsteps) bytes of device memory, 4-byte aligned, ZERO before the first use; the
+ * kernel leaves it zero, so one buffer serves every chain launched on the same stream.  Chains on different streams need
+ * different buffers.  Lists the persistent kernel cannot take (T > 1 shapes, rows that are not 16-byte multiples, K too
+ * long for register-resident activations, fewer rows than CTAs, QGEMM_MS_EXACT) are run as one launch per step --
+ * same results; qgemm_last_path() tells (QGEMM_PATH_GEMV | QGEMM_PATH_CHAINED when the persistent kernel ran).
+ * New entry: the reference has no multi-GEMM launch; it is the successor of its per-projection launch sequence.
+ */
+#define QGEMM_CHAIN_MAX_MATS 3
+typedef struct qgemm_chain_step {
+    const void *act_q8_1;                       /* or NULL: quantize act_f32 in the kernel */
+    const float *act_f32;
+    const float *gate_f32;                      /* optional, with act_f32 */
+    int nmat;                                   /* 1..QGEMM_CHAIN_MAX_MATS matrices that share these activations */
+    const void *weights[QGEMM_CHAIN_MAX_MATS];
+    float *C[QGEMM_CHAIN_MAX_MATS];             /* C[m][f * ldc_f] */
+    int F[QGEMM_CHAIN_MAX_MATS];
+    int K;
+    int64_t ldc_f;
+    uint32_t flags;                             /* 0 or QGEMM_INPUTS_READY */
+} qgemm_chain_step;
+#define QGEMM_PATH_CHAINED 0x1000000u
+QGEMM_API size_t qgemm_gemv_chain_sync_bytes(int nsteps);
+QGEMM_API int qgemm_gemv_chain_max_steps(void);
+QGEMM_API int qgemm_gemv_chain(int wtype, const qgemm_chain_step *steps, int nsteps, uint32_t flags, void *sync,
+                               size_t sync_bytes, void *stream);
 
 /*
  * One-shot hint for the calling thread's NEXT decode-path qgemm_gemm*() call: once that launch

@@ -614,7 +614,10 @@ cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, i
         }
 #endif
         p.nmat = 0;
-        if (group) {
+        if (group && group->nmat == 1) {   // a group of one is a plain GEMV (the kernel reads wgt / C when nmat <= 1)
+            p.wgt = (const uint8_t*)group->wgt[0];
+            p.C = group->C[0] + (int64_t)t0 * ldc_t;
+        } else if (group) {
             p.nmat = group->nmat;
             p.fstart[0] = 0;
             for (int m = 0; m < group->nmat; m++) {
@@ -640,6 +643,420 @@ cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, i
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
+}
+
+
+// ===========================================================================================================
+// Chained decode GEMVs: ONE persistent launch walks a list of steps (each a GEMV or a group of GEMVs that share
+// their activations), with device-side dependencies between the steps.  A chain of separate launches pays, per
+// launch, the kernel boundary, an empty weight ring and the activation prologue (profiles/r02_decode_timeline.md:
+// ~2.3 us on top of a 4.7 us stream); here the producer warp never stops -- while the consumers of a CTA sit in
+// the barrier between two steps and fetch the next step's activations, the ring fills with the next step's
+// weights -- so the boundary costs the consumers' catch-up instead of an idle HBM.
+//   * same consumer code as gemv_kernel (one token, activations in registers), instantiated per (PPL, kFull)
+//     and selected per step: the steps of a chain may differ in K and F
+//   * a step that waits (QGEMM_INPUTS_READY not set) starts only after every CTA has finished every earlier
+//     step: per-step arrival counters in `sync` (device fence + barrier + one atomic per CTA and step; acquire
+//     spin by one thread).  All CTAs are co-resident (the host clamps the grid to the occupancy).
+//   * a step's activations are either ready-made q8_1 blocks (one bulk copy per CTA) or quantized inside the kernel from
+//     an fp32 vector -- typically the output of an earlier step of the same chain, optionally through SwiGLU
+//     (silu(x) * gate) -- with quantize_q8_1's arithmetic (include/quantize.h:165-193, default flags), every CTA
+//     for itself: the quantize launch between two projections disappears
+//   * counters return to zero: the last CTA to leave clears them
+// ===========================================================================================================
+constexpr int kChainMaxSteps = 160;
+constexpr int kChainMaxMat = 3;
+
+struct ChainStep {
+    const uint8_t* act;              // q8_1 [nb][36 B], or null: quantize from x (and gate)
+    const float* x;                  // fp32 [K] source of the activations when act == null
+    const float* gate;               // optional: quantize silu(x) * gate
+    const uint8_t* wgt[kChainMaxMat];
+    float* C[kChainMaxMat];
+    int fstart[kChainMaxMat + 1];    // rows numbered across the step's matrices
+    int nb;
+    int ldc_f;                       // C[m][f * ldc_f]  (one token)
+    unsigned char nmat, RT, WPR, ppl, full, wait;
+};
+
+template <int NS> struct ChainParams {
+    int nsteps;
+    int stages, stage_bytes;
+    uint32_t act_bytes;              // shared memory reserved for the raw activations (largest step)
+    unsigned* sync;                  // [nsteps + 1], zero on entry and on exit
+    int pdl;
+    const uint8_t* pf_ptr;
+    unsigned long long pf_bytes;
+    ChainStep st[NS];
+};
+constexpr int kChainSmall = 8;   // short chains (a layer) do not carry the long list's 16 KB of parameters
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const unsigned* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct ChainTile { int m, local, rows; };
+__device__ __forceinline__ ChainTile chain_tile_at(const ChainStep& st, int r0, int r_end) {
+    int m = 0;
+    while (m + 1 < st.nmat && r0 >= st.fstart[m + 1]) m++;
+    return {m, r0 - st.fstart[m], min(min((int)st.RT, r_end - r0), st.fstart[m + 1] - r0)};
+}
+
+// quantize_q8_1 of one block (default flags: roundf, clamp -128, s = fp16 of the sequential fp32 sum), 9 words out
+__device__ __forceinline__ int chain_round_half_away(float v) {
+    const float t = truncf(v);
+    const float r = v - t;
+    int q = __float2int_rz(t);
+    if (fabsf(r) >= 0.5f) q += (v < 0.0f) ? -1 : 1;
+    return q;
+}
+__device__ __forceinline__ void chain_quantize_block(const float* x, const float* gate, uint32_t* out) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const float4 a = __ldcg(reinterpret_cast<const float4*>(x) + i);
+        v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
+    }
+    if (gate) {   // silu_mul_f32_kernel's operation sequence (kernels/activation/silu.cuh:97-108)
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float4 g = __ldcg(reinterpret_cast<const float4*>(gate) + i);
+            v[4 * i] = __fmul_rn(__fdiv_rn(v[4 * i], __fadd_rn(1.0f, expf(-v[4 * i]))), g.x);
+            v[4 * i + 1] = __fmul_rn(__fdiv_rn(v[4 * i + 1], __fadd_rn(1.0f, expf(-v[4 * i + 1]))), g.y);
+            v[4 * i + 2] = __fmul_rn(__fdiv_rn(v[4 * i + 2], __fadd_rn(1.0f, expf(-v[4 * i + 2]))), g.z);
+            v[4 * i + 3] = __fmul_rn(__fdiv_rn(v[4 * i + 3], __fadd_rn(1.0f, expf(-v[4 * i + 3]))), g.w);
+        }
+    }
+    float amax = 0.0f, sum = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        amax = fmaxf(amax, fabsf(v[j]));
+        sum = __fadd_rn(sum, v[j]);
+    }
+    const float d = __fdiv_rn(amax, 127.0f);
+    const float id = (d > 0.0f) ? __fdiv_rn(1.0f, d) : 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        uint32_t packed = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int q = max(-128, min(127, chain_round_half_away(__fmul_rn(v[w * 4 + c], id))));
+            packed |= (uint32_t)(q & 0xff) << (8 * c);
+        }
+        out[1 + w] = packed;
+    }
+    out[0] = (uint32_t)__half_as_ushort(__float2half_rn(d)) | ((uint32_t)__half_as_ushort(__float2half_rn(sum)) << 16);
+}
+
+// the consumer warps' share of one step; ring position (s, ph) and slot parity carry over from step to step
+template <int WT, int PPL, bool kFull>
+__device__ __forceinline__ void chain_consume(const ChainStep& st, const int r_begin, const int r_end, const uint32_t* araw,
+                                              const uint8_t* stage0, const int stage_bytes, const int nstages, uint64_t* full,
+                                              uint64_t* empty, float* slots, int& s, uint32_t& ph, int& spar) {
+    using Fm = Fmt<WT>;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nb = st.nb, np = nb >> 1;
+    const int WPR = st.WPR;
+    const int rpp = kGemvWarps / WPR;
+    const int rslot = warp / WPR, sub = warp - rslot * WPR;
+    const size_t rowbytes = (size_t)nb * Fm::bytes;
+
+    ActPair areg[PPL];
+#pragma unroll
+    for (int j = 0; j < PPL; j++) {
+        const int pg = (j * WPR + sub) * 32 + lane;
+        if (kFull || j < PPL - 1 || pg < np) {
+            const uint32_t* w = araw + (size_t)(2 * pg) * 9;
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+                const uint32_t ds = w[9 * b];
+                areg[j].s[b] = prep_act_scale<WT, false>(half_bits_to_float(ds), half_bits_to_float(ds >> 16));
+#pragma unroll
+                for (int i = 0; i < 8; i++) areg[j].q[b][i] = (int)w[9 * b + 1 + i];
+            }
+        }
+    }
+    for (int g0 = r_begin; g0 < r_end;) {
+        const ChainTile tr = chain_tile_at(st, g0, r_end);
+        const int r0 = tr.local, rows = tr.rows;
+        float* Cm = st.C[tr.m];
+        g0 += rows;
+        ptx::mbar_wait(&full[s], ph);
+        const uint8_t* tile = stage0 + (size_t)s * stage_bytes;
+        for (int pass = 0; pass * rpp < rows; pass++) {
+            const int r = pass * rpp + rslot;
+            float acc = 0.f;
+            if (r < rows) {
+                const uint8_t* rowp = tile + (size_t)r * rowbytes;
+#pragma unroll
+                for (int j = 0; j < PPL; j++) {
+                    const int pg = (j * WPR + sub) * 32 + lane;
+                    if (kFull || j < PPL - 1 || pg < np) {
+                        uint32_t x[Pair<WT>::words];
+                        uint32_t w[2][8];
+                        WScale ws[2];
+                        load_pair<WT>(rowp + (size_t)pg * (2 * Fm::bytes), x);
+                        expand_pair<WT>(x, w, ws);
+                        acc = fold_block_pre<WT>(acc, pair_sumi<WT>(w[0], areg[j].q[0]), ws[0], areg[j].s[0]);
+                        acc = fold_block_pre<WT>(acc, pair_sumi<WT>(w[1], areg[j].q[1]), ws[1], areg[j].s[1]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (WPR == 1) {
+                if (r < rows && lane == 0) Cm[(int64_t)(r0 + r) * st.ldc_f] = acc;
+            } else {
+                float* sl = slots + spar * (kGemvWarps * 8);
+                if (lane == 0) sl[warp * 8] = acc;
+                ptx::bar_sync(2 + rslot, WPR * 32);
+                if (sub == 0 && lane == 0 && r < rows) {
+                    float v = 0.f;
+                    for (int k = 0; k < WPR; k++) v += sl[(rslot * WPR + k) * 8];
+                    Cm[(int64_t)(r0 + r) * st.ldc_f] = v;
+                }
+                spar ^= 1;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&empty[s]);
+        if (++s == nstages) { s = 0; ph ^= 1; }
+    }
+}
+
+template <int WT, int NS>
+__global__ void __launch_bounds__(kGemvThreads, kGemvCtasPerSm) gemv_chain_kernel(const __grid_constant__ ChainParams<NS> p) {
+    using Fm = Fmt<WT>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + kGemvMaxStages;
+    float* slots = reinterpret_cast<float*>(smem + kGemvSlotsOff);
+    uint64_t* abar = reinterpret_cast<uint64_t*>(smem + kGemvAbarOff);
+    uint8_t* a_raw = smem + kGemvActOff;
+    uint8_t* stage0 = smem + (((uint32_t)kGemvActOff + p.act_bytes + 127u) & ~127u);
+    const unsigned grid = gridDim.x;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.stages; s++) {
+            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&empty[s], kGemvWarps);
+        }
+        ptx::mbar_init(abar, 1);
+        ptx::fence_mbar_init();
+    }
+    __syncthreads();
+    if (p.pdl) ptx::griddep_launch_dependents();
+
+    if (warp == kGemvWarps) {
+        // ================= producer: one weight stream across all steps; never waits for a step boundary
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int k = 0; k < p.nsteps; k++) {
+                const ChainStep& st = p.st[k];
+                const int F = st.fstart[st.nmat];
+                const int r_begin = (int)(((int64_t)F * blockIdx.x) / grid);
+                const int r_end = (int)(((int64_t)F * (blockIdx.x + 1)) / grid);
+                const size_t rowbytes = (size_t)st.nb * Fm::bytes;
+                for (int r0 = r_begin; r0 < r_end;) {
+                    const ChainTile tr = chain_tile_at(st, r0, r_end);
+                    const uint8_t* src = st.wgt[tr.m] + (size_t)tr.local * rowbytes;
+                    const uint32_t bytes = (uint32_t)(tr.rows * rowbytes);
+                    ptx::mbar_wait(&empty[s], ph ^ 1);
+                    ptx::mbar_arrive_expect_tx(&full[s], bytes);
+                    ptx::bulk_g2s(stage0 + (size_t)s * p.stage_bytes, src, bytes, &full[s]);
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
+                    r0 += tr.rows;
+                }
+            }
+            if (p.pf_ptr) {
+                const unsigned long long chunk = ((p.pf_bytes / grid) + 15ull) & ~15ull;
+                unsigned long long off = chunk * blockIdx.x;
+                const unsigned long long end = min(off + chunk, p.pf_bytes & ~15ull);
+                for (; off < end; off += 16384ull)
+                    ptx::bulk_prefetch_l2(p.pf_ptr + off, (uint32_t)min(16384ull, end - off));
+            }
+        }
+        return;
+    }
+
+    // ================= consumers
+    if (p.pdl) ptx::griddep_wait();   // activations, C and the counters may still belong to the previous launch
+    int s = 0, spar = 0;
+    uint32_t ph = 0, aph = 0;
+    for (int k = 0; k < p.nsteps; k++) {
+        const ChainStep& st = p.st[k];
+        const int F = st.fstart[st.nmat];
+        const int r_begin = (int)(((int64_t)F * blockIdx.x) / grid);
+        const int r_end = (int)(((int64_t)F * (blockIdx.x + 1)) / grid);
+        if (st.act) {
+            if (tid == 0) {
+                if (st.wait && k > 0)
+                    while (ld_acquire_gpu(p.sync + (k - 1)) < grid) __nanosleep(20);
+                const uint32_t bytes = (uint32_t)st.nb * 36u;
+                ptx::mbar_arrive_expect_tx(abar, bytes);
+                ptx::bulk_g2s(a_raw, st.act, bytes, abar);
+            }
+            ptx::mbar_wait(abar, aph);
+            aph ^= 1;
+        } else {
+            if (st.wait && k > 0) {
+                if (tid == 0)
+                    while (ld_acquire_gpu(p.sync + (k - 1)) < grid) __nanosleep(20);
+                ptx::bar_sync(1, kGemvWarps * 32);
+            }
+            for (int b = tid; b < st.nb; b += kGemvWarps * 32)
+                chain_quantize_block(st.x + (size_t)b * 32, st.gate ? st.gate + (size_t)b * 32 : nullptr,
+                                     reinterpret_cast<uint32_t*>(a_raw) + (size_t)b * 9);
+            ptx::fence_proxy_async();   // a later step may overwrite a_raw with a bulk copy
+            ptx::bar_sync(1, kGemvWarps * 32);
+        }
+        const uint32_t* araw = reinterpret_cast<const uint32_t*>(a_raw);
+#define QG_CHAIN_CASE(P, FULL) \
+    chain_consume<WT, P, FULL>(st, r_begin, r_end, araw, stage0, p.stage_bytes, p.stages, full, empty, slots, s, ph, spar)
+        if (st.full) {
+            if (st.ppl == 1) QG_CHAIN_CASE(1, true);
+            else if (st.ppl == 2) QG_CHAIN_CASE(2, true);
+            else QG_CHAIN_CASE(3, true);
+        } else {
+            if (st.ppl == 1) QG_CHAIN_CASE(1, false);
+            else if (st.ppl == 2) QG_CHAIN_CASE(2, false);
+            else QG_CHAIN_CASE(3, false);
+        }
+#undef QG_CHAIN_CASE
+        // this CTA's share of step k is stored: publish it (and free a_raw for the next step)
+        if (lane == 0) __threadfence();   // lane 0 of every warp is the one that stores
+        ptx::bar_sync(1, kGemvWarps * 32);
+        if (tid == 0) atomicAdd(p.sync + k, 1u);
+    }
+    if (tid == 0) {
+        // the last CTA to leave has seen every other CTA past its last wait: the counters can go back to zero
+        if (atomicAdd(p.sync + p.nsteps, 1u) == grid - 1) {
+            for (int k = 0; k <= p.nsteps; k++) p.sync[k] = 0u;
+        }
+    }
+}
+
+struct ChainStepHost {
+    const void* act; const float* x; const float* gate;
+    int nmat; const void* wgt[kChainMaxMat]; float* C[kChainMaxMat]; int F[kChainMaxMat];
+    int K; int ldc_f; int wait;
+};
+
+int gemv_chain_max_steps() { return kChainMaxSteps; }
+
+// Can this list run as one persistent launch?  (one token, register-resident activations for every step, rows and
+// activations bulk-copyable).  Fills *out with the kernel parameters.
+template <int NS>
+static bool gemv_chain_plan(int wtype, const ChainStepHost* steps, int nsteps, int grid, ChainParams<NS>* out, size_t* smem) {
+    if (nsteps < 1 || nsteps > NS) return false;
+    int stage_bytes = 0;
+    size_t act_bytes = 0;
+    for (int k = 0; k < nsteps; k++) {
+        const ChainStepHost& h = steps[k];
+        if (h.nmat < 1 || h.nmat > kChainMaxMat) return false;
+        const int nb = h.K / 32;
+        int Ftot = 0;
+        for (int m = 0; m < h.nmat; m++) {
+            if (!gemv_supported(wtype, h.act ? h.act : (const void*)h.x, h.wgt[m], h.F[m], h.K)) return false;
+            Ftot += h.F[m];
+        }
+        if (h.act) {
+            if (reinterpret_cast<uintptr_t>(h.act) % 16 != 0 || ((size_t)nb * kQ81Bytes) % 16 != 0) return false;
+        } else {
+            if (reinterpret_cast<uintptr_t>(h.x) % 16 != 0 || (h.gate && reinterpret_cast<uintptr_t>(h.gate) % 16 != 0)) return false;
+        }
+        GemvPlan pl;
+        if (!gemv_plan(wtype, 1, Ftot, h.K, grid, true, &pl) || pl.tt != 1 || pl.ppl < 1 || pl.ppl > 3) return false;
+        ChainStep& st = out->st[k];
+        st = ChainStep{};
+        st.act = (const uint8_t*)h.act; st.x = h.x; st.gate = h.gate;
+        st.fstart[0] = 0;
+        for (int m = 0; m < h.nmat; m++) {
+            st.wgt[m] = (const uint8_t*)h.wgt[m];
+            st.C[m] = h.C[m];
+            st.fstart[m + 1] = st.fstart[m] + h.F[m];
+        }
+        for (int m = h.nmat; m < kChainMaxMat; m++) st.fstart[m + 1] = st.fstart[h.nmat];
+        st.nb = nb; st.ldc_f = h.ldc_f;
+        st.nmat = (unsigned char)h.nmat; st.RT = (unsigned char)pl.rt; st.WPR = (unsigned char)pl.wpr; st.ppl = (unsigned char)pl.ppl;
+        st.full = (nb / 2) == pl.ppl * pl.wpr * 32 ? 1 : 0;
+        st.wait = h.wait ? 1 : 0;
+        stage_bytes = max(stage_bytes, (int)(((size_t)pl.rt * nb * block_bytes(wtype) + 127) / 128 * 128));
+        act_bytes = max(act_bytes, (size_t)nb * kQ81Bytes);
+    }
+    const size_t fixed = (((size_t)kGemvActOff + act_bytes + 127) & ~(size_t)127);
+    if (fixed + 2 * (size_t)stage_bytes > (size_t)kGemvSmemBudget) return false;
+    int stages = (int)(((size_t)kGemvSmemBudget - fixed) / stage_bytes);
+    stages = max(2, min(kGemvMaxStages, stages));
+    if (const char* e = QGEMM_ENV("QGEMM_CHAIN_STAGES")) stages = max(2, min(stages, atoi(e)));  // tuning aid
+    out->nsteps = nsteps;
+    out->stages = stages;
+    out->stage_bytes = stage_bytes;
+    out->act_bytes = (uint32_t)act_bytes;
+    *smem = fixed + (size_t)stages * stage_bytes;
+    return true;
+}
+
+template <int WT, int NS>
+static cudaError_t launch_chain_wt(const ChainParams<NS>& p, size_t smem, int num_sms, cudaStream_t st) {
+    auto kernel = gemv_chain_kernel<WT, NS>;
+    if (cudaError_t e = smem_optin(reinterpret_cast<const void*>(kernel), smem)) return e;
+    // the grid must be co-resident (steps wait for each other inside the kernel)
+    int occ = 0;
+    if (cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kGemvThreads, smem)) return e;
+    if (occ < kGemvCtasPerSm) return cudaErrorLaunchOutOfResources;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(kGemvCtasPerSm * num_sms);
+    cfg.blockDim = dim3(kGemvThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = p.pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p);
+    note_launch();
+    return e;
+}
+
+template <int NS>
+static cudaError_t launch_chain_ns(int wtype, const ChainStepHost* steps, int nsteps, uint32_t flags, unsigned* sync, int num_sms,
+                                   cudaStream_t st, const void* pf_ptr, size_t pf_bytes) {
+    static thread_local ChainParams<NS> p;   // up to 16 KB: not on the stack of a caller we do not know
+    size_t smem = 0;
+    const int grid = kGemvCtasPerSm * num_sms;
+    if (!gemv_chain_plan<NS>(wtype, steps, nsteps, grid, &p, &smem)) return cudaErrorNotSupported;
+    p.sync = sync;
+    p.pdl = (flags & QGEMM_WEIGHTS_STATIC) ? 1 : 0;
+    p.pf_ptr = reinterpret_cast<uintptr_t>(pf_ptr) % 16 == 0 ? (const uint8_t*)pf_ptr : nullptr;
+    p.pf_bytes = pf_bytes;
+    switch (wtype) {
+    case QGEMM_TYPE_Q4_0: return launch_chain_wt<QGEMM_TYPE_Q4_0, NS>(p, smem, num_sms, st);
+    case QGEMM_TYPE_Q4_1: return launch_chain_wt<QGEMM_TYPE_Q4_1, NS>(p, smem, num_sms, st);
+    case QGEMM_TYPE_Q5_0: return launch_chain_wt<QGEMM_TYPE_Q5_0, NS>(p, smem, num_sms, st);
+    case QGEMM_TYPE_Q5_1: return launch_chain_wt<QGEMM_TYPE_Q5_1, NS>(p, smem, num_sms, st);
+    case QGEMM_TYPE_Q8_0: return launch_chain_wt<QGEMM_TYPE_Q8_0, NS>(p, smem, num_sms, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+// cudaErrorNotSupported: the list does not fit the persistent kernel (the caller launches the steps one by one)
+cudaError_t launch_gemv_chain(int wtype, const ChainStepHost* steps, int nsteps, uint32_t flags, unsigned* sync, int num_sms,
+                              cudaStream_t st, const void* pf_ptr, size_t pf_bytes) {
+    if ((flags & QGEMM_MS_EXACT) && (wtype == QGEMM_TYPE_Q4_1 || wtype == QGEMM_TYPE_Q5_1)) return cudaErrorNotSupported;
+    const int grid = kGemvCtasPerSm * num_sms;
+    for (int k = 0; k < nsteps; k++) {   // every CTA owns rows of every step
+        int Ftot = 0;
+        for (int m = 0; m < steps[k].nmat && m < kChainMaxMat; m++) Ftot += steps[k].F[m];
+        if (Ftot < grid) return cudaErrorNotSupported;
+    }
+    if (nsteps <= kChainSmall) return launch_chain_ns<kChainSmall>(wtype, steps, nsteps, flags, sync, num_sms, st, pf_ptr, pf_bytes);
+    return launch_chain_ns<kChainMaxSteps>(wtype, steps, nsteps, flags, sync, num_sms, st, pf_ptr, pf_bytes);
 }
 
 }  // namespace qgemm

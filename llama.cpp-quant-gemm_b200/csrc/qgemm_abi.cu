@@ -7,6 +7,7 @@
 #include <map>
 #include <mutex>
 #include <utility>
+#include <vector>
 
 #include "qgemm_common.cuh"
 
@@ -14,6 +15,7 @@ namespace qgemm {
 
 // kernels (defined in the other translation units)
 cudaError_t launch_quantize_q8_1(const float*, void*, int64_t nblocks, uint32_t flags, cudaStream_t);
+cudaError_t launch_quantize_q8_1_f16(const void*, void*, int64_t nblocks, uint32_t flags, cudaStream_t);
 cudaError_t launch_quantize_weight(int wtype, const float*, void*, int64_t nblocks, uint32_t flags, cudaStream_t);
 cudaError_t launch_dequantize(int type, const void*, float*, int64_t nblocks, cudaStream_t);
 cudaError_t launch_gemm_sequential(int wtype, const void* act, const void* wgt, float* C, int T, int F, int K,
@@ -28,6 +30,14 @@ struct GemvGroup { int nmat; const void* wgt[8]; float* C[8]; int F[8]; };
 cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
                         int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t, const PeerOut* peer, const void* pf_ptr,
                         size_t pf_bytes, const GemvGroup* group);
+struct ChainStepHost {
+    const void* act; const float* x; const float* gate;
+    int nmat; const void* wgt[3]; float* C[3]; int F[3];
+    int K; int ldc_f; int wait;
+};
+int gemv_chain_max_steps();
+cudaError_t launch_gemv_chain(int wtype, const ChainStepHost* steps, int nsteps, uint32_t flags, unsigned* sync, int num_sms,
+                              cudaStream_t st, const void* pf_ptr, size_t pf_bytes);
 bool gemv_mma_supported(int wtype, const void* act, const void* wgt, int T, int F, int K);
 cudaError_t launch_gemv_mma(int wtype, const void* act, const void* wgt, float* C, int T, int F, int K, int64_t ldc_t,
                             int64_t ldc_f, uint32_t flags, int num_sms, cudaStream_t, const PeerOut* peer = nullptr);
@@ -327,6 +337,17 @@ int qgemm_quantize_q8_1(const float* x, void* y, int64_t rows, int64_t K, uint32
     return e == cudaSuccess ? QGEMM_OK : cuda_fail(e, "quantize_q8_1 launch");
 }
 
+int qgemm_quantize_q8_1_f16(const void* x_f16, void* y, int64_t rows, int64_t K, uint32_t flags, void* stream) {
+    if (rows < 0 || K < 0 || (K % kQK) != 0) return QGEMM_E_BADARG;
+    if (rows == 0 || K == 0) return QGEMM_OK;
+    if (!x_f16 || !y) return QGEMM_E_BADARG;
+    if (!aligned(x_f16, 2) || !aligned(y, 4)) return QGEMM_E_ALIGN;
+    DeviceInfo dev;
+    if (int rc = device_check(&dev)) return rc;
+    const cudaError_t e = launch_quantize_q8_1_f16(x_f16, y, rows * (K / kQK), flags, (cudaStream_t)stream);
+    return e == cudaSuccess ? QGEMM_OK : cuda_fail(e, "quantize_q8_1_f16 launch");
+}
+
 int qgemm_quantize_weight(int wtype, const float* x, void* y, int64_t rows, int64_t K, uint32_t flags, void* stream) {
     if (!is_weight_type(wtype) || rows < 0 || K < 0 || (K % kQK) != 0) return QGEMM_E_BADARG;
     if (rows == 0 || K == 0) return QGEMM_OK;
@@ -401,6 +422,74 @@ int qgemm_gemm_group(int wtype, const void* act_q8_1, int nmat, const void* cons
     t_pf_bytes = 0;
     t_last_path = QGEMM_PATH_GEMV;
     return e == cudaSuccess ? QGEMM_OK : cuda_fail(e, "gemm_group launch");
+}
+
+size_t qgemm_gemv_chain_sync_bytes(int nsteps) { return nsteps < 1 ? 0 : sizeof(unsigned) * ((size_t)nsteps + 1); }
+int qgemm_gemv_chain_max_steps(void) { return gemv_chain_max_steps(); }
+
+int qgemm_gemv_chain(int wtype, const qgemm_chain_step* steps, int nsteps, uint32_t flags, void* sync, size_t sync_bytes,
+                     void* stream) {
+    if (!steps || nsteps < 1 || !is_weight_type(wtype)) return QGEMM_E_BADARG;
+    if (!sync || sync_bytes < qgemm_gemv_chain_sync_bytes(nsteps)) return QGEMM_E_WORKSPACE;
+    if (!aligned(sync, 4)) return QGEMM_E_ALIGN;
+    for (int k = 0; k < nsteps; k++) {
+        const qgemm_chain_step& s = steps[k];
+        if (s.nmat < 1 || s.nmat > QGEMM_CHAIN_MAX_MATS || s.K < 32 || (s.K % kQK) != 0) return QGEMM_E_BADARG;
+        if (!s.act_q8_1 && !s.act_f32) return QGEMM_E_BADARG;
+        if (s.act_q8_1 && (s.act_f32 || s.gate_f32)) return QGEMM_E_BADARG;
+        if (s.flags & ~QGEMM_INPUTS_READY) return QGEMM_E_BADARG;
+        if (s.ldc_f < 1 || s.ldc_f > 0x7fffffff) return QGEMM_E_BADARG;
+        for (int m = 0; m < s.nmat; m++) {
+            if (!s.weights[m] || !s.C[m] || s.F[m] < 1) return QGEMM_E_BADARG;
+            if (!aligned(s.weights[m], 2) || !aligned(s.C[m], 4)) return QGEMM_E_ALIGN;
+        }
+        if (s.act_q8_1 ? !aligned(s.act_q8_1, 4) : (!aligned(s.act_f32, 4) || !aligned(s.gate_f32, 4))) return QGEMM_E_ALIGN;
+    }
+    DeviceInfo dev;
+    if (int rc = device_check(&dev)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const void* pf_ptr = t_pf_ptr;
+    const size_t pf_bytes = t_pf_bytes;
+    t_pf_ptr = nullptr;
+    t_pf_bytes = 0;
+    if (nsteps <= gemv_chain_max_steps() && !(flags & (QGEMM_SEQUENTIAL | QGEMM_PATH_MASK) & ~QGEMM_PATH_GEMV)) {
+        std::vector<ChainStepHost> hs((size_t)nsteps);
+        for (int k = 0; k < nsteps; k++) {
+            const qgemm_chain_step& s = steps[k];
+            ChainStepHost& h = hs[(size_t)k];
+            h = ChainStepHost{};
+            h.act = s.act_q8_1; h.x = s.act_f32; h.gate = s.gate_f32;
+            h.nmat = s.nmat;
+            for (int m = 0; m < s.nmat; m++) { h.wgt[m] = s.weights[m]; h.C[m] = s.C[m]; h.F[m] = s.F[m]; }
+            h.K = s.K; h.ldc_f = (int)s.ldc_f; h.wait = (s.flags & QGEMM_INPUTS_READY) ? 0 : 1;
+        }
+        cudaError_t e = launch_gemv_chain(wtype, hs.data(), nsteps, flags, (unsigned*)sync, dev.sms, st, pf_ptr, pf_bytes);
+        if (e == cudaSuccess) {
+            t_last_path = QGEMM_PATH_GEMV | QGEMM_PATH_CHAINED;
+            return QGEMM_OK;
+        }
+        if (e != cudaErrorNotSupported) return cuda_fail(e, "gemv_chain launch");
+    }
+    // one launch per step (and a quantize launch in front of a step that brings fp32 activations): same results
+    for (int k = 0; k < nsteps; k++) {
+        const qgemm_chain_step& s = steps[k];
+        const void* act = s.act_q8_1;
+        void* tmp = nullptr;
+        if (!act) {
+            const size_t bytes = (size_t)(s.K / kQK) * kQ81Bytes;
+            if (cudaError_t e = cudaMallocAsync(&tmp, bytes, st)) return cuda_fail(e, "gemv_chain scratch");
+            cudaError_t e = s.gate_f32 ? launch_quantize_q8_1_silu_mul(s.act_f32, s.gate_f32, tmp, s.K / kQK, 0, st)
+                                       : launch_quantize_q8_1(s.act_f32, tmp, s.K / kQK, 0, st);
+            if (e != cudaSuccess) { cudaFreeAsync(tmp, st); return cuda_fail(e, "gemv_chain quantize"); }
+            note_launch();
+            act = tmp;
+        }
+        const uint32_t f = (flags & ~QGEMM_INPUTS_READY) | ((s.flags & QGEMM_INPUTS_READY) && s.act_q8_1 ? QGEMM_INPUTS_READY : 0u);
+        int rc = qgemm_gemm_group(wtype, act, s.nmat, s.weights, s.C, s.F, 1, s.K, 1, s.ldc_f, f, stream);
+        if (tmp) cudaFreeAsync(tmp, st);
+        if (rc) return rc;
+    }
+    return QGEMM_OK;
 }
 
 size_t qgemm_prepack_bytes(int wtype, int F, int K) {

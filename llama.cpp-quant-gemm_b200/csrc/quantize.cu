@@ -161,8 +161,77 @@ quantize_q8_1_kernel(const float* __restrict__ x, uint32_t* __restrict__ y, int6
     }
 }
 
+// ---------------------------------------------------------------------------
+// The remaining quantize_q8_1 flavours of the reference (SURVEY 8 row A2'), none of them on the hot path: one warp per
+// block, lane = element.
+//   QGEMM_Q81_TREE_SUM       s = pairwise tree sum (i, i+16), (i, i+8), (i, i+4), (i, i+2), (0, 1): the shared-memory
+//                            reduction of quantize_fp16_to_q8_1_smem (kernels/gemm/gemm_fused.cuh:96-127)
+//   QGEMM_Q81_ID_FROM_HALF_D 1/d from the fp16-rounded d, and q narrowed to int8 before the clamp (gemm_fused.cuh:131-140)
+//   QGEMM_Q81_ZERO_D1        an all-zero block stores d = 1.0 (schemas/definitions/quantization/quantize_q8_1.json)
+// kHalfIn: the input is fp16 (the reference's fused kernel reads half activations).
+// ---------------------------------------------------------------------------
+template <bool kHalfIn>
+__global__ void __launch_bounds__(256) quantize_q8_1_lanes_kernel(const void* __restrict__ xin, uint8_t* __restrict__ y, int64_t nblocks,
+                                                                  uint32_t flags) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b >= nblocks) return;
+    float v;
+    if constexpr (kHalfIn) v = __half2float(reinterpret_cast<const __half*>(xin)[b * 32 + lane]);
+    else v = reinterpret_cast<const float*>(xin)[b * 32 + lane];
+    float amax = fabsf(v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    float sum;
+    if (flags & QGEMM_Q81_TREE_SUM) {
+        sum = v;   // lane i < w adds lane i + w: the reference's tree, level by level
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum = __fadd_rn(sum, __shfl_down_sync(0xffffffffu, sum, o));
+        sum = __shfl_sync(0xffffffffu, sum, 0);
+    } else {
+        sum = 0.0f;   // element order, like quantize_row_q8_1_ref
+#pragma unroll
+        for (int j = 0; j < 32; j++) sum = __fadd_rn(sum, __shfl_sync(0xffffffffu, v, j));
+    }
+    float d = __fdiv_rn(amax, 127.0f);
+    float id = (d > 0.0f) ? __fdiv_rn(1.0f, d) : 0.0f;
+    if (flags & QGEMM_Q81_ID_FROM_HALF_D) {
+        const float dh = __half2float(__float2half_rn(d));
+        id = (dh != 0.0f) ? __fdiv_rn(1.0f, dh) : 0.0f;
+    }
+    if ((flags & QGEMM_Q81_ZERO_D1) && amax == 0.0f) d = 1.0f;
+    const float sv = __fmul_rn(v, id);
+    int q = (flags & QGEMM_Q81_ROUND_EVEN) ? __float2int_rn(sv) : round_half_away(sv);
+    if (flags & QGEMM_Q81_ID_FROM_HALF_D) q = (int)(int8_t)(q & 0xff);   // the reference's `(int8_t)roundf(..)` before its clamp
+    q = max((flags & QGEMM_Q81_CLAMP127) ? -127 : -128, min(127, q));
+    int sum_q = q;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum_q += __shfl_xor_sync(0xffffffffu, sum_q, o);
+    uint8_t* dst = y + b * 36;
+    dst[4 + lane] = (uint8_t)(q & 0xff);
+    if (lane == 0) {
+        const float s = (flags & QGEMM_Q81_S_FROM_QSUM) ? __fmul_rn(__int2float_rn(sum_q), d) : sum;
+        *reinterpret_cast<uint32_t*>(dst) =
+            (uint32_t)__half_as_ushort(__float2half_rn(d)) | ((uint32_t)__half_as_ushort(__float2half_rn(s)) << 16);
+    }
+}
+
+constexpr uint32_t kQ81LaneFlags = QGEMM_Q81_TREE_SUM | QGEMM_Q81_ID_FROM_HALF_D | QGEMM_Q81_ZERO_D1;
+
+cudaError_t launch_quantize_q8_1_f16(const void* x_f16, void* y, int64_t nblocks, uint32_t flags, cudaStream_t st) {
+    if (nblocks == 0) return cudaSuccess;
+    quantize_q8_1_lanes_kernel<true><<<(unsigned)((nblocks + 7) / 8), 256, 0, st>>>(x_f16, (uint8_t*)y, nblocks, flags);
+    note_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_quantize_q8_1(const float* x, void* y, int64_t nblocks, uint32_t flags, cudaStream_t st) {
     if (nblocks == 0) return cudaSuccess;
+    if (flags & kQ81LaneFlags) {   // the flavours of SURVEY row A2': not hot, own kernel
+        quantize_q8_1_lanes_kernel<false><<<(unsigned)((nblocks + 7) / 8), 256, 0, st>>>(x, (uint8_t*)y, nblocks, flags);
+        note_launch();
+        return cudaGetLastError();
+    }
     const int64_t per_cta = (int64_t)kQWarps * 32;
     const unsigned grid = (unsigned)((nblocks + per_cta - 1) / per_cta);
     if ((reinterpret_cast<uintptr_t>(x) & 15) == 0)

@@ -23,8 +23,8 @@ import torch
 
 from . import _lib
 from ._lib import (  # noqa: F401  (re-exported constants)
-    GEMM_FOLD_REFSEQ, GEMM_INPUTS_READY, GEMM_MS_EXACT, GEMM_WEIGHTS_PREPACKED, GEMM_SEQUENTIAL, GEMM_WEIGHTS_STATIC, PATH_AUTO, PATH_GEMV, PATH_GENERIC, PATH_MMA, PATH_TCGEN05,
-    Q81_CLAMP127, Q81_ROUND_AWAY, Q81_ROUND_EVEN, Q81_S_FROM_QSUM,
+    GEMM_FOLD_REFSEQ, GEMM_INPUTS_READY, GEMM_MS_EXACT, GEMM_WEIGHTS_PREPACKED, GEMM_SEQUENTIAL, GEMM_WEIGHTS_STATIC, PATH_AUTO, PATH_CHAINED, PATH_GEMV, PATH_GENERIC, PATH_MMA, PATH_TCGEN05,
+    Q81_CLAMP127, Q81_FUSED_F16, Q81_ID_FROM_HALF_D, Q81_ROUND_AWAY, Q81_ROUND_EVEN, Q81_S_FROM_QSUM, Q81_TREE_SUM, Q81_ZERO_D1,
     TYPE_Q4_0, TYPE_Q4_1, TYPE_Q5_0, TYPE_Q5_1, TYPE_Q8_0, TYPE_Q8_1,
 )
 
@@ -62,15 +62,31 @@ def _workspace(device: torch.device, nbytes: int) -> torch.Tensor | None:
     return ws
 
 
-def _quantize(x: torch.Tensor, qtype: int, flags: int) -> torch.Tensor:
+def _quantize(x: torch.Tensor, qtype: int, flags: int, out: torch.Tensor | None = None) -> torch.Tensor:
     _check(x.is_cuda, "Input must be a CUDA tensor")
+    if x.dtype == torch.float16 and qtype == TYPE_Q8_1:
+        # superset: fp16 activations (the input type of the reference's gemm_q4_0_fp16_fused, kernels/gemm/gemm_fused.cuh:157)
+        _check(x.dim() >= 1 and x.shape[-1] % 32 == 0, f"Last dimension must be divisible by 32, got {x.shape[-1]}")
+        x = x.contiguous()
+        K = x.shape[-1]
+        rows = x.numel() // K if K else 0
+        if out is None:
+            out = torch.empty(*x.shape[:-1], K // 32, 36, dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().qgemm_quantize_q8_1_f16(x.data_ptr(), out.data_ptr(), rows, K, flags, _stream(x))
+        _lib.raise_on_error(rc, "quantize")
+        return out
     _check(x.dtype == torch.float32, "Input must be float32")
     _check(x.dim() >= 1, "Input must have at least 1 dimension")
     K = x.shape[-1]
     _check(K % 32 == 0, f"Last dimension must be divisible by 32, got {K}")
     x = x.contiguous()
     rows = x.numel() // K if K else 0
-    out = torch.empty(*x.shape[:-1], K // 32, BLOCK_BYTES[qtype], dtype=torch.uint8, device=x.device)
+    if out is None:
+        out = torch.empty(*x.shape[:-1], K // 32, BLOCK_BYTES[qtype], dtype=torch.uint8, device=x.device)
+    else:   # superset: write into a caller-owned buffer (a decode runtime keeps its activation buffers)
+        _check(out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous()
+               and out.numel() == rows * (K // 32) * BLOCK_BYTES[qtype], "out must be a contiguous uint8 tensor of the quantized size")
     with torch.cuda.device(x.device):
         if qtype == TYPE_Q8_1:
             rc = _lib.lib().qgemm_quantize_q8_1(x.data_ptr(), out.data_ptr(), rows, K, flags, _stream(x))
@@ -85,13 +101,13 @@ def quantize_q4_0(x: torch.Tensor, flags: int = Q81_ROUND_AWAY) -> torch.Tensor:
     return _quantize(x, TYPE_Q4_0, flags)
 
 
-def quantize_q8_1(x: torch.Tensor, flags: int = Q81_ROUND_AWAY) -> torch.Tensor:
+def quantize_q8_1(x: torch.Tensor, flags: int = Q81_ROUND_AWAY, out: torch.Tensor | None = None) -> torch.Tensor:
     """FP32 [..., K] -> Q8_1 bytes [..., K//32, 36] (python/quant_gemm/__init__.py:46-56).
 
     Default flags reproduce include/quantize.h:165-193 byte for byte; pass
     Q81_CLAMP127 for the reference python extension's clamp (gemm_ops.cu:106-108).
     """
-    return _quantize(x, TYPE_Q8_1, flags)
+    return _quantize(x, TYPE_Q8_1, flags, out)
 
 
 def quantize_q8_1_silu_mul(x: torch.Tensor, gate: torch.Tensor, flags: int = Q81_ROUND_AWAY) -> torch.Tensor:
@@ -257,6 +273,90 @@ def gemm_group(weights_q: list, activation_q: torch.Tensor, Ms: list, N: int, K:
     return outs
 
 
+_chain_sync: dict[tuple[int, int], torch.Tensor] = {}
+
+
+class GemvChain:
+    """A list of one-token GEMV steps that ONE persistent launch executes in order (qgemm_gemv_chain): the successor of
+    the reference's launch-per-projection decode loop.  Each step is a dict:
+
+        weights : list of 1..3 quantized matrices that share the step's activations (fused q/k/v, gate/up)
+        Ms      : their row counts
+        K       : row length
+        act_q   : ready-made q8_1 activations [1, K/32, 36] u8          -- or --
+        act     : fp32 [K] (e.g. the `out` of an earlier step; quantized inside the kernel), optional `gate`: fp32 [K],
+                  the value quantized is then silu(act) * gate
+        outs    : optional list of [M, 1] fp32 outputs (allocated when absent)
+        ready   : True = the activations do not come from an earlier step: the step need not wait for them
+
+    The descriptor array is built once; calling the object launches it on the current stream."""
+
+    def __init__(self, steps: list, wtype: int, flags: int = 0):
+        _check(len(steps) >= 1, "GemvChain needs at least one step")
+        self.wtype, self.flags, self.n = wtype, flags, len(steps)
+        self.arr = (_lib.QgemmChainStep * self.n)()
+        self.outs, self._keep = [], []
+        dev = None
+        for k, st in enumerate(steps):
+            ws, Ms, K = [w.contiguous() for w in st["weights"]], list(st["Ms"]), int(st["K"])
+            _check(1 <= len(ws) <= 3 and len(Ms) == len(ws), "a chain step takes 1..3 matrices")
+            _check(K % 32 == 0, f"K must be divisible by 32, got {K}")
+            nb = K // 32
+            dev = ws[0].device
+            d = self.arr[k]
+            for m, (w, M) in enumerate(zip(ws, Ms)):
+                _check(w.is_cuda and w.dtype == torch.uint8 and w.numel() == M * nb * BLOCK_BYTES[wtype], "Weight shape mismatch")
+            outs = st.get("outs") or [torch.empty((M, 1), dtype=torch.float32, device=dev) for M in Ms]
+            for o, M in zip(outs, Ms):
+                _check(o.is_cuda and o.dtype == torch.float32 and o.is_contiguous() and o.numel() == M, "out must be M fp32 values")
+            if st.get("act_q") is not None:
+                a = st["act_q"].contiguous()
+                _check(a.is_cuda and a.dtype == torch.uint8 and a.numel() == nb * 36, "Activation shape mismatch")
+                d.act_q8_1 = a.data_ptr()
+                self._keep.append(a)
+            else:
+                a = st["act"]
+                _check(a.is_cuda and a.dtype == torch.float32 and a.is_contiguous() and a.numel() == K, "act must be K fp32 values")
+                d.act_f32 = a.data_ptr()
+                self._keep.append(a)
+                g = st.get("gate")
+                if g is not None:
+                    _check(g.is_cuda and g.dtype == torch.float32 and g.is_contiguous() and g.numel() == K, "gate must be K fp32 values")
+                    d.gate_f32 = g.data_ptr()
+                    self._keep.append(g)
+            d.nmat = len(ws)
+            for m, (w, o, M) in enumerate(zip(ws, outs, Ms)):
+                d.weights[m], d.C[m], d.F[m] = w.data_ptr(), o.data_ptr(), M
+            d.K, d.ldc_f = K, 1
+            d.flags = GEMM_INPUTS_READY if st.get("ready") else 0
+            self._keep += ws
+            self.outs.append(outs)
+        self.device = dev
+        self.sync_bytes = int(_lib.lib().qgemm_gemv_chain_sync_bytes(self.n))
+
+    def _sync(self) -> torch.Tensor:
+        key = (self.device.index or 0, torch.cuda.current_stream(self.device).cuda_stream)
+        t = _chain_sync.get(key)
+        if t is None or t.numel() < self.sync_bytes:
+            t = torch.zeros(max(self.sync_bytes, 4096), dtype=torch.uint8, device=self.device)
+            torch.cuda.synchronize(self.device)   # the zeros are in place whatever stream the first launch uses
+            _chain_sync[key] = t
+        return t
+
+    def __call__(self) -> list:
+        t = self._sync()
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().qgemm_gemv_chain(self.wtype, self.arr, self.n, self.flags, t.data_ptr(), t.numel(),
+                                             torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.raise_on_error(rc, "gemv_chain")
+        return self.outs
+
+
+def gemv_chain(steps: list, wtype: int, flags: int = 0) -> list:
+    """One-shot form of GemvChain: returns the list of per-step output lists."""
+    return GemvChain(steps, wtype, flags)()
+
+
 def gemm_q4_0_q8_1(weight_q, activation_q, M, N, K, flags: int = 0):
     """Q4_0 x Q8_1 GEMM -> [M, N] float32 (python/quant_gemm/__init__.py:59-75)."""
     return gemm(weight_q, activation_q, M, N, K, TYPE_Q4_0, flags)
@@ -379,5 +479,5 @@ __all__ = [
     "quantize_q4_1", "quantize_q5_0", "quantize_q5_1", "quantize_q8_0", "dequantize",
     "gemm", "gemm_q4_1_q8_1", "gemm_q5_0_q8_1", "gemm_q5_1_q8_1", "gemm_q8_0_q8_1", "gemm_w4a8",
     "gemm_a16", "gemm_q4_0_fp32", "quantize_q8_1_silu_mul", "quantize_q8_1_rms_norm",
-    "gemm_group", "prepack_weights", "block_sumi", "launch_count", "reset_launch_count", "last_path", "hint_next_weights",
+    "gemm_group", "GemvChain", "gemv_chain", "prepack_weights", "block_sumi", "launch_count", "reset_launch_count", "last_path", "hint_next_weights",
 ]

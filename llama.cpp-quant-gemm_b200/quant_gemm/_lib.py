@@ -10,6 +10,8 @@ LIB_PATH = os.path.join(_PKG, "lib", "libqgemm_sm100.so")
 
 TYPE_Q4_0, TYPE_Q4_1, TYPE_Q5_0, TYPE_Q5_1, TYPE_Q8_0, TYPE_Q8_1 = 2, 3, 6, 7, 8, 9
 Q81_ROUND_AWAY, Q81_ROUND_EVEN, Q81_S_FROM_QSUM, Q81_CLAMP127 = 0, 1, 2, 4
+Q81_TREE_SUM, Q81_ID_FROM_HALF_D, Q81_ZERO_D1 = 8, 16, 32
+Q81_FUSED_F16 = Q81_TREE_SUM | Q81_ID_FROM_HALF_D | Q81_CLAMP127
 GEMM_MS_EXACT, GEMM_SEQUENTIAL, GEMM_WEIGHTS_STATIC, GEMM_INPUTS_READY = 0x1, 0x8, 0x10, 0x20
 GEMM_WEIGHTS_PREPACKED, GEMM_STREAM_ALLOC, GEMM_FOLD_REFSEQ = 0x40, 0x80, 0x1000
 PATH_AUTO, PATH_GENERIC, PATH_GEMV, PATH_MMA, PATH_TCGEN05 = 0x000, 0x100, 0x200, 0x300, 0x400
@@ -25,6 +27,7 @@ SYMBOLS = {
     "qgemm_last_path": (_u32, []),
     "qgemm_last_error_detail": (C.c_char_p, []),
     "qgemm_quantize_q8_1": (_i, [_p, _p, _i64, _i64, _u32, _p]),
+    "qgemm_quantize_q8_1_f16": (_i, [_p, _p, _i64, _i64, _u32, _p]),
     "qgemm_quantize_q8_1_silu_mul": (_i, [_p, _p, _p, _i64, _i64, _u32, _p]),
     "qgemm_quantize_q8_1_rms_norm": (_i, [_p, _p, _p, _i64, _i64, C.c_float, _u32, _p, _p]),
     "qgemm_quantize_weight": (_i, [_i, _p, _p, _i64, _i64, _u32, _p]),
@@ -51,7 +54,18 @@ class QgemmPeers(C.Structure):
                 ("launches_per_step", _u32), ("launch_index", _u32), ("wait_index", _u32), ("C_multicast", _p)]
 
 
+class QgemmChainStep(C.Structure):
+    """struct qgemm_chain_step of include/qgemm.h"""
+    _fields_ = [("act_q8_1", _p), ("act_f32", _p), ("gate_f32", _p), ("nmat", _i), ("weights", _p * 3), ("C", _p * 3),
+                ("F", _i * 3), ("K", _i), ("ldc_f", _i64), ("flags", _u32)]
+
+
+PATH_CHAINED = 0x1000000
+
 SYMBOLS.update({
+    "qgemm_gemv_chain_sync_bytes": (_sz, [_i]),
+    "qgemm_gemv_chain_max_steps": (_i, []),
+    "qgemm_gemv_chain": (_i, [_i, C.POINTER(QgemmChainStep), _i, _u32, _p, _sz, _p]),
     "qgemm_gemm_peers": (_i, [_i, _p, _p, C.POINTER(QgemmPeers), _i, _i, _i, _i64, _i64, _u32, _p]),
     "qgemm_gemm_group_peers": (_i, [_i, _p, _i, C.POINTER(_p), C.POINTER(_i), C.POINTER(_i64), C.POINTER(QgemmPeers), _i, _i,
                                _i64, _i64, _u32, _p]),

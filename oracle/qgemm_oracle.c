@@ -166,11 +166,29 @@ void qo_quantize_q8_1(const float *x, void *y, int64_t n, unsigned flags)
             if (a > amax) amax = a; /* == std::max(amax, |x|) for non-NaN input */
             sum += src[j];
         }
-        const float d = amax / 127.0f;
-        const float id = (d > 0) ? 1.0f / d : 0.0f;
+        if (flags & QO_Q81_TREE_SUM) {
+            /* kernels/gemm/gemm_fused.cuh:96-127: s[i] += s[i+16] (i < 16), += s[i+8], += s[i+4], += s[i+2], s[0] + s[1] */
+            float t[32];
+            for (int j = 0; j < 32; j++) t[j] = src[j];
+            for (int w = 16; w >= 1; w >>= 1)
+                for (int j = 0; j < w; j++) t[j] = t[j] + t[j + w];
+            sum = t[0];
+        }
+        float d = amax / 127.0f;
+        float id = (d > 0) ? 1.0f / d : 0.0f;
+        if (flags & QO_Q81_ID_FROM_HALF_D) {
+            /* gemm_fused.cuh:131-133: every thread re-reads d from the stored half and inverts THAT */
+            const float dh = qo_fp16_to_fp32(qo_fp32_to_fp16(d));
+            id = (dh != 0.0f) ? 1.0f / dh : 0.0f;
+        }
+        if ((flags & QO_Q81_ZERO_D1) && amax == 0.0f) d = 1.0f; /* quantize_q8_1.json: "d = 1.0 if amax == 0"; q stays 0 */
         for (int j = 0; j < 32; j++) {
             const float v = src[j] * id;
             int q = (flags & QO_Q81_ROUND_EVEN) ? rn_even(v) : (int)roundf(v);
+            /* gemm_fused.cuh:138-139 narrows to int8_t BEFORE clamping (`int8_t q = (int8_t)roundf(val * id)`; nvcc: F2I to
+             * s32, low byte sign-extended).  It matters only where the fp16 d is subnormal and much smaller than the fp32 d
+             * (amax below ~1e-3): there |x * id| can pass 127.5 and the reference wraps. */
+            if (flags & QO_Q81_ID_FROM_HALF_D) q = (int)(int8_t)(uint8_t)((unsigned)q & 0xffu);
             if (q < lo) q = lo;
             if (q > 127) q = 127;
             dst[4 + j] = (uint8_t)(int8_t)q;
@@ -182,6 +200,16 @@ void qo_quantize_q8_1(const float *x, void *y, int64_t n, unsigned flags)
         } else {
             st16(dst + 2, qo_fp32_to_fp16(sum));
         }
+    }
+}
+
+void qo_quantize_q8_1_f16(const uint16_t *x_f16, void *y, int64_t n, unsigned flags)
+{
+    /* gemm_fused.cuh:90-93,137: every element enters as __half2float(fp16_data[tid]) */
+    float buf[32];
+    for (int64_t i = 0; i + 32 <= n; i += 32) {
+        for (int j = 0; j < 32; j++) buf[j] = qo_fp16_to_fp32(x_f16[i + j]);
+        qo_quantize_q8_1(buf, (uint8_t *)y + (i / 32) * 36, 32, flags);
     }
 }
 

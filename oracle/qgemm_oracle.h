@@ -42,6 +42,11 @@ enum {
 #define QO_Q81_ROUND_EVEN 1u      /* __float2int_rn, include/quantize.h:302-337     */
 #define QO_Q81_S_FROM_QSUM 2u     /* s = half(sum_q * d), test_framework.cuh:195-225 */
 #define QO_Q81_CLAMP127 4u        /* clamp to +-127 (py ext gemm_ops.cu:75-110, framework) */
+#define QO_Q81_TREE_SUM 8u        /* s = pairwise tree sum (i, i+16), (i, i+8) ...: kernels/gemm/gemm_fused.cuh:96-127 */
+#define QO_Q81_ID_FROM_HALF_D 16u /* 1/d taken from the fp16-rounded d: gemm_fused.cuh:131-133                  */
+#define QO_Q81_ZERO_D1 32u        /* all-zero block stores d = 1.0: schemas/definitions/quantization/quantize_q8_1.json */
+/* the in-kernel quantizer of gemm_q4_0_fp16_fused (gemm_fused.cuh:76-143): fp16 input, the three properties above */
+#define QO_Q81_FUSED_F16 (QO_Q81_TREE_SUM | QO_Q81_ID_FROM_HALF_D | QO_Q81_CLAMP127)
 
 /* GEMM flags.  Same bit values as QGEMM_* in include/qgemm.h. */
 #define QO_GEMM_MS_EXACT 1u       /* q4_1/q5_1: m*s instead of the reference's m*s/4 */
@@ -57,6 +62,8 @@ size_t qo_block_bytes(int type);
 
 /* ---- quantizers --------------------------------------------------------- */
 /* x[rows*k] fp32 -> y[rows*k/32] block_q8_1 (36 B each). */
+/* fp16 input (the reference's fused kernel reads half activations, gemm_fused.cuh:76-143) */
+void qo_quantize_q8_1_f16(const uint16_t *x_f16, void *y, int64_t n, unsigned flags);
 void qo_silu_mul(const float *x, const float *gate, float *y, int64_t n);
 void qo_rms_norm(const float *x, const float *weight, float *y, int64_t n_rows, int64_t n_cols, float eps);
 void qo_quantize_q8_1(const float *x, void *y, int64_t n, unsigned flags);

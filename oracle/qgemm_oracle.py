@@ -32,6 +32,8 @@ TYPE_NAMES = {Q4_0: "q4_0", Q4_1: "q4_1", Q5_0: "q5_0", Q5_1: "q5_1", Q8_0: "q8_
 
 # quantize_q8_1 flags / gemm flags (same bits as include/qgemm.h)
 Q81_ROUND_AWAY, Q81_ROUND_EVEN, Q81_S_FROM_QSUM, Q81_CLAMP127 = 0, 1, 2, 4
+Q81_TREE_SUM, Q81_ID_FROM_HALF_D, Q81_ZERO_D1 = 8, 16, 32
+Q81_FUSED_F16 = Q81_TREE_SUM | Q81_ID_FROM_HALF_D | Q81_CLAMP127   # kernels/gemm/gemm_fused.cuh:76-143
 GEMM_MS_EXACT, GEMM_Q80_ASSOC_UNIT, GEMM_FMA = 1, 2, 4
 
 
@@ -72,6 +74,7 @@ class Oracle:
         L.qo_fp16_to_fp32.restype = _f
         L.qo_fp16_to_fp32.argtypes = [C.c_uint16]
         L.qo_quantize_q8_1.argtypes = [_p, _p, _i64, _u]
+        L.qo_quantize_q8_1_f16.argtypes = [_p, _p, _i64, _u]
         L.qo_silu_mul.argtypes = [_p, _p, _p, _i64]
         L.qo_rms_norm.argtypes = [_p, _p, _p, _i64, _i64, _f]
         for n in ("qo_quantize_q4_0_ref", "qo_quantize_q8_0_ref", "qo_to_q4_0", "qo_to_q4_1",
@@ -103,6 +106,14 @@ class Oracle:
 
     def quantize_q8_1(self, x, flags: int = Q81_ROUND_AWAY):
         return self._quant(self.lib.qo_quantize_q8_1, x, 36, flags)
+
+    def quantize_q8_1_f16(self, x_f16, flags: int = Q81_FUSED_F16):
+        """fp16 input [..., K] -> q8_1, the reference's in-kernel quantizer (kernels/gemm/gemm_fused.cuh:76-143) by default."""
+        x = np.ascontiguousarray(x_f16, dtype=np.float16)
+        assert x.shape[-1] % 32 == 0
+        out = np.empty(x.shape[:-1] + (x.shape[-1] // 32, 36), dtype=np.uint8)
+        self.lib.qo_quantize_q8_1_f16(_ptr(x), _ptr(out), x.size, flags)
+        return out
 
     def silu_mul(self, x, gate) -> np.ndarray:
         """silu(x) * gate in fp32, operation order of kernels/activation/silu.cuh:97-108."""
@@ -235,6 +246,8 @@ class Reference:
         if hasattr(L, "ref_gpu_silu_mul_f32"):   # kernels/activation/silu.cuh (added with the fused SwiGLU quantizer)
             L.ref_gpu_silu_mul_f32.argtypes = [_p, _p, _p, _i, _p]
             L.ref_cpu_silu_f32.argtypes = [_p, _p, _i]
+        if hasattr(L, "ref_gpu_quantize_fp16_to_q8_1_smem"):   # kernels/gemm/gemm_fused.cuh:76-143 (ref_shim_fused.cu)
+            L.ref_gpu_quantize_fp16_to_q8_1_smem.argtypes = [_p, _p, _i, _p]
         if hasattr(L, "ref_cpu_rms_norm_f32"):   # kernels/normalization/rms_norm.cuh
             L.ref_cpu_rms_norm_f32.argtypes = [_p, _p, _p, _i, _i, _f]
             L.ref_gpu_rms_norm_f32.argtypes = [_p, _p, _p, _i, _i, _f, _p]

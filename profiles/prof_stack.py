@@ -33,6 +33,25 @@ def hint(w):
     quant_gemm.hint_next_weights(w, min(WINDOW, end - w.data_ptr()))
 
 
+CHAIN = int(os.environ.get("PROF_CHAIN", "0"))   # layers per chained launch (qgemm_gemv_chain); 0: one launch per grouped projection
+if CHAIN:
+    chains = []
+    for c0 in range(0, LAYERS, CHAIN):
+        steps = []
+        for l in range(c0, min(c0 + CHAIN, LAYERS)):
+            m = mats[7 * l:7 * l + 7]
+            steps += [{"weights": [m[0], m[1], m[2]], "Ms": [4096] * 3, "K": 4096, "act_q": aq[4096]},
+                      {"weights": [m[3]], "Ms": [4096], "K": 4096, "act_q": aq[4096]},
+                      {"weights": [m[4], m[5]], "Ms": [11008] * 2, "K": 4096, "act_q": aq[4096]},
+                      {"weights": [m[6]], "Ms": [4096], "K": 11008, "act_q": aq[11008]}]
+        chains.append(quant_gemm.GemvChain(steps, 2, 0x10))
+    for ci, ch in enumerate(chains):
+        hint(mats[(7 * CHAIN * (ci + 1)) % len(mats)])
+        ch()
+    torch.cuda.synchronize()
+    print("ok (chained)")
+    sys.exit(0)
+
 for l in range(LAYERS):
     m = mats[7 * l:7 * l + 7]
     nxt = mats[(7 * l + 7) % len(mats)]

@@ -71,6 +71,56 @@ def test_argument_validation_without_gpu(lib):
     assert lib.qgemm_dequantize(2, p, C.c_void_p(0x1004), 1, 32, None) == ALIGN
 
 
+def test_chain_step_struct_layout_matches_header(tmp_path):
+    """ctypes mirror of struct qgemm_chain_step == the header's layout."""
+    import subprocess
+    from quant_gemm import _lib
+    src = tmp_path / "layout_chain.c"
+    fields = ["act_q8_1", "act_f32", "gate_f32", "nmat", "weights", "C", "F", "K", "ldc_f", "flags"]
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "qgemm.h"\nint main(void){printf("%zu", sizeof(qgemm_chain_step));'
+                   + "".join(f'printf(" %zu", offsetof(qgemm_chain_step, {f}));' for f in fields) + 'printf("\\n"); return 0;}\n')
+    exe = tmp_path / "layout_chain"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    S = _lib.QgemmChainStep
+    assert got == [C.sizeof(S)] + [getattr(S, f).offset for f in fields]
+
+
+def test_chain_argument_validation_without_gpu(lib):
+    from quant_gemm import _lib
+    BAD, ALIGN, WS = -1, -2, -5
+    S = _lib.QgemmChainStep
+    arr = (S * 2)()
+    for d in arr:
+        d.act_q8_1, d.nmat, d.K, d.ldc_f = 0x1000, 1, 4096, 1
+        d.weights[0], d.C[0], d.F[0] = 0x2000, 0x3000, 512
+    sync = C.c_void_p(0x4000)
+    assert lib.qgemm_gemv_chain_sync_bytes(2) == 12 and lib.qgemm_gemv_chain_sync_bytes(0) == 0
+    assert lib.qgemm_gemv_chain_max_steps() >= 128
+    assert lib.qgemm_gemv_chain(2, arr, 0, 0, sync, 64, None) == BAD
+    assert lib.qgemm_gemv_chain(4, arr, 2, 0, sync, 64, None) == BAD          # unknown type
+    assert lib.qgemm_gemv_chain(2, arr, 2, 0, None, 0, None) == WS
+    assert lib.qgemm_gemv_chain(2, arr, 2, 0, sync, 8, None) == WS            # needs 12 bytes
+    arr[1].nmat = 4
+    assert lib.qgemm_gemv_chain(2, arr, 2, 0, sync, 64, None) == BAD
+    arr[1].nmat = 1
+    arr[1].act_f32 = 0x5000                                                     # both kinds of activations
+    assert lib.qgemm_gemv_chain(2, arr, 2, 0, sync, 64, None) == BAD
+    arr[1].act_f32 = None
+    arr[1].K = 100
+    assert lib.qgemm_gemv_chain(2, arr, 2, 0, sync, 64, None) == BAD
+    arr[1].K = 4096
+    arr[1].weights[0] = 0x2001
+    assert lib.qgemm_gemv_chain(2, arr, 2, 0, sync, 64, None) == ALIGN
+    arr[1].weights[0] = 0x2000
+    arr[1].flags = 0x8
+    assert lib.qgemm_gemv_chain(2, arr, 2, 0, sync, 64, None) == BAD          # only QGEMM_INPUTS_READY is a step flag
+    arr[1].flags = 0x20
+    import torch
+    if not torch.cuda.is_available():
+        assert lib.qgemm_gemv_chain(2, arr, 2, 0, sync, 64, None) in (-3, -4)   # no device: fails loudly, computes nothing
+
+
 def test_no_cpu_fallback(lib):
     """Without a B200 the compute entries must fail loudly, never compute on the host."""
     import torch

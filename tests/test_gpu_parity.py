@@ -888,6 +888,9 @@ def test_gemm_group_equals_separate_calls(qg, O, wt, T, K):
         check_c(c, O.gemm(wt, aq, wq, layout="FT"), "group vs oracle")
         sep = host(qg.gemm(dw, da, F, T, K, wt, flags=0x200))
         assert (bits(c) == bits(sep)).all()
+    # a group of one matrix is a plain GEMV
+    one = qg.gemm_group(dws[:1], da, Fs[:1], T, K, wt)
+    assert (bits(host(one[0])) == bits(host(qg.gemm(dws[0], da, Fs[0], T, K, wt, flags=0x200)))).all()
     # T > 8 falls back to one launch per matrix, same answers
     x2, _ = datagen.model_like(12, 8, K, seed=6)
     aq2 = O.quantize_q8_1(x2)
