@@ -293,6 +293,17 @@ QGEMM_API int qgemm_gemm_f32act(int wtype, const float *act_f32, const void *wei
                       size_t workspace_bytes, void *stream);
 
 /*
+ * Same with fp16 activations act_f16[T][K] (2-byte aligned): qgemm_quantize_q8_1_f16 into the workspace, then the GEMM.
+ * Successor of gemm_q4_0_fp16_fused() (kernels/gemm/gemm_fused.cuh:311-338), whose kernel quantizes half activations to
+ * q8_1 in shared memory before the dot products; with QGEMM_Q81_FUSED_F16 << 16 in `flags` the quantized blocks are the
+ * ones its quantize_fp16_to_q8_1_smem() produces.  workspace: T * (K/32) * 36 bytes rounded up to 256, plus
+ * qgemm_workspace_bytes() for tensor-core sizes; NULL is accepted together with QGEMM_STREAM_ALLOC.
+ */
+QGEMM_API int qgemm_gemm_f16act(int wtype, const void *act_f16, const void *weight, float *C, int T, int F, int K,
+                                int64_t ldc_t, int64_t ldc_f, uint32_t flags, void *workspace, size_t workspace_bytes,
+                                void *stream);
+
+/*
  * The FFN down projection with its SwiGLU neighbour: C = W . quantize_q8_1(silu(x) * gate).  Same contract as
  * qgemm_gemm_f32act (workspace, flags, two launches at tensor-core sizes); x, gate: [T][K] fp32.  Replaces
  * silu_mul_forward_f32 (kernels/activation/silu.cuh:162-175) + quantize_q8_1_cuda + gemm_*: bit-equal to

@@ -569,6 +569,36 @@ static int gemm_f32act_impl(int wtype, const float* act_f32, const float* gate, 
                     workspace_bytes - a_q, st, dev);
 }
 
+int qgemm_gemm_f16act(int wtype, const void* act_f16, const void* weight, float* C, int T, int F, int K, int64_t ldc_t,
+                      int64_t ldc_f, uint32_t flags, void* workspace, size_t workspace_bytes, void* stream) {
+    if (int rc = check_gemm_args(wtype, act_f16, weight, C, T, F, K)) {
+        // check_gemm_args asks 4-byte alignment of the activations (q8_1 / fp32); halves need 2
+        if (!(rc == QGEMM_E_ALIGN && act_f16 && aligned(act_f16, 2) && aligned(weight, 2) && aligned(C, 4))) return rc;
+    }
+    if (T == 0 || F == 0) return QGEMM_OK;
+    DeviceInfo dev;
+    if (int rc = device_check(&dev)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t a_q = align_up((size_t)T * (K / kQK) * kQ81Bytes, 256);
+    void* pool = nullptr;
+    if (K > 0 && !workspace && (flags & QGEMM_STREAM_ALLOC)) {   // launcher-style callers bring no scratch
+        if (cudaError_t e = cudaMallocAsync(&pool, a_q, st)) return cuda_fail(e, "gemm_f16act scratch");
+        workspace = pool;
+        workspace_bytes = a_q;
+    }
+    if (K > 0 && (!workspace || workspace_bytes < a_q || !aligned(workspace, 16))) return QGEMM_E_WORKSPACE;
+    int rc = QGEMM_OK;
+    if (K > 0) {
+        const cudaError_t e = launch_quantize_q8_1_f16(act_f16, workspace, (int64_t)T * (K / kQK), (flags >> 16) & 0xffu, st);
+        if (e != cudaSuccess) rc = cuda_fail(e, "gemm_f16act quantize launch");
+    }
+    if (rc == QGEMM_OK)
+        rc = run_gemm(wtype, workspace, weight, C, T, F, K, ldc_t, ldc_f, flags & 0xffffu, workspace_bytes > a_q ? (char*)workspace + a_q : nullptr,
+                      workspace_bytes > a_q ? workspace_bytes - a_q : 0, st, dev);
+    if (pool) cudaFreeAsync(pool, st);
+    return rc;
+}
+
 int qgemm_gemm_a16(int wtype, const float* act_f32, const void* weight, float* C, int T, int F, int K, int64_t ldc_t,
                    int64_t ldc_f, uint32_t flags, void* stream) {
     if ((wtype != QGEMM_TYPE_Q4_0 && wtype != QGEMM_TYPE_Q8_0) || T < 0 || F < 0 || K < 0 || (K % kQK) != 0) return QGEMM_E_BADARG;

@@ -443,6 +443,16 @@ def gemm_q4_0_fp32(weight_q: torch.Tensor, activation: torch.Tensor, M: int, N: 
     return gemm_a16(weight_q, activation, M, N, K, TYPE_Q4_0)
 
 
+def gemm_q4_0_fp16_fused(weight_q: torch.Tensor, activation_f16: torch.Tensor, M: int, N: int, K: int) -> torch.Tensor:
+    """Q4_0 weights [M, K/32, 18] x FP16 activations [N, K] -> [M, N]: the reference's gemm_q4_0_fp16_fused
+    (kernels/gemm/gemm_fused.cuh:311-338, never bound by its extension).  The activations are quantized with the arithmetic of
+    that kernel's in-kernel quantizer (Q81_FUSED_F16), then take the q8_1 GEMM."""
+    _check(activation_f16.is_cuda and activation_f16.dtype == torch.float16, "Activation must be a CUDA float16 tensor")
+    _check(activation_f16.numel() == N * K, f"Activation shape mismatch: expected {N * K} elements, got {activation_f16.numel()}")
+    aq = _quantize(activation_f16.reshape(N, K), TYPE_Q8_1, Q81_FUSED_F16)
+    return gemm(weight_q, aq, M, N, K, TYPE_Q4_0)
+
+
 def block_sumi(weight_q: torch.Tensor, activation_q: torch.Tensor, M: int, N: int, K: int, wtype: int,
                flags: int = 0) -> torch.Tensor:
     """Test hook: int32 sumi[N tokens, M rows, K/32] exactly as the selected path computes it."""
@@ -478,6 +488,6 @@ __all__ = [
     # supersets
     "quantize_q4_1", "quantize_q5_0", "quantize_q5_1", "quantize_q8_0", "dequantize",
     "gemm", "gemm_q4_1_q8_1", "gemm_q5_0_q8_1", "gemm_q5_1_q8_1", "gemm_q8_0_q8_1", "gemm_w4a8",
-    "gemm_a16", "gemm_q4_0_fp32", "quantize_q8_1_silu_mul", "quantize_q8_1_rms_norm",
+    "gemm_a16", "gemm_q4_0_fp32", "gemm_q4_0_fp16_fused", "quantize_q8_1_silu_mul", "quantize_q8_1_rms_norm",
     "gemm_group", "GemvChain", "gemv_chain", "prepack_weights", "block_sumi", "launch_count", "reset_launch_count", "last_path", "hint_next_weights",
 ]

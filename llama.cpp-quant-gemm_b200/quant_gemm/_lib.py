@@ -39,6 +39,7 @@ SYMBOLS = {
     "qgemm_gemm_group": (_i, [_i, _p, _i, C.POINTER(_p), C.POINTER(_p), C.POINTER(_i), _i, _i, _i64, _i64, _u32, _p]),
     "qgemm_workspace_bytes": (_sz, [_i, _i, _i, _i, _u32]),
     "qgemm_gemm": (_i, [_i, _p, _p, _p, _i, _i, _i, _i64, _i64, _u32, _p, _sz, _p]),
+    "qgemm_gemm_f16act": (_i, [_i, _p, _p, _p, _i, _i, _i, _i64, _i64, _u32, _p, _sz, _p]),
     "qgemm_gemm_f32act": (_i, [_i, _p, _p, _p, _i, _i, _i, _i64, _i64, _u32, _p, _sz, _p]),
     "qgemm_gemm_f32act_silu_mul": (_i, [_i, _p, _p, _p, _p, _i, _i, _i, _i64, _i64, _u32, _p, _sz, _p]),
     "qgemm_gemm_a16": (_i, [_i, _p, _p, _p, _i, _i, _i, _i64, _i64, _u32, _p]),

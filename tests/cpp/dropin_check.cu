@@ -20,6 +20,7 @@
 #include "kernels/gemm/gemm_warp_optimized.cuh"
 #include "kernels/gemm/gemm_async_copy.cuh"
 #include "kernels/gemm/gemm_vectorized.cuh"
+#include "kernels/gemm/gemm_fused.cuh"
 
 // a stand-in for ggml.h (only what the adapter touches): the complete tensor type + the macro that says it is there
 #define GGML_MAX_DIMS 4
@@ -100,6 +101,15 @@ int main(int argc, char** argv) {
     fetch("c_hook16.f32");
     if (qgemm_ggml_cuda_op_mul_mat_q(QUANT_TYPE_Q4_0, (const char*)w4, (const char*)a, c, K, 0, F, T, K, F, st) != 0) return 10;
     fetch("c_hook.f32");
+
+    // fp16 activations through the reference's fused launcher name: quantized like its in-kernel quantizer, then the q8_1 GEMM
+    {
+        std::vector<char> hx = slurp(dir + "/x.f16");
+        half* xh = to_dev<half>(hx);
+        gemm_q4_0_fp16_fused(w4, xh, c, F, T, K, st);
+        if (qgemm_dropin_last_status() != 0) return 11;
+        fetch("c_fused16.f32");
+    }
 
     // the unchanged launcher reaches the tensor-core path on its own (scratch from the stream's pool) ...
     printf("launcher path 0x%x\n", qgemm_last_path());

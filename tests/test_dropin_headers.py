@@ -47,6 +47,7 @@ def test_reference_entry_point_names_are_all_present():
                                                  "gemm_q4_0_q8_1_tile2d_large"],
         "kernels/gemm/gemm_async_copy.cuh": ["gemm_q4_0_q8_1_async"],
         "kernels/gemm/gemm_vectorized.cuh": ["gemm_q4_0_q8_1_vec_safe", "gemm_q4_0_q8_1_vec_float4"],
+        "kernels/gemm/gemm_fused.cuh": ["gemm_q4_0_fp16_fused"],
     }
     for path, fns in names.items():
         text = open(os.path.join(ROOT, path)).read()
@@ -64,6 +65,7 @@ def test_dropin_program_matches_oracle(tmp_path):
     x, w = datagen.model_like(T, F, K, seed=99)
     wq = {n: O.quantize_weight(t, w) for n, t in (("q4_0", qo.Q4_0), ("q5_1", qo.Q5_1), ("q8_0", qo.Q8_0))}
     x.tofile(tmp_path / "x.f32")
+    x.astype(np.float16).tofile(tmp_path / "x.f16")
     for n, q in wq.items():
         q.tofile(tmp_path / f"w_{n}.bin")
     (tmp_path / "dims.txt").write_text(f"{T} {F} {K}\n")
@@ -84,6 +86,9 @@ def test_dropin_program_matches_oracle(tmp_path):
         r16 = O.gemm_f32act_dequant(wt, x, wq[key], layout="TF")
         assert qo.max_norm_err(load(name, (T, F)), r16) <= 1e-5, name
     assert qo.max_norm_err(load("c_hook.f32", (T, F)).T, ref["q4_0"]) <= 1e-5
+    # gemm_q4_0_fp16_fused: half activations quantized with the arithmetic of the reference's in-kernel quantizer
+    a16 = O.quantize_q8_1_f16(x.astype(np.float16), qo.Q81_FUSED_F16)
+    assert qo.max_norm_err(load("c_fused16.f32", (F, T)), O.gemm(qo.Q4_0, a16, wq["q4_0"], layout="FT")) <= 1e-5
     for name, key, transposed in [("c_inc_q4_0.f32", "q4_0", True), ("c_inc_q4_0_b.f32", "q4_0", True),
                                   ("c_inc_q8_0.f32", "q8_0", True), ("c_ggml_q4_0.f32", "q4_0", False),
                                   ("c_ggml_q5_1.f32", "q5_1", False), ("c_tile2d.f32", "q4_0", False),

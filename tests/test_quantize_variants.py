@@ -132,3 +132,19 @@ def test_gpu_f16_input_default_flags_and_reference_device_function():
     ours = qg.quantize_q8_1(d16, qg.Q81_FUSED_F16).cpu().numpy().reshape(-1, 36)
     assert (ours == ref).all(), "product kernel differs from the reference's device function"
     assert (O.quantize_q8_1_f16(x16, qo.Q81_FUSED_F16).reshape(-1, 36) == ref).all(), "oracle restatement differs from the reference"
+
+
+@pytest.mark.gpu
+def test_gemm_q4_0_fp16_fused_python_entry():
+    import torch
+    import datagen
+    import quant_gemm as qg
+    O = qo.Oracle()
+    N, M, K = 5, 300, 2048
+    x, w = datagen.model_like(N, M, K, seed=4)
+    wq = O.quantize_weight(qo.Q4_0, w)
+    x16 = x.astype(np.float16)
+    out = qg.gemm_q4_0_fp16_fused(torch.from_numpy(wq).cuda(), torch.from_numpy(x16).cuda(), M, N, K)
+    torch.cuda.synchronize()
+    ref = O.gemm(qo.Q4_0, O.quantize_q8_1_f16(x16, qo.Q81_FUSED_F16), wq, layout="FT")
+    assert qo.max_norm_err(out.cpu().numpy(), ref) <= 1e-5
