@@ -241,12 +241,15 @@ QGEMM_API int qgemm_gemm_group(int wtype, const void *act_q8_1, int nmat, const 
  *   - act_f32 (act_q8_1 == NULL): K floats that the kernel quantizes itself with quantize_q8_1's default arithmetic
  *     (include/quantize.h:165-193) -- typically the C of an EARLIER step of the same chain, so the quantize launch
  *     between two projections disappears; with gate_f32 != NULL the quantized value is silu(act_f32[i]) * gate_f32[i]
- *     (kernels/activation/silu.cuh:97-108), the SwiGLU in front of the down projection.
+ *     (kernels/activation/silu.cuh:97-108), the SwiGLU in front of the down projection.  The CTAs quantize the vector
+ *     together (one block per warp) into scratch inside `sync` and every CTA copies the result: such a step always waits
+ *     for all earlier steps, whatever its flags.
  * Step flags: QGEMM_INPUTS_READY = this step's activations are not produced by an earlier step of the chain (nor by
  * work still in flight when the chain starts computing): it may begin before the earlier steps have finished.  Without
  * it a step starts when every earlier step has completed on the whole device (stream-order semantics).
  *
- * sync: qgemm_gemv_chain_sync_bytes(nsteps) bytes of device memory, 4-byte aligned, ZERO before the first use; the
+ * sync: qgemm_gemv_chain_sync_bytes(nsteps) bytes of device memory (arrival counters + 108 KB of quantizer scratch), 4-byte
+ * aligned, ZERO before the first use; the
  * kernel leaves it zero, so one buffer serves every chain launched on the same stream.  Chains on different streams need
  * different buffers.  Lists the persistent kernel cannot take (T > 1 shapes, rows that are not 16-byte multiples, K too
  * long for register-resident activations, fewer rows than CTAs, QGEMM_MS_EXACT) are run as one launch per step --

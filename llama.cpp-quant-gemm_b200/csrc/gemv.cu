@@ -666,6 +666,7 @@ cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, i
 // ===========================================================================================================
 constexpr int kChainMaxSteps = 160;
 constexpr int kChainMaxMat = 3;
+constexpr int kChainQStride = 1536 * 36;   // longest row the register-resident consumers take: 3 pairs x 8 warps x 32 lanes
 
 struct ChainStep {
     const uint8_t* act;              // q8_1 [nb][36 B], or null: quantize from x (and gate)
@@ -683,7 +684,9 @@ template <int NS> struct ChainParams {
     int nsteps;
     int stages, stage_bytes;
     uint32_t act_bytes;              // shared memory reserved for the raw activations (largest step)
-    unsigned* sync;                  // [nsteps + 1], zero on entry and on exit
+    unsigned* sync;                  // [2 * nsteps + 1] counters, zero on entry and on exit: step arrivals [0, nsteps), exit
+                                     // ticket [nsteps], quantizer arrivals [nsteps + 1, 2 * nsteps + 1)
+    uint8_t* qscratch;               // two buffers of kChainQStride bytes: the q8_1 blocks of a step that quantizes its input
     int pdl;
     const uint8_t* pf_ptr;
     unsigned long long pf_bytes;
@@ -712,42 +715,28 @@ __device__ __forceinline__ int chain_round_half_away(float v) {
     if (fabsf(r) >= 0.5f) q += (v < 0.0f) ? -1 : 1;
     return q;
 }
-__device__ __forceinline__ void chain_quantize_block(const float* x, const float* gate, uint32_t* out) {
-    float v[32];
+// One warp quantizes one block, lane = element: quantize_q8_1's default arithmetic (include/quantize.h:165-193: roundf, clamp
+// -128, s = fp16 of the fp32 sum taken in element order), optionally on silu(x) * gate in silu_mul_f32_kernel's operation
+// sequence (kernels/activation/silu.cuh:97-108).  36 bytes out.
+// Not inlined on purpose: inside the chain kernel's register budget (96, with spills) one build of this loop body faulted on its
+// first load although every address it was given was right (printed from the kernel); as a function of its own it has its own
+// register allocation.  It runs once per block and step: the call costs nothing that matters.
+__device__ __noinline__ void chain_quantize_block_lanes(const float* x, const float* gate, uint8_t* out, int lane) {
+    float v = __ldcg(x + lane);
+    if (gate) v = __fmul_rn(__fdiv_rn(v, __fadd_rn(1.0f, expf(-v))), __ldcg(gate + lane));
+    float amax = fabsf(v);
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const float4 a = __ldcg(reinterpret_cast<const float4*>(x) + i);
-        v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
-    }
-    if (gate) {   // silu_mul_f32_kernel's operation sequence (kernels/activation/silu.cuh:97-108)
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    float sum = 0.0f;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const float4 g = __ldcg(reinterpret_cast<const float4*>(gate) + i);
-            v[4 * i] = __fmul_rn(__fdiv_rn(v[4 * i], __fadd_rn(1.0f, expf(-v[4 * i]))), g.x);
-            v[4 * i + 1] = __fmul_rn(__fdiv_rn(v[4 * i + 1], __fadd_rn(1.0f, expf(-v[4 * i + 1]))), g.y);
-            v[4 * i + 2] = __fmul_rn(__fdiv_rn(v[4 * i + 2], __fadd_rn(1.0f, expf(-v[4 * i + 2]))), g.z);
-            v[4 * i + 3] = __fmul_rn(__fdiv_rn(v[4 * i + 3], __fadd_rn(1.0f, expf(-v[4 * i + 3]))), g.w);
-        }
-    }
-    float amax = 0.0f, sum = 0.0f;
-#pragma unroll
-    for (int j = 0; j < 32; j++) {
-        amax = fmaxf(amax, fabsf(v[j]));
-        sum = __fadd_rn(sum, v[j]);
-    }
+    for (int j = 0; j < 32; j++) sum = __fadd_rn(sum, __shfl_sync(0xffffffffu, v, j));
     const float d = __fdiv_rn(amax, 127.0f);
     const float id = (d > 0.0f) ? __fdiv_rn(1.0f, d) : 0.0f;
-#pragma unroll
-    for (int w = 0; w < 8; w++) {
-        uint32_t packed = 0;
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const int q = max(-128, min(127, chain_round_half_away(__fmul_rn(v[w * 4 + c], id))));
-            packed |= (uint32_t)(q & 0xff) << (8 * c);
-        }
-        out[1 + w] = packed;
-    }
-    out[0] = (uint32_t)__half_as_ushort(__float2half_rn(d)) | ((uint32_t)__half_as_ushort(__float2half_rn(sum)) << 16);
+    const int q = max(-128, min(127, chain_round_half_away(__fmul_rn(v, id))));
+    out[4 + lane] = (uint8_t)(q & 0xff);
+    if (lane == 0)
+        *reinterpret_cast<uint32_t*>(out) =
+            (uint32_t)__half_as_ushort(__float2half_rn(d)) | ((uint32_t)__half_as_ushort(__float2half_rn(sum)) << 16);
 }
 
 // the consumer warps' share of one step; ring position (s, ph) and slot parity carry over from step to step
@@ -903,14 +892,28 @@ __global__ void __launch_bounds__(kGemvThreads, kGemvCtasPerSm) gemv_chain_kerne
             ptx::mbar_wait(abar, aph);
             aph ^= 1;
         } else {
-            if (st.wait && k > 0) {
+            // fp32 source: the CTAs quantize it TOGETHER, one block per warp (every CTA for itself would be 296-fold redundant:
+            // 8 us per step measured, profiles/r02_chain.md), into a scratch buffer in global memory that every CTA then
+            // copies.  Such a step always starts after every earlier step has completed (the source is usually one of their
+            // outputs, and the two scratch buffers alternate on that order).
+            if (k > 0) {
                 if (tid == 0)
                     while (ld_acquire_gpu(p.sync + (k - 1)) < grid) __nanosleep(20);
                 ptx::bar_sync(1, kGemvWarps * 32);
             }
-            for (int b = tid; b < st.nb; b += kGemvWarps * 32)
-                chain_quantize_block(st.x + (size_t)b * 32, st.gate ? st.gate + (size_t)b * 32 : nullptr,
-                                     reinterpret_cast<uint32_t*>(a_raw) + (size_t)b * 9);
+            uint8_t* qbuf = p.qscratch + (size_t)(k & 1) * kChainQStride;
+            for (int b = (int)blockIdx.x + warp * (int)grid; b < st.nb; b += kGemvWarps * (int)grid)
+                chain_quantize_block_lanes(st.x + (size_t)b * 32, st.gate ? st.gate + (size_t)b * 32 : nullptr, qbuf + (size_t)b * 36, lane);
+            __threadfence();
+            ptx::bar_sync(1, kGemvWarps * 32);
+            if (tid == 0) {
+                atomicAdd(p.sync + p.nsteps + 1 + k, 1u);
+                while (ld_acquire_gpu(p.sync + p.nsteps + 1 + k) < grid) __nanosleep(20);
+            }
+            ptx::bar_sync(1, kGemvWarps * 32);
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(qbuf);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(a_raw);
+            for (int i = tid; i < st.nb * 9; i += kGemvWarps * 32) dst[i] = __ldcg(src + i);
             ptx::fence_proxy_async();   // a later step may overwrite a_raw with a bulk copy
             ptx::bar_sync(1, kGemvWarps * 32);
         }
@@ -935,7 +938,7 @@ __global__ void __launch_bounds__(kGemvThreads, kGemvCtasPerSm) gemv_chain_kerne
     if (tid == 0) {
         // the last CTA to leave has seen every other CTA past its last wait: the counters can go back to zero
         if (atomicAdd(p.sync + p.nsteps, 1u) == grid - 1) {
-            for (int k = 0; k <= p.nsteps; k++) p.sync[k] = 0u;
+            for (int k = 0; k <= 2 * p.nsteps; k++) p.sync[k] = 0u;
         }
     }
 }
@@ -947,6 +950,11 @@ struct ChainStepHost {
 };
 
 int gemv_chain_max_steps() { return kChainMaxSteps; }
+// The counters come first and the quantizer scratch sits at a FIXED offset behind the longest list's counters: one buffer then
+// serves chains of any length (with a length-dependent offset a short chain's scratch would land on -- and un-zero -- the
+// counters of a longer one that shares the buffer).
+static size_t gemv_chain_counter_bytes(int) { return ((size_t)(2 * kChainMaxSteps + 1) * sizeof(unsigned) + 255) / 256 * 256; }
+size_t gemv_chain_sync_bytes(int nsteps) { return gemv_chain_counter_bytes(nsteps) + 2 * (size_t)kChainQStride; }
 
 // Can this list run as one persistent launch?  (one token, register-resident activations for every step, rows and
 // activations bulk-copyable).  Fills *out with the kernel parameters.
@@ -1032,6 +1040,7 @@ static cudaError_t launch_chain_ns(int wtype, const ChainStepHost* steps, int ns
     const int grid = kGemvCtasPerSm * num_sms;
     if (!gemv_chain_plan<NS>(wtype, steps, nsteps, grid, &p, &smem)) return cudaErrorNotSupported;
     p.sync = sync;
+    p.qscratch = reinterpret_cast<uint8_t*>(sync) + gemv_chain_counter_bytes(nsteps);
     p.pdl = (flags & QGEMM_WEIGHTS_STATIC) ? 1 : 0;
     p.pf_ptr = reinterpret_cast<uintptr_t>(pf_ptr) % 16 == 0 ? (const uint8_t*)pf_ptr : nullptr;
     p.pf_bytes = pf_bytes;

@@ -36,6 +36,7 @@ struct ChainStepHost {
     int K; int ldc_f; int wait;
 };
 int gemv_chain_max_steps();
+size_t gemv_chain_sync_bytes(int nsteps);
 cudaError_t launch_gemv_chain(int wtype, const ChainStepHost* steps, int nsteps, uint32_t flags, unsigned* sync, int num_sms,
                               cudaStream_t st, const void* pf_ptr, size_t pf_bytes);
 bool gemv_mma_supported(int wtype, const void* act, const void* wgt, int T, int F, int K);
@@ -424,7 +425,7 @@ int qgemm_gemm_group(int wtype, const void* act_q8_1, int nmat, const void* cons
     return e == cudaSuccess ? QGEMM_OK : cuda_fail(e, "gemm_group launch");
 }
 
-size_t qgemm_gemv_chain_sync_bytes(int nsteps) { return nsteps < 1 ? 0 : sizeof(unsigned) * ((size_t)nsteps + 1); }
+size_t qgemm_gemv_chain_sync_bytes(int nsteps) { return nsteps < 1 ? 0 : gemv_chain_sync_bytes(nsteps); }
 int qgemm_gemv_chain_max_steps(void) { return gemv_chain_max_steps(); }
 
 int qgemm_gemv_chain(int wtype, const qgemm_chain_step* steps, int nsteps, uint32_t flags, void* sync, size_t sync_bytes,

@@ -89,7 +89,7 @@ def test_chain_equals_separate_launches_and_oracle(qg, O, wt):
                 if rep == 0:
                     check_c(c, O.gemm(wt, aq, wq, layout="FT"), f"chain vs oracle K={K} F={F}")
     sync = next(iter(qg._chain_sync.values()))
-    assert int(host(sync).view(np.uint32)[: chain.n + 1].sum()) == 0, "arrival counters not cleared"
+    assert int(host(sync).view(np.uint32)[: 2 * chain.n + 1].sum()) == 0, "arrival counters not cleared"
 
 
 @pytest.mark.parametrize("wt", [qo.Q4_0, qo.Q5_1, qo.Q8_0])
@@ -121,6 +121,8 @@ def test_chain_quantizes_fp32_activations_in_kernel(qg, O, wt):
         assert (bits(host(od)) == bits(host(rd))).all(), "in-kernel SwiGLU quantizer differs from quantize_q8_1_silu_mul"
         rn = qg.gemm(dn, qg.quantize_q8_1(rd.view(1, K)), 600, 1, K, wt, flags=qg.PATH_GEMV)
         assert (bits(host(on)) == bits(host(rn))).all(), "in-kernel quantizer differs from quantize_q8_1"
+    sync = next(iter(qg._chain_sync.values()))
+    assert int(host(sync).view(np.uint32)[: 2 * chain.n + 1].sum()) == 0, "arrival counters not cleared"
     # and against the CPU oracle, stage by stage on the GPU's own intermediate values
     cg, cu, cd = host(og).reshape(1, Fi), host(ou).reshape(1, Fi), host(od).reshape(1, K)
     check_c(host(og), O.gemm(wt, aq, w_gate, layout="FT"), "gate")
@@ -128,6 +130,23 @@ def test_chain_quantizes_fp32_activations_in_kernel(qg, O, wt):
     check_c(host(od), O.gemm(wt, hq, w_down, layout="FT"), "down")
     check_c(host(on), O.gemm(wt, O.quantize_q8_1(cd), w_next, layout="FT"), "next")
     assert np.abs(cd).max() > 1e-3 and np.abs(host(on)).max() > 1e-4, "degenerate data"
+
+
+def test_chains_of_different_lengths_share_one_sync_buffer(qg, O):
+    """A short chain with in-kernel quantization followed by a long one on the same stream (same sync buffer): the short
+    chain's scratch must not land on the long chain's counters."""
+    wt = qo.Q8_0
+    K, F = 2048, 320
+    x, w = datagen.model_like(1, F, K, seed=8)
+    wq = O.quantize_weight(wt, w * (50.0 / np.sqrt(K)))
+    dw, dx = dev(wq), dev(x.reshape(-1))
+    ref = O.gemm(wt, O.quantize_q8_1(x), wq, layout="FT")
+    long_n = 100
+    for n in (long_n, 2, long_n, 3, long_n):     # the long one first, so that the shared buffer has its size from the start
+        res = qg.gemv_chain([{"weights": [dw], "Ms": [F], "K": K, "act": dx} for _ in range(n)], wt)
+        assert qg.last_path() & qg.PATH_CHAINED
+        for outs in (res[0], res[-1]):
+            check_c(host(outs[0]), ref, f"chain of {n}")
 
 
 def test_chain_fallbacks_give_the_same_results(qg, O):
