@@ -572,11 +572,10 @@ static int gemm_f32act_impl(int wtype, const float* act_f32, const float* gate, 
 
 int qgemm_gemm_f16act(int wtype, const void* act_f16, const void* weight, float* C, int T, int F, int K, int64_t ldc_t,
                       int64_t ldc_f, uint32_t flags, void* workspace, size_t workspace_bytes, void* stream) {
-    if (int rc = check_gemm_args(wtype, act_f16, weight, C, T, F, K)) {
-        // check_gemm_args asks 4-byte alignment of the activations (q8_1 / fp32); halves need 2
-        if (!(rc == QGEMM_E_ALIGN && act_f16 && aligned(act_f16, 2) && aligned(weight, 2) && aligned(C, 4))) return rc;
-    }
+    if (!is_weight_type(wtype) || T < 0 || F < 0 || K < 0 || (K % kQK) != 0) return QGEMM_E_BADARG;
     if (T == 0 || F == 0) return QGEMM_OK;
+    if (!act_f16 || !weight || !C) return QGEMM_E_BADARG;
+    if (!aligned(act_f16, 2) || !aligned(weight, 2) || !aligned(C, 4)) return QGEMM_E_ALIGN;   // halves: 2-byte alignment
     DeviceInfo dev;
     if (int rc = device_check(&dev)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
