@@ -390,9 +390,18 @@ def main():
             quant_gemm.hint_next_weights(w, min(args.prefetch_mb << 20, arena_end - w.data_ptr()))
         else:
             quant_gemm.hint_next_weights(w)
-    acts_host = {K: torch.randn((1, K), generator=torch.Generator().manual_seed(7 + K)).pin_memory() for K in (4096, 11008)}
-    acts_dev = {K: v.to(dev) for K, v in acts_host.items()}
-    acts_q = {K: quant_gemm.quantize_q8_1(v) for K, v in acts_dev.items()}
+    # the step's two activation vectors (K = 4096 and K = 11008) live back to back in one pinned host buffer, one device
+    # buffer and one q8_1 buffer: one host->device copy and one quantize_q8_1 launch per step, views per K
+    KS = (4096, 11008)
+    acts_host_all = torch.cat([torch.randn((1, K), generator=torch.Generator().manual_seed(7 + K)) for K in KS], dim=1).pin_memory()
+    acts_dev_all = acts_host_all.to(dev)
+    acts_q_all = quant_gemm.quantize_q8_1(acts_dev_all)            # [1, sum(K)/32, 36]
+    acts_host, acts_dev, acts_q, k0 = {}, {}, {}, 0
+    for K in KS:
+        acts_host[K] = acts_host_all[:, k0:k0 + K]
+        acts_dev[K] = acts_dev_all[:, k0:k0 + K]
+        acts_q[K] = acts_q_all[:, k0 // 32:(k0 + K) // 32]            # block boundaries: same bytes as quantizing each vector alone
+        k0 += K
     # gathered C of every GEMV, [F_total, T=1] each, carved out of one buffer so the step's result
     # goes back to the host in one copy
     total_out = sum(F * tp for F, K, _ in mats)
@@ -505,9 +514,8 @@ def main():
             plan.end_step()
 
     def e2e_step():
-        for K in acts_host:
-            acts_dev[K].copy_(acts_host[K], non_blocking=True)
-            quant_gemm.quantize_q8_1(acts_dev[K], out=acts_q[K])   # the decode runtime's fixed activation buffers
+        acts_dev_all.copy_(acts_host_all, non_blocking=True)
+        quant_gemm.quantize_q8_1(acts_dev_all, out=acts_q_all)     # the decode runtime's fixed activation buffers
         if groups and not chains and plan is None and args.d2h_chunk_layers > 0:
             # the step's results go back to the host as they are produced: every few layers a side stream copies the finished
             # slice of the output buffer while the next layers compute (same bytes, same pinned destination); the step ends
