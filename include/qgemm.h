@@ -284,6 +284,13 @@ QGEMM_API int qgemm_gemv_chain(int wtype, const qgemm_chain_step *steps, int nst
  * on results, ignored by the other paths.  (NULL, 0) clears it.
  */
 QGEMM_API int qgemm_hint_next_weights(const void *next_weights, size_t bytes);
+/* The same hint as explicit arguments of the call it applies to: no state is kept between calls. */
+QGEMM_API int qgemm_gemm_hinted(int wtype, const void *act_q8_1, const void *weight, float *C, int T, int F, int K,
+                                int64_t ldc_t, int64_t ldc_f, uint32_t flags, void *workspace, size_t workspace_bytes,
+                                void *stream, const void *next_weights, size_t next_bytes);
+QGEMM_API int qgemm_gemm_group_hinted(int wtype, const void *act_q8_1, int nmat, const void *const *weights,
+                                      float *const *Cs, const int *Fs, int T, int K, int64_t ldc_t, int64_t ldc_f,
+                                      uint32_t flags, void *stream, const void *next_weights, size_t next_bytes);
 
 /*
  * Same, with fp32 activations act_f32[T][K]: quantize_q8_1 (flags' QGEMM_Q81_*

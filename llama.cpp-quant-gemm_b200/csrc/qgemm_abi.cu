@@ -570,6 +570,26 @@ static int gemm_f32act_impl(int wtype, const float* act_f32, const float* gate, 
                     workspace_bytes - a_q, st, dev);
 }
 
+// Explicit-argument forms of the L2 hint: nothing outlives the call (the one-shot qgemm_hint_next_weights() keeps the hint in
+// thread-local state between two calls).
+int qgemm_gemm_hinted(int wtype, const void* act_q8_1, const void* weight, float* C, int T, int F, int K, int64_t ldc_t,
+                      int64_t ldc_f, uint32_t flags, void* workspace, size_t workspace_bytes, void* stream,
+                      const void* next_weights, size_t next_bytes) {
+    qgemm_hint_next_weights(next_weights, next_bytes);
+    const int rc = qgemm_gemm(wtype, act_q8_1, weight, C, T, F, K, ldc_t, ldc_f, flags, workspace, workspace_bytes, stream);
+    qgemm_hint_next_weights(nullptr, 0);   // a path that does not take hints (or an error) must not leave it for a later call
+    return rc;
+}
+
+int qgemm_gemm_group_hinted(int wtype, const void* act_q8_1, int nmat, const void* const* weights, float* const* Cs, const int* Fs,
+                            int T, int K, int64_t ldc_t, int64_t ldc_f, uint32_t flags, void* stream, const void* next_weights,
+                            size_t next_bytes) {
+    qgemm_hint_next_weights(next_weights, next_bytes);
+    const int rc = qgemm_gemm_group(wtype, act_q8_1, nmat, weights, Cs, Fs, T, K, ldc_t, ldc_f, flags, stream);
+    qgemm_hint_next_weights(nullptr, 0);
+    return rc;
+}
+
 int qgemm_gemm_f16act(int wtype, const void* act_f16, const void* weight, float* C, int T, int F, int K, int64_t ldc_t,
                       int64_t ldc_f, uint32_t flags, void* workspace, size_t workspace_bytes, void* stream) {
     if (!is_weight_type(wtype) || T < 0 || F < 0 || K < 0 || (K % kQK) != 0) return QGEMM_E_BADARG;

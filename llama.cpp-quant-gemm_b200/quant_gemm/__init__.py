@@ -210,7 +210,8 @@ def hint_next_weights(next_weight_q: torch.Tensor | None, nbytes: int | None = N
 
 
 def gemm(weight_q: torch.Tensor, activation_q: torch.Tensor, M: int, N: int, K: int, wtype: int,
-         flags: int = 0, out: torch.Tensor | None = None) -> torch.Tensor:
+         flags: int = 0, out: torch.Tensor | None = None, next_weight_q: torch.Tensor | None = None,
+         next_nbytes: int | None = None) -> torch.Tensor:
     """C[M,N] = W[M,K] @ A[N,K]^T, M = weight rows, N = tokens (ggml convention).
 
     Checks mirror bindings.cpp:49-70.
@@ -240,9 +241,15 @@ def gemm(weight_q: torch.Tensor, activation_q: torch.Tensor, M: int, N: int, K: 
     with torch.cuda.device(weight_q.device):
         ws_bytes = L.qgemm_workspace_bytes(wtype, N, M, K, flags)
         ws = _workspace(weight_q.device, ws_bytes)
-        rc = L.qgemm_gemm(wtype, activation_q.data_ptr(), weight_q.data_ptr(), out.data_ptr(), N, M, K,
-                          1, N, flags, ws.data_ptr() if ws is not None else None,
-                          ws.numel() if ws is not None else 0, _stream(weight_q))
+        if next_weight_q is not None:   # the L2 hint as an argument of this call (qgemm_gemm_hinted): no state between calls
+            nbytes = next_weight_q.numel() * next_weight_q.element_size() if next_nbytes is None else int(next_nbytes)
+            rc = L.qgemm_gemm_hinted(wtype, activation_q.data_ptr(), weight_q.data_ptr(), out.data_ptr(), N, M, K,
+                                     1, N, flags, ws.data_ptr() if ws is not None else None,
+                                     ws.numel() if ws is not None else 0, _stream(weight_q), next_weight_q.data_ptr(), nbytes)
+        else:
+            rc = L.qgemm_gemm(wtype, activation_q.data_ptr(), weight_q.data_ptr(), out.data_ptr(), N, M, K,
+                              1, N, flags, ws.data_ptr() if ws is not None else None,
+                              ws.numel() if ws is not None else 0, _stream(weight_q))
     _lib.raise_on_error(rc, "gemm")
     return out
 

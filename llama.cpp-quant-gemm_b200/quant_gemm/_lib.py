@@ -37,6 +37,8 @@ SYMBOLS = {
     "qgemm_prepack_bytes": (_sz, [_i, _i, _i]),
     "qgemm_prepack_weights": (_i, [_i, _p, _i, _i, _p, _p]),
     "qgemm_gemm_group": (_i, [_i, _p, _i, C.POINTER(_p), C.POINTER(_p), C.POINTER(_i), _i, _i, _i64, _i64, _u32, _p]),
+    "qgemm_gemm_hinted": (_i, [_i, _p, _p, _p, _i, _i, _i, _i64, _i64, _u32, _p, _sz, _p, _p, _sz]),
+    "qgemm_gemm_group_hinted": (_i, [_i, _p, _i, C.POINTER(_p), C.POINTER(_p), C.POINTER(_i), _i, _i, _i64, _i64, _u32, _p, _p, _sz]),
     "qgemm_workspace_bytes": (_sz, [_i, _i, _i, _i, _u32]),
     "qgemm_gemm": (_i, [_i, _p, _p, _p, _i, _i, _i, _i64, _i64, _u32, _p, _sz, _p]),
     "qgemm_gemm_f16act": (_i, [_i, _p, _p, _p, _i, _i, _i, _i64, _i64, _u32, _p, _sz, _p]),

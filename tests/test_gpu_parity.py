@@ -888,6 +888,9 @@ def test_gemm_group_equals_separate_calls(qg, O, wt, T, K):
         check_c(c, O.gemm(wt, aq, wq, layout="FT"), "group vs oracle")
         sep = host(qg.gemm(dw, da, F, T, K, wt, flags=0x200))
         assert (bits(c) == bits(sep)).all()
+    # the L2 hint as an argument of the call: same numbers (it is a pure performance hint), and nothing is left behind
+    hinted = qg.gemm(dws[0], da, Fs[0], T, K, wt, flags=0x200, next_weight_q=dws[1])
+    assert (bits(host(hinted)) == bits(host(qg.gemm(dws[0], da, Fs[0], T, K, wt, flags=0x200)))).all()
     # a group of one matrix is a plain GEMV
     one = qg.gemm_group(dws[:1], da, Fs[:1], T, K, wt)
     assert (bits(host(one[0])) == bits(host(qg.gemm(dws[0], da, Fs[0], T, K, wt, flags=0x200)))).all()
