@@ -654,10 +654,11 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u4 x s8 -> s32 (dp4a), fp32 fold", "data": "synthetic",
-        "config": dict(workload_config(world, tp), launch_form=(
+        "config": workload_config(world, tp),     # the same object the reference arm prints
+        "launch_form": (
             f"{len(chains)} persistent chained launches per step ({args.chain} layer(s) = {4 * args.chain} grouped projections each, "
             "qgemm_gemv_chain); every projection waits for its predecessor to complete on the whole device" if chains else
-            f"{launches_per_step} launches per step, one per (grouped) projection")),
+            f"{launches_per_step} launches per step, one per (grouped) projection"),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT,
                 "h2d_bytes_per_step": sum(v.numel() * 4 for v in acts_host.values()),
