@@ -122,6 +122,26 @@ def test_chain_argument_validation_without_gpu(lib):
         assert lib.qgemm_gemv_chain(2, arr, 2, 0, sync, need, None) in (-3, -4)   # no device: fails loudly, computes nothing
 
 
+def test_new_entries_validate_before_any_cuda_call(lib):
+    """fp16-activation entries and the explicit-hint forms: argument errors are reported with or without a device."""
+    BAD, ALIGN = -1, -2
+    p = C.c_void_p(0x1000)
+    odd = C.c_void_p(0x1001)
+    assert lib.qgemm_quantize_q8_1_f16(p, p, 1, 33, 0, None) == BAD            # K % 32
+    assert lib.qgemm_quantize_q8_1_f16(None, p, 1, 32, 0, None) == BAD
+    assert lib.qgemm_quantize_q8_1_f16(odd, p, 1, 32, 0, None) == ALIGN        # halves: 2-byte alignment
+    assert lib.qgemm_quantize_q8_1_f16(C.c_void_p(0x1002), p, 0, 32, 0, None) == 0   # empty: no-op
+    assert lib.qgemm_gemm_f16act(2, p, p, p, 1, 1, 31, 1, 1, 0, None, 0, None) == BAD
+    assert lib.qgemm_gemm_f16act(4, p, p, p, 1, 1, 32, 1, 1, 0, None, 0, None) == BAD
+    assert lib.qgemm_gemm_f16act(2, odd, p, p, 1, 1, 32, 1, 1, 0, None, 0, None) == ALIGN
+    assert lib.qgemm_gemm_f16act(2, C.c_void_p(0x1002), p, p, 0, 5, 32, 1, 1, 0, None, 0, None) == 0   # 2-byte aligned halves are fine
+    assert lib.qgemm_gemm_hinted(2, p, p, p, 1, 1, 31, 1, 1, 0, None, 0, None, p, 64) == BAD
+    assert lib.qgemm_gemm_hinted(2, p, p, p, 0, 5, 32, 1, 1, 0, None, 0, None, p, 64) == 0
+    wp, cp, fs = (C.c_void_p * 1)(0x2000), (C.c_void_p * 1)(0x3000), (C.c_int * 1)(8)
+    assert lib.qgemm_gemm_group_hinted(2, p, 0, wp, cp, fs, 1, 32, 1, 1, 0, None, p, 64) == BAD   # nmat = 0
+    assert lib.qgemm_gemm_group_hinted(2, p, 1, wp, cp, fs, 1, 31, 1, 1, 0, None, p, 64) == BAD
+
+
 def test_no_cpu_fallback(lib):
     """Without a B200 the compute entries must fail loudly, never compute on the host."""
     import torch
