@@ -652,7 +652,10 @@ cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, i
 // launch, the kernel boundary, an empty weight ring and the activation prologue (profiles/r02_decode_timeline.md:
 // ~2.3 us on top of a 4.7 us stream); here the producer warp never stops -- while the consumers of a CTA sit in
 // the barrier between two steps and fetch the next step's activations, the ring fills with the next step's
-// weights -- so the boundary costs the consumers' catch-up instead of an idle HBM.
+// weights -- the intent being that a boundary costs the consumers' catch-up instead of an idle HBM.  Measured
+// (profiles/r02_chain.md): a boundary inside the kernel (fence + device-wide barrier + activation fetch) costs more than a
+// programmatic launch boundary and the consumers have no speed in reserve to catch up with, so this form is SLOWER than one
+// launch per projection and is not what AUTO or bench.py use; it is API surface (one launch per layer, in-kernel quantization).
 //   * same consumer code as gemv_kernel (one token, activations in registers), instantiated per (PPL, kFull)
 //     and selected per step: the steps of a chain may differ in K and F
 //   * a step that waits (QGEMM_INPUTS_READY not set) starts only after every CTA has finished every earlier
@@ -660,8 +663,9 @@ cudaError_t launch_gemv(int wtype, const void* act, const void* wgt, float* C, i
 //     spin by one thread).  All CTAs are co-resident (the host clamps the grid to the occupancy).
 //   * a step's activations are either ready-made q8_1 blocks (one bulk copy per CTA) or quantized inside the kernel from
 //     an fp32 vector -- typically the output of an earlier step of the same chain, optionally through SwiGLU
-//     (silu(x) * gate) -- with quantize_q8_1's arithmetic (include/quantize.h:165-193, default flags), every CTA
-//     for itself: the quantize launch between two projections disappears
+//     (silu(x) * gate) -- with quantize_q8_1's arithmetic (include/quantize.h:165-193, default flags): the CTAs quantize
+//     the vector together (one warp per block, scratch in `sync`, a second device-wide barrier) and every CTA copies the
+//     result; the quantize launch between two projections disappears
 //   * counters return to zero: the last CTA to leave clears them
 // ===========================================================================================================
 constexpr int kChainMaxSteps = 160;
